@@ -1,0 +1,96 @@
+/*
+ * ballbox_ext.h -- extensions of the B200-native library that the reference
+ * does not have.  Nothing here changes the meaning of the reference API in
+ * ballbox.h; a program that never calls these gets the drop-in behaviour
+ * (BBX_SYNC_COMPAT: host arrays are uploaded before and downloaded after every
+ * PhysicsStep, exactly as if the step had run on the host).
+ */
+#ifndef BALLBOX_EXT_H
+#define BALLBOX_EXT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- residency ------------------------------------------------------------ */
+#define BBX_SYNC_COMPAT    0   /* default: upload / step / download in every PhysicsStep   */
+#define BBX_SYNC_RESIDENT  1   /* state stays in HBM; host arrays move only on request     */
+
+#define BBX_DL_BODIES       1  /* positions, rotations, velocities, sleep state            */
+#define BBX_DL_CONSTRAINTS  2  /* world->constraints in the reference's emission order     */
+
+void BallboxSetSyncMode(PhysicsWorld* world, int mode);
+int  BallboxUpload(PhysicsWorld* world);               /* host arrays -> device; 0 = ok       */
+int  BallboxDownload(PhysicsWorld* world, int what);   /* device -> host arrays; 0 = ok       */
+int  PhysicsStepN(PhysicsWorld* world, float deltaTime, int steps);  /* resident stepping     */
+int  BallboxSynchronize(PhysicsWorld* world);          /* wait for queued device work         */
+
+/* ---- device selection; `stream` is a cudaStream_t passed as void* ---------- */
+int  BallboxSetDevice(PhysicsWorld* world, int device);
+void BallboxSetStream(PhysicsWorld* world, void* stream);
+
+/* ---- error channel (the reference has none: a failed CUDA call or a buffer
+ * overflow makes PhysicsStep a no-op and leaves a sticky message here) ------- */
+const char* BallboxGetLastError(PhysicsWorld* world);  /* NULL when healthy */
+void        BallboxClearError(PhysicsWorld* world);
+
+/* ---- device SDF colliders.  A host function pointer cannot run on the GPU;
+ * UseSDF(world, fn) keeps the pointer (so user code still compiles) and the
+ * next PhysicsStep fails loudly unless one of these was selected as well. ---- */
+#define BBX_SDF_NONE        0
+#define BBX_SDF_PLANE_Y     1  /* f(p) = p.y - params[0]                                    */
+#define BBX_SDF_WAVY_DET    2  /* f(p) = p.y - S(p.x)*S(p.z), S = bbx_det_sin (bit-exact on
+                                  CPU and GPU; see bbx_sdf_library.h)                       */
+#define BBX_SDF_WAVY_LIBM   3  /* f(p) = p.y - sinf(p.x)*sinf(p.z) with CUDA sinf (README)  */
+#define BBX_SDF_SPHERE_IN   4  /* inside of a sphere: f(p) = params[0] - |p|                */
+void UseSDFDevice(PhysicsWorld* world, int sdf_id, const float* params8);
+
+/* ---- solver schedule ------------------------------------------------------- */
+#define BBX_SOLVER_EXACT     0 /* level-scheduled Gauss-Seidel: bit-identical to the
+                                  reference's sequential sweep (default)                    */
+#define BBX_SOLVER_COLOURED  1 /* graph-coloured Gauss-Seidel: reorders the sweep          */
+void BallboxSetSolverSchedule(PhysicsWorld* world, int schedule);
+
+/* ---- statistics of the most recent step (and totals since creation) -------- */
+typedef struct {
+    long long steps;               /* device steps executed                                 */
+    long long body_steps;          /* sum over steps of (spheres + boxes)                   */
+    long long kernel_launches;     /* CUDA kernels launched by this library                 */
+    int  spheres, boxes;           /* bodies on the device                                  */
+    int  candidate_pairs;          /* broadphase output of the last step (SS+SB+BB)         */
+    int  contacts;                 /* contacts of the last step                             */
+    int  solver_contacts;          /* contacts touching >= 1 dynamic body                   */
+    int  touched_bodies;           /* dynamic bodies with >= 1 contact                      */
+    int  levels;                   /* dependency levels (exact) or colours (coloured)       */
+    int  overflow;                 /* bit0 pairs, bit1 contacts, bit2 grid, bit3 callbacks  */
+    int  grid_cells;
+    int  reserved[5];
+} BallboxStats;
+int BallboxGetStats(PhysicsWorld* world, BallboxStats* out);
+
+/* ---- batches of independent worlds (RL style).  All worlds of a batch share
+ * one device context and are stepped by the same kernels; worlds never
+ * interact.  Settings, gravity and SDF are taken from world 0. --------------- */
+typedef struct PhysicsWorldBatch PhysicsWorldBatch;
+PhysicsWorldBatch* CreatePhysicsWorldBatch(int n_worlds, int max_spheres, int max_boxes,
+                                           int max_collisions);
+void          DestroyPhysicsWorldBatch(PhysicsWorldBatch* batch);
+int           BatchWorldCount(PhysicsWorldBatch* batch);
+PhysicsWorld* BatchWorld(PhysicsWorldBatch* batch, int index);
+int  BatchSetDevice(PhysicsWorldBatch* batch, int device);
+void BatchSetStream(PhysicsWorldBatch* batch, void* stream);
+int  BatchUpload(PhysicsWorldBatch* batch);
+int  BatchDownload(PhysicsWorldBatch* batch, int what);
+int  PhysicsStepBatch(PhysicsWorldBatch* batch, float deltaTime, int steps);
+int  BatchSynchronize(PhysicsWorldBatch* batch);
+int  BatchGetStats(PhysicsWorldBatch* batch, BallboxStats* out);
+const char* BatchGetLastError(PhysicsWorldBatch* batch);
+
+/* ---- library identity ------------------------------------------------------ */
+const char* BallboxBackendName(void);   /* "ballbox-b200/cuda-sm_100a" */
+int         BallboxDeviceCount(void);   /* 0 when no CUDA device is visible */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BALLBOX_EXT_H */
