@@ -1,0 +1,334 @@
+// bbx_broadphase.cu -- uniform-grid broadphase (K2-K5).
+//
+// The reference has NO broadphase: CollectCollisions runs three all-pairs loops
+// (ballbox.h:1986-1987, :2011-2012, :2050-2051).  This file replaces the loop
+// bounds with a grid: bodies are binned by a one-pass radix (counting) sort on
+// their cell key, every small body scans a half stencil of 14 cells, and bodies
+// too large for the grid (static walls, ground) are tested against every body of
+// their world.  A pair survives when the bounding spheres touch, which is
+// necessary for each narrowphase hit condition, so the
+// set of contacts is exactly the reference's.  Sphere-sphere pairs are resolved
+// here (the test is 20 flops); sphere-box and box-box pairs are compacted into
+// candidate lists for the narrowphase kernels.
+#include "bbx_dev.cuh"
+
+// ---------------------------------------------------------------------------
+// exclusive scan of ints: three small kernels (tile reduce, spine, apply)
+// ---------------------------------------------------------------------------
+#define SCAN_TILE 2048           // 256 threads x 8 items
+
+__global__ void __launch_bounds__(256) k_scan_reduce(const int* in, int* tile_sums, int n_max, const int* n_dev)
+{
+    int n = n_dev ? min(*n_dev, n_max) : n_max;
+    int base = blockIdx.x * SCAN_TILE;
+    if (base >= n) { if (threadIdx.x == 0) tile_sums[blockIdx.x] = 0; return; }
+    int s = 0;
+    for (int k = 0; k < 8; k++) { int i = base + k * 256 + threadIdx.x; if (i < n) s += in[i]; }
+    __shared__ int ws[8];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; k++) t += ws[k]; tile_sums[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_spine(int* tile_sums, int n_tiles, int* total_out)
+{
+    __shared__ int ws[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = (i < n_tiles) ? tile_sums[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = ws[threadIdx.x], z = w;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, z, o); if (threadIdx.x >= o) z += y; }
+            ws[threadIdx.x] = z - w;
+        }
+        __syncthreads();
+        int excl = carry + ws[threadIdx.x >> 5] + x - v;
+        if (i < n_tiles) tile_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const int* in, int* out, int* out2, const int* tile_sums, int n_max, const int* n_dev)
+{
+    int n = n_dev ? min(*n_dev, n_max) : n_max;
+    int base = blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    // each thread owns 8 consecutive items
+    int i0 = base + threadIdx.x * 8;
+    int v[8]; int s = 0;
+    for (int k = 0; k < 8; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+    __shared__ int ws[8];
+    int x = s;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < (threadIdx.x >> 5); k++) woff += ws[k];
+    int run = tile_sums[blockIdx.x] + woff + x - s;
+    for (int k = 0; k < 8; k++) {
+        if (i0 + k < n) { out[i0 + k] = run; if (out2) out2[i0 + k] = run; }
+        run += v[k];
+    }
+}
+
+// out[i] = sum(in[0..i)); n = min(*n_dev, n_max) when n_dev != NULL.  total_out
+// (device pointer, optional) receives the grand total.
+int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out)
+{
+    int tiles = (n_max + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles < 1) tiles = 1;
+    if (tiles > (1 << 16)) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "scan too large", __FILE__, __LINE__);
+    BBX_LAUNCH(d, k_scan_reduce, tiles, 256, 0, in, d->scan_tmp, n_max, n_dev);
+    BBX_LAUNCH(d, k_scan_spine, 1, 1024, 0, d->scan_tmp, tiles, total_out);
+    BBX_LAUNCH(d, k_scan_apply, tiles, 256, 0, in, out, out2, d->scan_tmp, n_max, n_dev);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// bounds of the small bodies + per-step counter reset
+// ---------------------------------------------------------------------------
+__global__ void k_step_reset(BbxDev dv)
+{
+    StepCounters* c = dv.ctr;
+    c->n_sorted = 0; c->n_cand_sb = 0; c->n_cand_bb = 0; c->n_contacts = 0; c->n_solver = 0; c->n_touched = 0;
+    c->n_levels = 0; c->n_ss_tests = 0; c->n_frontier0 = 0; c->n_events = 0;
+    c->bounds[0] = c->bounds[1] = c->bounds[2] = 0xffffffffu;
+    c->bounds[3] = c->bounds[4] = c->bounds[5] = 0u;
+}
+
+__global__ void __launch_bounds__(256) k_bounds(BbxDev dv)
+{
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dv.N; i += gridDim.x * blockDim.x) {
+        unsigned char f = dv.flags[i];
+        if (!(f & BF_VALID) || (f & BF_BIG)) continue;
+        float4 p = dv.pos[i];
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+    for (int k = 0; k < 3; k++) {
+        for (int o = 16; o; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 3; k++) {
+            if (lo[k] < 3.0e38f) atomicMin(&dv.ctr->bounds[k], f2ord(lo[k]));
+            if (hi[k] > -3.0e38f) atomicMax(&dv.ctr->bounds[3 + k], f2ord(hi[k]));
+        }
+    }
+}
+
+// one thread: choose the cell size and the grid dimensions for this step
+__global__ void k_grid_setup(BbxDev dv)
+{
+    GridParams* g = dv.grid;
+    StepCounters* c = dv.ctr;
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) { lo[k] = ord2f(c->bounds[k]); hi[k] = ord2f(c->bounds[3 + k]); }
+    if (c->bounds[0] == 0xffffffffu || !(hi[0] >= lo[0]) || !(hi[1] >= lo[1]) || !(hi[2] >= lo[2])) {
+        lo[0] = lo[1] = lo[2] = 0.0f; hi[0] = hi[1] = hi[2] = 1.0f;       // no small bodies (or NaNs)
+    }
+    // clamp absurd extents (a body that flew away): bodies outside are binned into border cells
+    for (int k = 0; k < 3; k++) { lo[k] = fmaxf(lo[k], -1.0e18f); hi[k] = fminf(hi[k], 1.0e18f); }
+    float cell = 2.0f * g->small_cut * 1.01f + 1e-4f;      // 1% slack: cell-coordinate rounding can never split a touching pair by 2 cells
+    long long budget = dv.cap_cells / dv.n_worlds;
+    int nx, ny, nz;
+    for (int it = 0; it < 200; it++) {
+        float ex = (hi[0] - lo[0]) / cell, ey = (hi[1] - lo[1]) / cell, ez = (hi[2] - lo[2]) / cell;
+        if (ex < 30000.0f && ey < 30000.0f && ez < 30000.0f) {
+            nx = (int)ex + 2; ny = (int)ey + 2; nz = (int)ez + 2;
+            if ((long long)nx * ny * nz <= budget) break;
+        }
+        cell *= 1.25f;
+        nx = ny = nz = 1;
+    }
+    if ((long long)nx * ny * nz > budget) { nx = ny = nz = 1; g->overflow = 1; }
+    g->cell = cell; g->inv_cell = 1.0f / cell;
+    g->ox = lo[0] - 0.5f * cell; g->oy = lo[1] - 0.5f * cell; g->oz = lo[2] - 0.5f * cell;
+    g->nx = nx; g->ny = ny; g->nz = nz;
+    g->cells_per_world = nx * ny * nz;
+    g->n_cells = g->cells_per_world * dv.n_worlds;
+}
+
+__device__ __forceinline__ int cell_coord(float p, float o, float inv, int n)
+{
+    float f = floorf((p - o) * inv);
+    // NaN and out-of-range positions land in a border cell (still conservative: see DESIGN.md)
+    int c = (f >= 0.0f) ? ((f < (float)n) ? (int)f : n - 1) : 0;
+    return c;
+}
+
+__device__ __forceinline__ int world_of(const BbxDev& dv, int g)
+{
+    return (g < dv.NS) ? g / max(dv.cap_s, 1) : (g - dv.NS) / max(dv.cap_b, 1);
+}
+
+__global__ void __launch_bounds__(256) k_cell_count(BbxDev dv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dv.N) return;
+    unsigned char f = dv.flags[i];
+    if (!(f & BF_VALID) || (f & BF_BIG)) { dv.body_cell[i] = -1; return; }
+    const GridParams g = *dv.grid;
+    float4 p = dv.pos[i];
+    int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
+    int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
+    int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+    int c = world_of(dv, i) * g.cells_per_world + (cz * g.ny + cy) * g.nx + cx;
+    dv.body_cell[i] = c;
+    atomicAdd(&dv.cell_count[c], 1);
+}
+
+__global__ void __launch_bounds__(256) k_cell_scatter(BbxDev dv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dv.N) return;
+    int c = dv.body_cell[i];
+    if (c < 0) return;
+    int slot = atomicAdd(&dv.cell_cursor[c], 1);
+    dv.sorted_id[slot] = i;
+    dv.sorted_pos[slot] = dv.pos[i];
+}
+
+// ---------------------------------------------------------------------------
+// pair finding.  One thread per grid slot (cell order, so a warp's bodies are
+// spatial neighbours and share most of their stencil in L1/L2).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void emit_ss_contact(const BbxDev& dv, int a, float4 pa, int b, float4 pb)
+{
+    // CheckSphereCollisionWithData, ballbox.h:451-471, with A = lower index
+    float3 n = v3sub(xyz(pb), xyz(pa));
+    float dist = v3len(n);
+    float rs = pa.w + pb.w;
+    bool hit = dist < rs;
+    int slot = warp_append(&dv.ctr->n_contacts, hit);
+    if (!hit) return;
+    if (slot >= dv.cap_contacts) { atomicOr(&dv.ctr->overflow, 2); return; }
+    float3 nrm = (dist > 1e-6f) ? v3scale(n, 1.0f / dist) : f3(1.0f, 0.0f, 0.0f);
+    float3 pt = v3add(xyz(pa), v3scale(nrm, pa.w));
+    dv.c_ids[slot] = make_int4(a, b, 0, PH_SS);
+    dv.c_pt[slot] = make_float4(pt.x, pt.y, pt.z, rs - dist);
+    dv.c_nrm[slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.0f);
+}
+
+__device__ __forceinline__ bool bounds_touch(float4 a, float4 b)
+{
+    float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+    float d2 = dx * dx + dy * dy + dz * dz, rs = a.w + b.w;
+    return d2 <= rs * rs * 1.001f + 1e-5f;
+}
+
+// classify one geometric neighbour pair (i, j) and route it
+__device__ __forceinline__ void route_pair(const BbxDev& dv, int i, float4 pi, int j, float4 pj)
+{
+    bool ib = i >= dv.NS, jb = j >= dv.NS;
+    if (!ib && !jb) {
+        if (i < j) emit_ss_contact(dv, i, pi, j, pj); else emit_ss_contact(dv, j, pj, i, pi);
+        return;
+    }
+    bool touch = bounds_touch(pi, pj);
+    if (ib && jb) {
+        int slot = warp_append(&dv.ctr->n_cand_bb, touch);
+        if (!touch) return;
+        if (slot >= dv.cap_cand) { atomicOr(&dv.ctr->overflow, 1); return; }
+        dv.cand_bb[slot] = (i < j) ? make_int2(i, j) : make_int2(j, i);
+    } else {
+        int slot = warp_append(&dv.ctr->n_cand_sb, touch);
+        if (!touch) return;
+        if (slot >= dv.cap_cand) { atomicOr(&dv.ctr->overflow, 1); return; }
+        dv.cand_sb[slot] = ib ? make_int2(j, i) : make_int2(i, j);       // (sphere, box)
+    }
+}
+
+__global__ void __launch_bounds__(128) k_find_pairs(BbxDev dv)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_sorted = dv.cell_start[dv.grid->n_cells];
+    if (p >= n_sorted) return;
+    const GridParams g = *dv.grid;
+    int i = dv.sorted_id[p];
+    float4 pi = dv.sorted_pos[p];
+    int c = dv.body_cell[i];
+    int w = c / g.cells_per_world;
+    int lc = c - w * g.cells_per_world;
+    int cx = lc % g.nx, cy = (lc / g.nx) % g.ny, cz = lc / (g.nx * g.ny);
+    int wbase = w * g.cells_per_world;
+
+    // own cell: partners later in the sorted order
+    {
+        int e = dv.cell_start[c + 1];
+        for (int q = p + 1; q < e; q++) route_pair(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q]);
+    }
+    // 13 forward neighbours: (dz,dy,dx) > (0,0,0) lexicographically
+    for (int dz = 0; dz <= 1; dz++) {
+        int z = cz + dz;
+        if (z >= g.nz) continue;
+        for (int dy = (dz ? -1 : 0); dy <= 1; dy++) {
+            int y = cy + dy;
+            if (y < 0 || y >= g.ny) continue;
+            int x0 = (dz == 0 && dy == 0) ? cx + 1 : cx - 1;
+            int x1 = cx + 1;
+            if (x0 < 0) x0 = 0;
+            if (x1 >= g.nx) x1 = g.nx - 1;
+            if (x0 > x1) continue;
+            int row = wbase + (z * g.ny + y) * g.nx;
+            int s = dv.cell_start[row + x0], e = dv.cell_start[row + x1 + 1];   // consecutive cells: one run
+            for (int q = s; q < e; q++) route_pair(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q]);
+        }
+    }
+    // big bodies of this world
+    int bs = dv.big_start[w], be = dv.big_start[w + 1];
+    for (int k = bs; k < be; k++) {
+        int j = dv.big_list[k];
+        route_pair(dv, i, pi, j, dv.pos[j]);
+    }
+}
+
+// big-big pairs inside each world (few bodies: one thread per big body)
+__global__ void k_find_pairs_big(BbxDev dv)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int nbig = dv.big_start[dv.n_worlds];
+    if (k >= nbig) return;
+    int i = dv.big_list[k];
+    int w = world_of(dv, i);
+    float4 pi = dv.pos[i];
+    for (int m = dv.big_start[w]; m < dv.big_start[w + 1]; m++) {
+        int j = dv.big_list[m];
+        if (j <= i) continue;
+        route_pair(dv, i, pi, j, dv.pos[j]);
+    }
+}
+
+int bbx_stage_broadphase(BbxDev* d, const BbxStepParams* p)
+{
+    (void)p;
+    int nb = bbx_blocks(d->N, 256);
+    BBX_LAUNCH(d, k_step_reset, 1, 1, 0, *d);
+    BBX_LAUNCH(d, k_bounds, BBX_NUM_SMS * 4, 256, 0, *d);
+    BBX_LAUNCH(d, k_grid_setup, 1, 1, 0, *d);
+    BBX_CUDA(d, cudaMemsetAsync(d->cell_count, 0, sizeof(int) * ((size_t)d->cap_cells + 1), d->stream));
+    BBX_LAUNCH(d, k_cell_count, nb, 256, 0, *d);
+    // n = n_cells + 1 so that cell_start[n_cells] is the number of binned bodies
+    int rc = bbx_scan_exclusive(d, d->cell_count, d->cell_start, d->cell_cursor, d->cap_cells + 1, NULL, NULL);
+    if (rc) return rc;
+    BBX_LAUNCH(d, k_cell_scatter, nb, 256, 0, *d);
+    BBX_LAUNCH(d, k_find_pairs, bbx_blocks(d->N, 128), 128, 0, *d);
+    BBX_LAUNCH(d, k_find_pairs_big, bbx_blocks(d->N, 128), 128, 0, *d);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,231 @@
+// bbx_dev.cuh -- device-side data layout and exact-arithmetic helpers shared by
+// the sm_100a kernels.
+//
+// ARITHMETIC CONTRACT.  Every kernel that produces physics results is compiled
+// with -fmad=false and uses only IEEE binary32 + - * / sqrtf in the operation
+// order of the reference (ballbox.h:501-639), so that results are bit-identical
+// to the reference built with gcc -ffp-contract=off.  Do not
+// "simplify" expressions in this directory: x + 0.0f, v * -1.0f and the
+// association of sums are deliberate.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bbx_cuda.h"
+#include "bbx_sdf_library.h"
+
+// ---------------------------------------------------------------------------
+// body flags (one byte per body slot)
+// ---------------------------------------------------------------------------
+#define BF_STATIC   1u
+#define BF_SLEEP    2u
+#define BF_VALID    4u
+#define BF_HASCB    8u
+#define BF_BIG     16u     // static body too large for the grid: tested against every body of its world
+
+// contact phases, in the reference's emission order (ballbox.h:1985-2114)
+#define PH_SS   0
+#define PH_BB   1
+#define PH_SB   2
+#define PH_SSDF 3
+#define PH_BSDF 4
+
+#define BBX_NUM_SMS 148
+
+struct GridParams {
+    float ox, oy, oz;        // origin of cell (0,0,0)
+    float cell, inv_cell;
+    int   nx, ny, nz;
+    int   cells_per_world;
+    int   n_cells;           // cells_per_world * n_worlds
+    float small_cut;         // largest bounding radius that goes into the grid
+    int   overflow;
+};
+
+// counters that live in device memory so that no stage needs a host round trip
+struct StepCounters {
+    int n_sorted;            // bodies placed in the grid
+    int n_cand_sb;           // sphere-box candidates
+    int n_cand_bb;           // box-box candidates
+    int n_contacts;          // contacts appended (all phases)
+    int n_solver;            // contacts with >= 1 dynamic body
+    int n_touched;           // dynamic bodies with >= 1 contact
+    int n_levels;
+    int overflow;            // bit0 pairs, bit1 contacts, bit2 grid, bit3 events
+    int n_ss_tests;
+    int n_frontier0;
+    int n_events;
+    int pad[5];
+    unsigned int bounds[6];  // ordered-int encoded min xyz / max xyz of small bodies
+    unsigned int cut_dyn;    // float bits: largest bounding radius among non-static bodies
+    unsigned int cut_all;    // float bits: largest bounding radius among all bodies
+    int n_big;
+    int pad2[5];
+};
+
+struct BbxDev {
+    int device;
+    cudaStream_t stream;
+    int n_worlds, cap_s, cap_b;          // per-world capacities
+    int NS, NB, N;                       // total slots: NS = n_worlds*cap_s, NB = n_worlds*cap_b
+    int cap_contacts_world;
+    int cap_contacts;                    // total contact capacity
+    int cap_cand;                        // capacity of each candidate list
+    int cap_cells;
+    int cap_levels;
+    int coop_blocks;                     // co-resident blocks for the solver
+    int n_big_host;
+
+    // raw mirrors of the host arrays (12-byte Vec3 stride), the unit of H2D/D2H
+    float *r_s_pos, *r_s_radius, *r_s_vel, *r_s_force, *r_s_mass, *r_s_angvel, *r_s_torque, *r_s_inertia, *r_s_timer;
+    unsigned char *r_s_static, *r_s_sleep, *r_s_hascb;
+    float *r_b_pos, *r_b_size, *r_b_rot, *r_b_vel, *r_b_force, *r_b_mass, *r_b_angvel, *r_b_torque, *r_b_inertia, *r_b_timer;
+    unsigned char *r_b_static, *r_b_sleep, *r_b_hascb;
+    int *d_s_count, *d_b_count;          // [n_worlds]
+
+    // packed working state, one float4 per body slot (spheres first, then boxes)
+    float4 *pos;        // xyz, w = bounding radius (sphere: its radius)
+    float4 *lin;        // linear velocity, w = 1/mass (0 when static)
+    float4 *ang;        // angular velocity, w = 1/inertia for spheres (0 when static)
+    float  *mass;       // N
+    float  *timer;      // N
+    unsigned char *flags;   // N
+    float4 *rot;        // NB box rotations
+    float4 *half;       // NB half extents, w unused
+    float4 *invI;       // NB 1/Ix 1/Iy 1/Iz (0 when static)
+
+    // grid
+    GridParams *grid;
+    int *cell_count, *cell_start, *cell_cursor;   // cap_cells (+1)
+    int *body_cell;                               // N
+    int *sorted_id;  float4 *sorted_pos;          // N
+    int *big_list;   int *big_start;              // N, n_worlds+1
+    int *scan_tmp;                                // block sums for scans
+
+    // candidates and contacts (unordered append buffers)
+    int2 *cand_sb, *cand_bb;
+    int4 *c_ids;        // a gid, b gid (-2 = SDF), k, phase
+    float4 *c_pt;       // contact point, w = penetration
+    float4 *c_nrm;      // contact normal A->B
+
+    // solver records in contact order (written by presolve)
+    float4 *L0, *L1, *L2, *L3;   // (n, bias) (rA, mN) (rB, mT0) (jn, jt0, jt1, mT1)
+    int2   *Lid;                 // dynamic gids (or -1)
+    int *deg, *adj_start, *adj_cursor;           // N (+1)
+    unsigned long long *adj;                     // 2*cap_contacts
+    int *next_a, *next_b, *indeg;                // cap_contacts
+    int *queue;                                  // cap_contacts: level-major order (contact ids)
+    int *slot_of;                                // cap_contacts: inverse of queue
+    int *level_count;                            // cap_levels+2
+    // level-major copies streamed by iterations >= 1
+    float4 *M0, *M1, *M2, *M3; int2 *Mid;
+
+    StepCounters *ctr;           // device
+    StepCounters *ctr_host;      // pinned host copy
+    unsigned long long *sort_keys;   // export: 64-bit reference-order keys
+    ContactConstraint *export_buf;   // export staging (device)
+
+    // bookkeeping
+    long long launches, steps, body_steps;
+    int n_valid_spheres, n_valid_boxes;
+    BbxStepParams last_params;
+    int have_params;
+    char *err;                   // 256-byte host buffer (kept out of the by-value kernel argument)
+    int has_err;
+};
+
+// ---------------------------------------------------------------------------
+// error handling / launch accounting
+// ---------------------------------------------------------------------------
+int  bbx_fail(BbxDev* d, int code, const char* what, const char* file, int line);
+#define BBX_CUDA(dev, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+        return bbx_fail((dev), (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define BBX_LAUNCH(dev, kernel, grid, block, smem, ...) do { \
+        kernel<<<(grid), (block), (smem), (dev)->stream>>>(__VA_ARGS__); (dev)->launches++; } while (0)
+
+static inline int bbx_blocks(long long n, int block) { long long b = (n + block - 1) / block; return (int)(b < 1 ? 1 : b); }
+
+// stage entry points (one translation unit each)
+int bbx_stage_pack(BbxDev* d);
+int bbx_stage_unpack(BbxDev* d);
+int bbx_stage_integrate_velocities(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_broadphase(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_narrowphase(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_solve(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_integrate_positions(BbxDev* d, const BbxStepParams* p);
+int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// exact vector math (reference ballbox.h:501-535)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 v3add(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 v3sub(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 v3scale(float3 v, float s) { return f3(v.x * s, v.y * s, v.z * s); }
+__device__ __forceinline__ float  v3dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 v3cross(float3 a, float3 b)
+{
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float  v3len(float3 v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
+__device__ __forceinline__ float3 v3norm(float3 v)
+{
+    float l = v3len(v);
+    if (l < 1e-6f) return f3(0.0f, 0.0f, 0.0f);
+    return v3scale(v, 1.0f / l);
+}
+__device__ __forceinline__ float3 v3mul(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+
+// glibc 2.39 fminf/fmaxf return the FIRST operand on ties (measured in this
+// image: fminf(+0,-0) = +0, fminf(-0,+0) = -0) and the non-NaN operand otherwise.
+__device__ __forceinline__ float bb_fminf(float x, float y) { return (x <= y || y != y) ? x : y; }
+__device__ __forceinline__ float bb_fmaxf(float x, float y) { return (x >= y || y != y) ? x : y; }
+
+// quaternion helpers (reference ballbox.h:543-562, :625-639)
+__device__ __forceinline__ float4 qconj(float4 q) { return make_float4(-q.x, -q.y, -q.z, q.w); }
+__device__ __forceinline__ float3 qrot(float4 q, float3 v)
+{
+    float3 u = f3(q.x, q.y, q.z);
+    float  s = q.w;
+    float3 a = v3scale(v, s * s - v3dot(u, u));
+    float3 b = v3scale(u, 2.0f * v3dot(u, v));
+    float3 c = v3scale(v3cross(u, v), 2.0f * s);
+    return v3add(v3add(a, b), c);
+}
+
+// order-preserving float <-> uint encoding for atomicMin/atomicMax
+__device__ __forceinline__ unsigned int f2ord(float f)
+{
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// bounding radius of a box whose rotation may be non-unit: QuatRotateVec3 scales
+// by |q|^2 (ballbox.h:630-639) and AddBox never normalises (ballbox.h:716).
+__device__ __forceinline__ float box_bound_radius(float3 half, float4 q)
+{
+    float q2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    if (!(q2 > 1.0f)) q2 = 1.0f;
+    return v3len(half) * q2 * 1.0005f + 1e-5f;
+}
+
+// warp-aggregated append: every calling lane with pred reserves one slot
+__device__ __forceinline__ int warp_append(int* counter, bool pred)
+{
+    unsigned int active = __activemask();
+    unsigned int mask = __ballot_sync(active, pred);
+    if (!pred) return -1;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+#endif // __CUDACC__

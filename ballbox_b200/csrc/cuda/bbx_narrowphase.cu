@@ -1,0 +1,450 @@
+// bbx_narrowphase.cu -- K6/K7: contact generation on the compacted candidate
+// lists and SDF probing.  Every function restates the reference's arithmetic in
+// the same operation order (see the ARITHMETIC CONTRACT in bbx_dev.cuh); the
+// quirks listed in SURVEY.md section 8a rows 5-9 are reproduced, not fixed.
+//
+//   sphere-box            CheckSphereBoxCollisionWithData   ballbox.h:1565-1626
+//   SAT + contact point   SATCollision                      ballbox.h:1040-1111
+//                         CheckBoxCollisionWithData         ballbox.h:1117-1132
+//   manifold              GenerateBoxBoxManifold            ballbox.h:2550-2724
+//                         SelectOptimalContactPoints        ballbox.h:2726-2843
+//   SDF                   sphere block :2074-2106, SDF_EstimateNormal :2318-2331,
+//                         GenerateBoxSDFContacts :2413-2477
+#include "bbx_dev.cuh"
+
+// full-warp reservation of n slots per lane (n may be 0); all 32 lanes must call
+__device__ __forceinline__ int warp_reserve(int* counter, int n)
+{
+    int lane = threadIdx.x & 31;
+    int incl = n;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - n;
+}
+
+__device__ __forceinline__ void store_contact(const BbxDev& dv, int slot, int a, int b, int k, int phase,
+                                              float3 pt, float pen, float3 nrm)
+{
+    dv.c_ids[slot] = make_int4(a, b, k, phase);
+    dv.c_pt[slot] = make_float4(pt.x, pt.y, pt.z, pen);
+    dv.c_nrm[slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.0f);
+}
+
+// ---------------------------------------------------------------------------
+// sphere - box
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool sphere_box_contact(float3 sp, float sr, float3 bp, float3 bh, float4 bq,
+                                                   float3& pt, float3& nrm, float& pen)
+{
+    float3 rel = v3sub(sp, bp);
+    float3 loc = qrot(qconj(bq), rel);
+    float3 cp = f3(bb_fmaxf(-bh.x, bb_fminf(loc.x, bh.x)),
+                   bb_fmaxf(-bh.y, bb_fminf(loc.y, bh.y)),
+                   bb_fmaxf(-bh.z, bb_fminf(loc.z, bh.z)));
+    float3 diff = v3sub(loc, cp);
+    float d2 = v3dot(diff, diff);
+    if (!(d2 <= sr * sr)) return false;
+    float dist = sqrtf(d2);
+    float3 n;
+    if (dist > 1e-6f) {
+        n = v3scale(diff, 1.0f / dist);
+    } else {                                           // centre inside the box: axis of largest |local| (:1595-1603)
+        float ax = fabsf(loc.x), ay = fabsf(loc.y), az = fabsf(loc.z);
+        if (ax >= ay && ax >= az)      n = loc.x > 0 ? f3(1, 0, 0) : f3(-1, 0, 0);
+        else if (ay >= az)             n = loc.y > 0 ? f3(0, 1, 0) : f3(0, -1, 0);
+        else                           n = loc.z > 0 ? f3(0, 0, 1) : f3(0, 0, -1);
+    }
+    n = qrot(bq, n);
+    float3 s2b = v3sub(bp, sp);
+    if (v3dot(n, s2b) < 0.0f) n = v3scale(n, -1.0f);   // :1610-1614
+    pt = v3add(sp, v3scale(n, -sr));                   // far side of the sphere (:1617-1619)
+    nrm = n;
+    pen = sr - dist;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_narrow_sb(BbxDev dv)
+{
+    int n = min(dv.ctr->n_cand_sb, dv.cap_cand);
+    int n_round = (n + 31) & ~31;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
+        bool hit = false;
+        float3 pt, nrm; float pen = 0.0f; int2 pr = make_int2(0, 0);
+        if (t < n) {
+            pr = dv.cand_sb[t];
+            float4 sp = dv.pos[pr.x], bp = dv.pos[pr.y];
+            int b = pr.y - dv.NS;
+            hit = sphere_box_contact(xyz(sp), sp.w, xyz(bp), xyz(dv.half[b]), dv.rot[b], pt, nrm, pen);
+        }
+        int slot = warp_reserve(&dv.ctr->n_contacts, hit ? 1 : 0);
+        if (hit) {
+            if (slot < dv.cap_contacts) store_contact(dv, slot, pr.x, pr.y, 0, PH_SB, pt, pen, nrm);
+            else atomicOr(&dv.ctr->overflow, 2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// box - box: SAT
+// ---------------------------------------------------------------------------
+struct Obb { float3 c; float3 h; float3 ax[3]; };
+
+__device__ __forceinline__ float comp3(float3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+__device__ __forceinline__ Obb make_obb(float3 pos, float3 half, float4 q)            // CreateOBB :826-834
+{
+    Obb o; o.c = pos; o.h = half;
+    o.ax[0] = qrot(q, f3(1, 0, 0)); o.ax[1] = qrot(q, f3(0, 1, 0)); o.ax[2] = qrot(q, f3(0, 0, 1));
+    return o;
+}
+
+__device__ __forceinline__ void obb_vertices(const Obb& o, float3 v[8])               // GetOBBVertices :837-850
+{
+    float3 hX = v3scale(o.ax[0], o.h.x), hY = v3scale(o.ax[1], o.h.y), hZ = v3scale(o.ax[2], o.h.z);
+    v[0] = v3add(v3add(v3add(o.c, hX), hY), hZ);
+    v[1] = v3add(v3add(v3sub(o.c, hZ), hX), hY);
+    v[2] = v3add(v3add(v3add(o.c, hX), hZ), v3scale(hY, -1.0f));
+    v[3] = v3add(v3sub(v3add(o.c, hX), hY), v3scale(hZ, -1.0f));
+    v[4] = v3add(v3add(v3add(o.c, hY), hZ), v3scale(hX, -1.0f));
+    v[5] = v3add(v3sub(v3add(o.c, hY), hZ), v3scale(hX, -1.0f));
+    v[6] = v3add(v3sub(v3add(o.c, hZ), hX), v3scale(hY, -1.0f));
+    v[7] = v3sub(v3sub(v3sub(o.c, hX), hY), hZ);
+}
+
+__device__ __forceinline__ void project_obb(const Obb& o, float3 axis, float& mn, float& mx)   // :853-861
+{
+    float cpj = v3dot(o.c, axis);
+    float ext = o.h.x * fabsf(v3dot(o.ax[0], axis)) + o.h.y * fabsf(v3dot(o.ax[1], axis)) + o.h.z * fabsf(v3dot(o.ax[2], axis));
+    mn = cpj - ext; mx = cpj + ext;
+}
+
+__device__ __forceinline__ bool overlap_on_axis(const Obb& a, const Obb& b, float3 axis, float& pd)   // :864-884
+{
+    float min1, max1, min2, max2;
+    project_obb(a, axis, min1, max1);
+    project_obb(b, axis, min2, max2);
+    if (max1 < min2 || max2 < min1) return false;
+    float ov = bb_fminf(max1, max2) - bb_fmaxf(min1, min2);
+    pd = ov;
+    if (min1 < min2) pd *= -1.0f;
+    return true;
+}
+
+// VertexFaceCollision :908-950 (with IsPointInFaceBounds :891-900)
+__device__ __noinline__ float3 vertex_face(const Obb& vo, const Obb& fo, float& smallest)
+{
+    float3 vtx[8];
+    obb_vertices(vo, vtx);
+    float3 best = f3(0, 0, 0);
+    smallest = 999999.0f;
+    for (int i = 0; i < 3; i++) {
+        float3 fn = fo.ax[i];
+        float3 U = v3norm(fo.ax[(i + 1) % 3]);
+        float3 V = v3norm(fo.ax[(i + 2) % 3]);
+        float uH = comp3(fo.h, (i + 1) % 3), vH = comp3(fo.h, (i + 2) % 3);
+        for (int dir = -1; dir <= 1; dir += 2) {
+            float3 dn = v3scale(fn, (float)dir);
+            float off = comp3(fo.h, i) * (float)dir;
+            float3 fc = v3add(fo.c, v3scale(fn, off));
+            for (int j = 0; j < 8; j++) {
+                float sd = v3dot(v3sub(vtx[j], fc), dn);
+                if (sd < 0.0f) {
+                    float pdep = -sd;
+                    float3 rel = v3sub(vtx[j], fc);
+                    float uc = v3dot(rel, U), vc = v3dot(rel, V);
+                    if (fabsf(uc) <= uH && fabsf(vc) <= vH) {
+                        if (pdep < smallest) { smallest = pdep; best = vtx[j]; }
+                    }
+                }
+            }
+        }
+    }
+    return best;
+}
+
+// SquaredDistanceBetweenEdges :953-990
+__device__ __forceinline__ float sq_dist_edges(float3 p1, float3 q1, float3 p2, float3 q2)
+{
+    float3 d1 = v3sub(q1, p1), d2 = v3sub(q2, p2), r = v3sub(p1, p2);
+    float a = v3dot(d1, d1), e = v3dot(d2, d2), f = v3dot(d2, r);
+    float s, t;
+    if (a <= 1e-6f && e <= 1e-6f) return v3dot(r, r);
+    if (a <= 1e-6f) {
+        s = 0.0f;
+        t = bb_fmaxf(0.0f, bb_fminf(1.0f, f / e));
+    } else {
+        float c = v3dot(d1, r);
+        if (e <= 1e-6f) {
+            t = 0.0f;
+            s = bb_fmaxf(0.0f, bb_fminf(1.0f, -c / a));
+        } else {
+            float b = v3dot(d1, d2);
+            float denom = a * e - b * b;
+            if (denom != 0.0f) s = bb_fmaxf(0.0f, bb_fminf(1.0f, (b * f - c * e) / denom));
+            else s = 0.0f;
+            t = bb_fmaxf(0.0f, bb_fminf(1.0f, (b * s + f) / e));
+        }
+    }
+    float3 c1 = v3add(p1, v3scale(d1, s)), c2 = v3add(p2, v3scale(d2, t));
+    float3 df = v3sub(c1, c2);
+    return v3dot(df, df);
+}
+
+// ClosestPointBetweenEdges :993-1034: whatever edge wins, the result is the
+// midpoint of the two centres -- unless every tested edge pair is >= 999999 apart.
+__device__ __noinline__ float3 closest_point_between_edges(const Obb& o1, const Obb& o2)
+{
+    float3 v1[8], v2[8];
+    obb_vertices(o1, v1);
+    obb_vertices(o2, v2);
+    float3 e1[3] = { v3sub(v1[1], v1[0]), v3sub(v1[2], v1[0]), v3sub(v1[4], v1[0]) };
+    float3 e2[3] = { v3sub(v2[1], v2[0]), v3sub(v2[2], v2[0]), v3sub(v2[4], v2[0]) };
+    float mind = 999999.0f;
+    float3 cp = f3(0, 0, 0);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float d = sq_dist_edges(v1[0], v3add(v1[0], e1[i]), v2[0], v3add(v2[0], e2[j]));
+            if (d < mind) { mind = d; cp = v3scale(v3add(o1.c, o2.c), 0.5f); }
+        }
+    return cp;
+}
+
+// SATCollision :1040-1111 + the normal flip of CheckBoxCollisionWithData :1121-1129
+__device__ bool sat_contact(const Obb& A, const Obb& B, float3& pt, float3& nrm, float& pen)
+{
+    float minPd = 999999.0f;
+    float3 smallest = f3(0, 0, 0);
+    int axisType = -1, idx = 0;
+#define SAT_TEST(AXIS) do { float3 ax_ = (AXIS); float pd_ = 0.0f; \
+        if (!overlap_on_axis(A, B, ax_, pd_)) return false; \
+        if (fabsf(pd_) < fabsf(minPd)) { minPd = pd_; smallest = v3scale(ax_, (pd_ < 0) ? -1.0f : 1.0f); axisType = idx; } \
+        idx++; } while (0)
+    // the reference first builds the (compacted) axis list, then tests in order; the
+    // outcome of every test is independent of the others, so interleaving is equivalent
+    for (int i = 0; i < 3; i++) SAT_TEST(A.ax[i]);
+    for (int i = 0; i < 3; i++) SAT_TEST(B.ax[i]);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float3 cr = v3cross(A.ax[i], B.ax[j]);
+            float l = v3len(cr);
+            if (l > 1e-6f) SAT_TEST(v3scale(cr, 1.0f / l));
+        }
+#undef SAT_TEST
+    pen = fabsf(minPd);
+    nrm = smallest;
+    if (axisType >= 0 && axisType <= 5) {
+        float d1, d2;
+        float3 p1 = vertex_face(A, B, d1);
+        float3 p2 = vertex_face(B, A, d2);
+        pt = (d1 < d2) ? p1 : p2;
+    } else if (axisType >= 6) {
+        pt = closest_point_between_edges(A, B);
+    } else {
+        pt = v3scale(v3add(A.c, B.c), 0.5f);
+    }
+    float3 c2c = v3sub(B.c, A.c);
+    if (v3dot(nrm, c2c) < 0.0f) nrm = v3scale(nrm, -1.0f);
+    return true;
+}
+
+// is `p` inside box (pos, half, q) grown by tol?  returns the minimum face slack
+__device__ __forceinline__ bool inside_box(float3 p, float3 pos, float3 half, float4 q, float tol, float& slack)
+{
+    float3 loc = qrot(qconj(q), v3sub(p, pos));
+    if (fabsf(loc.x) <= half.x + tol && fabsf(loc.y) <= half.y + tol && fabsf(loc.z) <= half.z + tol) {
+        float px = half.x - fabsf(loc.x), py = half.y - fabsf(loc.y), pz = half.z - fabsf(loc.z);
+        slack = bb_fminf(px, bb_fminf(py, pz));
+        return true;
+    }
+    return false;
+}
+
+// GenerateBoxBoxManifold + SelectOptimalContactPoints.  Returns the number of
+// manifold points (0 = no collision).
+__device__ int box_box_manifold(float3 posA, float3 hA, float4 qA, float3 posB, float3 hB, float4 qB,
+                                float tol, float pen_tol, int max_contacts,
+                                float3 out_pt[8], float out_pen[8], float3& normal)
+{
+    Obb A = make_obb(posA, hA, qA), B = make_obb(posB, hB, qB);
+    float3 cpt[24]; float cpen[24]; int cc = 0;
+    float3 spt; float spen;
+    if (!sat_contact(A, B, spt, normal, spen)) return 0;
+    cpt[0] = spt; cpen[0] = spen; cc = 1;                          // :2583-2585
+    float3 vA[8], vB[8];
+    obb_vertices(A, vA);
+    obb_vertices(B, vB);
+    for (int i = 0; i < 8 && cc < 24; i++) {                       // :2595-2622
+        float sl;
+        if (inside_box(vA[i], posB, hB, qB, tol, sl) && sl > pen_tol) { cpt[cc] = vA[i]; cpen[cc] = sl; cc++; }
+    }
+    for (int i = 0; i < 8 && cc < 24; i++) {                       // :2625-2652
+        float sl;
+        if (inside_box(vB[i], posA, hA, qA, tol, sl) && sl > pen_tol) { cpt[cc] = vB[i]; cpen[cc] = sl; cc++; }
+    }
+    if (cc < 3) {                                                  // :2656-2714, edge table copied literally
+        for (int e = 0; e < 12 && cc < 24; e++) {
+            float3 s, t;
+            if (e < 4)      { s = vA[e];     t = vA[(e + 1) % 4]; }
+            else if (e < 8) { s = vA[e];     t = vA[4 + ((e - 4 + 1) % 4)]; }
+            else            { s = vA[e - 8]; t = vA[e - 8 + 4]; }
+            float3 mid = v3scale(v3add(s, t), 0.5f);
+            float sl;
+            if (inside_box(mid, posB, hB, qB, tol, sl) && sl > pen_tol) { cpt[cc] = mid; cpen[cc] = sl; cc++; }
+        }
+    }
+    // ---- SelectOptimalContactPoints :2726-2843 ----
+    if (cc <= 2) {
+        for (int i = 0; i < cc; i++) { out_pt[i] = cpt[i]; out_pen[i] = cpen[i]; }
+        return cc;
+    }
+    int deep = 0;
+    for (int i = 1; i < cc; i++) if (cpen[i] > cpen[deep]) deep = i;
+    out_pt[0] = cpt[deep]; out_pen[0] = cpen[deep];
+    if (cc <= max_contacts) {
+        int k = 1;
+        for (int i = 0; i < cc; i++) if (i != deep) { out_pt[k] = cpt[i]; out_pen[k] = cpen[i]; k++; }
+        return cc;
+    }
+    float3 centre = f3(0, 0, 0);
+    for (int i = 0; i < cc; i++) centre = v3add(centre, cpt[i]);
+    centre = v3scale(centre, 1.0f / (float)cc);
+    int rem = max_contacts - 1;
+    float bestd[8]; int besti[8];
+    for (int j = 0; j < rem; j++) { bestd[j] = -1.0f; besti[j] = -1; }
+    for (int i = 0; i < cc; i++) {
+        if (i == deep) continue;
+        float dist = v3len(v3sub(cpt[i], centre));
+        for (int j = 0; j < rem; j++) {
+            if (dist > bestd[j]) {
+                for (int k = rem - 1; k > j; k--) { bestd[k] = bestd[k - 1]; besti[k] = besti[k - 1]; }
+                bestd[j] = dist; besti[j] = i;
+                break;
+            }
+        }
+    }
+    int np = 1;
+    for (int j = 0; j < rem; j++) if (besti[j] >= 0) { out_pt[np] = cpt[besti[j]]; out_pen[np] = cpen[besti[j]]; np++; }
+    return np;
+}
+
+__global__ void __launch_bounds__(128) k_narrow_bb(BbxDev dv, float tol, float pen_tol, int max_contacts)
+{
+    int n = min(dv.ctr->n_cand_bb, dv.cap_cand);
+    int n_round = (n + 31) & ~31;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
+        int np = 0;
+        float3 pts[8]; float pens[8]; float3 normal = f3(0, 0, 0);
+        int2 pr = make_int2(0, 0);
+        if (t < n) {
+            pr = dv.cand_bb[t];
+            int a = pr.x - dv.NS, b = pr.y - dv.NS;
+            float4 pa = dv.pos[pr.x], pb = dv.pos[pr.y];
+            np = box_box_manifold(xyz(pa), xyz(dv.half[a]), dv.rot[a], xyz(pb), xyz(dv.half[b]), dv.rot[b],
+                                  tol, pen_tol, max_contacts, pts, pens, normal);
+        }
+        int slot = warp_reserve(&dv.ctr->n_contacts, np);
+        if (np > 0) {
+            if (slot + np <= dv.cap_contacts) {
+                for (int k = 0; k < np; k++) store_contact(dv, slot + k, pr.x, pr.y, k, PH_BB, pts[k], pens[k], normal);
+            } else atomicOr(&dv.ctr->overflow, 2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SDF probing
+// ---------------------------------------------------------------------------
+struct SdfDesc { int id; float prm[8]; float eps; };
+
+__device__ __forceinline__ float sdf_at(const SdfDesc& s, float3 p) { return bbx_sdf_eval(s.id, s.prm, p.x, p.y, p.z); }
+
+__device__ __forceinline__ float3 sdf_normal(const SdfDesc& s, float3 p)               // SDF_EstimateNormal :2318-2331
+{
+    float e = s.eps;
+    float3 ex = f3(e, 0.0f, 0.0f), ey = f3(0.0f, e, 0.0f), ez = f3(0.0f, 0.0f, e);
+    float nx = (sdf_at(s, v3add(p, ex)) - sdf_at(s, v3sub(p, ex))) / (2.0f * e);
+    float ny = (sdf_at(s, v3add(p, ey)) - sdf_at(s, v3sub(p, ey))) / (2.0f * e);
+    float nz = (sdf_at(s, v3add(p, ez)) - sdf_at(s, v3sub(p, ez))) / (2.0f * e);
+    return v3norm(f3(nx, ny, nz));
+}
+
+__global__ void __launch_bounds__(256) k_sdf_spheres(BbxDev dv, SdfDesc sdf)
+{
+    int n_round = (dv.NS + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool hit = false; float3 pt, nrm; float pen = 0.0f;
+        if (i < dv.NS && (dv.flags[i] & BF_VALID)) {
+            float4 p4 = dv.pos[i];
+            float3 c = xyz(p4); float r = p4.w;
+            float dd = sdf_at(sdf, c);
+            if (dd < r) {                                           // :2086
+                hit = true;
+                pen = r - dd;
+                nrm = v3scale(sdf_normal(sdf, c), -1.0f);
+                pt = v3sub(c, v3scale(nrm, r));                     // :2094
+            }
+        }
+        int slot = warp_reserve(&dv.ctr->n_contacts, hit ? 1 : 0);
+        if (hit) {
+            if (slot < dv.cap_contacts) store_contact(dv, slot, i, -2, 0, PH_SSDF, pt, pen, nrm);
+            else atomicOr(&dv.ctr->overflow, 2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_sdf_boxes(BbxDev dv, SdfDesc sdf)
+{
+    const int edge_pairs[12][2] = { {0,1},{1,2},{2,3},{3,0}, {4,5},{5,6},{6,7},{7,4}, {0,4},{1,5},{2,6},{3,7} };   // :2454-2458
+    int n_round = (dv.NB + 31) & ~31;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_round; b += gridDim.x * blockDim.x) {
+        int g = dv.NS + b;
+        bool valid = b < dv.NB && (dv.flags[g] & BF_VALID);
+        float3 vtx[8];
+        unsigned int mask = 0;            // which of the 20 probes penetrate
+        if (valid) {
+            Obb o = make_obb(xyz(dv.pos[g]), xyz(dv.half[b]), dv.rot[b]);
+            obb_vertices(o, vtx);
+            for (int k = 0; k < 8; k++) if (sdf_at(sdf, vtx[k]) < -0.001f) mask |= 1u << k;
+            for (int e = 0; e < 12; e++) {
+                float3 mid = v3scale(v3add(vtx[edge_pairs[e][0]], vtx[edge_pairs[e][1]]), 0.5f);
+                if (sdf_at(sdf, mid) < -0.001f) mask |= 1u << (8 + e);
+            }
+        }
+        int np = __popc(mask);
+        int slot = warp_reserve(&dv.ctr->n_contacts, np);
+        if (np > 0) {
+            if (slot + np > dv.cap_contacts) { atomicOr(&dv.ctr->overflow, 2); continue; }
+            int k = 0;
+            for (int pidx = 0; pidx < 20; pidx++) {
+                if (!(mask & (1u << pidx))) continue;
+                float3 p = (pidx < 8) ? vtx[pidx]
+                                      : v3scale(v3add(vtx[edge_pairs[pidx - 8][0]], vtx[edge_pairs[pidx - 8][1]]), 0.5f);
+                float dd = sdf_at(sdf, p);
+                float3 nrm = v3scale(sdf_normal(sdf, p), -1.0f);
+                store_contact(dv, slot + k, g, -2, k, PH_BSDF, p, -dd, nrm);
+                k++;
+            }
+        }
+    }
+}
+
+int bbx_stage_narrowphase(BbxDev* d, const BbxStepParams* p)
+{
+    int mc = p->settings.manifold_max_contacts;
+    if (mc < 1) mc = 1;
+    if (mc > MAX_MANIFOLD_CONTACTS) mc = MAX_MANIFOLD_CONTACTS;
+    BBX_LAUNCH(d, k_narrow_bb, BBX_NUM_SMS * 8, 128, 0, *d, p->settings.manifold_contact_tolerance,
+               p->settings.manifold_penetration_tolerance, mc);
+    BBX_LAUNCH(d, k_narrow_sb, BBX_NUM_SMS * 8, 256, 0, *d);
+    if (p->sdf_id != BBX_SDF_NONE) {
+        SdfDesc s; s.id = p->sdf_id; s.eps = p->settings.sdf_normal_epsilon;
+        for (int k = 0; k < 8; k++) s.prm[k] = p->sdf_params[k];
+        if (d->NS > 0) BBX_LAUNCH(d, k_sdf_spheres, BBX_NUM_SMS * 8, 256, 0, *d, s);
+        if (d->NB > 0) BBX_LAUNCH(d, k_sdf_boxes, BBX_NUM_SMS * 8, 128, 0, *d, s);
+    }
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,382 @@
+// bbx_state.cu -- device context lifetime, host<->HBM transfer of the public SoA
+// arrays (reference ballbox.h:62-95) and the pack/unpack kernels that convert
+// between the user-visible 12-byte Vec3 layout and the float4 working layout.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "bbx_dev.cuh"
+
+int bbx_fail(BbxDev* d, int code, const char* what, const char* file, int line)
+{
+    if (d && !d->has_err && d->err) {
+        snprintf(d->err, 256, "ballbox-b200: %s (code %d) at %s:%d", what, code, file, line);
+        d->has_err = 1;
+        fprintf(stderr, "%s\n", d->err);
+    }
+    return code ? code : BBX_ERR_STICKY;
+}
+
+extern "C" int bbx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void* bbx_host_alloc(size_t bytes, int* pinned)
+{
+    void* p = NULL;
+    if (bytes == 0) bytes = 16;
+    if (pinned) *pinned = 0;
+    if (bbx_device_count() > 0 && bytes <= ((size_t)3 << 30)) {
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) {
+            memset(p, 0, bytes);
+            if (pinned) *pinned = 1;
+            return p;
+        }
+        cudaGetLastError();
+    }
+    return calloc(1, bytes);
+}
+
+extern "C" void bbx_host_free(void* p, int pinned)
+{
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
+}
+
+template <typename T>
+static int dalloc(BbxDev* d, T** p, size_t count)
+{
+    if (count == 0) count = 1;
+    BBX_CUDA(d, cudaMalloc((void**)p, count * sizeof(T)));
+    BBX_CUDA(d, cudaMemsetAsync(*p, 0, count * sizeof(T), d->stream));
+    return 0;
+}
+#define DALLOC(ptr, count) do { int rc_ = dalloc(d, &(ptr), (size_t)(count)); if (rc_) return rc_; } while (0)
+
+extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s, int cap_b, int cap_contacts_world)
+{
+    if (!out || n_worlds < 1 || cap_s < 0 || cap_b < 0 || cap_contacts_world < 0) return BBX_ERR_BAD_ARGUMENT;
+    *out = NULL;
+    if (bbx_device_count() <= 0) {
+        fprintf(stderr, "ballbox-b200: no CUDA device visible; this library has no CPU fallback\n");
+        return BBX_ERR_NO_DEVICE;
+    }
+    BbxDev* d = (BbxDev*)calloc(1, sizeof(BbxDev));
+    if (!d) return BBX_ERR_BAD_ARGUMENT;
+    *out = d;                      // caller destroys on failure
+    d->err = (char*)calloc(256, 1);
+    d->device = device;
+    BBX_CUDA(d, cudaSetDevice(device));
+    d->stream = 0;
+    d->n_worlds = n_worlds; d->cap_s = cap_s; d->cap_b = cap_b;
+    long long NS = (long long)n_worlds * cap_s, NB = (long long)n_worlds * cap_b;
+    long long CC = (long long)n_worlds * cap_contacts_world;
+    if (NS + NB > (1ll << 28) || CC > (1ll << 28)) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "capacity too large", __FILE__, __LINE__);
+    if (NS >= (1 << 24) || NB >= (1 << 24)) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "more than 2^24 bodies of one type", __FILE__, __LINE__);
+    d->NS = (int)NS; d->NB = (int)NB; d->N = (int)(NS + NB);
+    d->cap_contacts_world = cap_contacts_world;
+    d->cap_contacts = (int)(CC < 1024 ? 1024 : CC);
+    long long cc2 = 2ll * d->cap_contacts;
+    d->cap_cand = (int)(cc2 < 65536 ? 65536 : cc2);
+    long long cells = 4ll * d->N;
+    if (cells < 65536) cells = 65536;
+    if (cells > (1ll << 25)) cells = 1ll << 25;
+    if (cells < 64ll * n_worlds) cells = 64ll * n_worlds;
+    d->cap_cells = (int)cells;
+    int N = d->N;
+
+    DALLOC(d->r_s_pos, 3 * NS); DALLOC(d->r_s_radius, NS); DALLOC(d->r_s_vel, 3 * NS); DALLOC(d->r_s_force, 3 * NS);
+    DALLOC(d->r_s_mass, NS); DALLOC(d->r_s_angvel, 3 * NS); DALLOC(d->r_s_torque, 3 * NS); DALLOC(d->r_s_inertia, NS);
+    DALLOC(d->r_s_timer, NS); DALLOC(d->r_s_static, NS); DALLOC(d->r_s_sleep, NS); DALLOC(d->r_s_hascb, NS);
+    DALLOC(d->r_b_pos, 3 * NB); DALLOC(d->r_b_size, 3 * NB); DALLOC(d->r_b_rot, 4 * NB); DALLOC(d->r_b_vel, 3 * NB);
+    DALLOC(d->r_b_force, 3 * NB); DALLOC(d->r_b_mass, NB); DALLOC(d->r_b_angvel, 3 * NB); DALLOC(d->r_b_torque, 3 * NB);
+    DALLOC(d->r_b_inertia, 3 * NB); DALLOC(d->r_b_timer, NB); DALLOC(d->r_b_static, NB); DALLOC(d->r_b_sleep, NB);
+    DALLOC(d->r_b_hascb, NB);
+    DALLOC(d->d_s_count, n_worlds); DALLOC(d->d_b_count, n_worlds);
+
+    DALLOC(d->pos, N); DALLOC(d->lin, N); DALLOC(d->ang, N); DALLOC(d->mass, N); DALLOC(d->timer, N); DALLOC(d->flags, N);
+    DALLOC(d->rot, NB); DALLOC(d->half, NB); DALLOC(d->invI, NB);
+
+    DALLOC(d->grid, 1);
+    DALLOC(d->cell_count, d->cap_cells + 1); DALLOC(d->cell_start, d->cap_cells + 1); DALLOC(d->cell_cursor, d->cap_cells + 1);
+    DALLOC(d->body_cell, N); DALLOC(d->sorted_id, N); DALLOC(d->sorted_pos, N);
+    DALLOC(d->big_list, N); DALLOC(d->big_start, n_worlds + 1);
+    DALLOC(d->scan_tmp, 1 << 16);
+
+    DALLOC(d->cand_sb, d->cap_cand); DALLOC(d->cand_bb, d->cap_cand);
+    int C = d->cap_contacts;
+    DALLOC(d->c_ids, C); DALLOC(d->c_pt, C); DALLOC(d->c_nrm, C);
+    DALLOC(d->L0, C); DALLOC(d->L1, C); DALLOC(d->L2, C); DALLOC(d->L3, C); DALLOC(d->Lid, C);
+    DALLOC(d->deg, N + 1); DALLOC(d->adj_start, N + 1); DALLOC(d->adj_cursor, N + 1);
+    DALLOC(d->adj, 2 * (size_t)C);
+    DALLOC(d->next_a, C); DALLOC(d->next_b, C); DALLOC(d->indeg, C);
+    DALLOC(d->queue, C); DALLOC(d->slot_of, C); DALLOC(d->level_count, C + 4);
+    DALLOC(d->M0, C); DALLOC(d->M1, C); DALLOC(d->M2, C); DALLOC(d->M3, C); DALLOC(d->Mid, C);
+    DALLOC(d->ctr, 1);
+    DALLOC(d->sort_keys, C);
+    d->export_buf = NULL;          // allocated on first constraint download
+    BBX_CUDA(d, cudaHostAlloc((void**)&d->ctr_host, sizeof(StepCounters), cudaHostAllocDefault));
+    memset(d->ctr_host, 0, sizeof(StepCounters));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+extern "C" void bbx_dev_destroy(BbxDev* d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = { d->r_s_pos, d->r_s_radius, d->r_s_vel, d->r_s_force, d->r_s_mass, d->r_s_angvel, d->r_s_torque,
+        d->r_s_inertia, d->r_s_timer, d->r_s_static, d->r_s_sleep, d->r_s_hascb, d->r_b_pos, d->r_b_size, d->r_b_rot,
+        d->r_b_vel, d->r_b_force, d->r_b_mass, d->r_b_angvel, d->r_b_torque, d->r_b_inertia, d->r_b_timer, d->r_b_static,
+        d->r_b_sleep, d->r_b_hascb, d->d_s_count, d->d_b_count, d->pos, d->lin, d->ang, d->mass, d->timer, d->flags,
+        d->rot, d->half, d->invI, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
+        d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->c_ids, d->c_pt, d->c_nrm,
+        d->L0, d->L1, d->L2, d->L3, d->Lid, d->deg, d->adj_start, d->adj_cursor, d->adj, d->next_a, d->next_b, d->indeg,
+        d->queue, d->slot_of, d->level_count, d->M0, d->M1, d->M2, d->M3, d->Mid, d->ctr, d->sort_keys, d->export_buf };
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
+    if (d->ctr_host) cudaFreeHost(d->ctr_host);
+    cudaGetLastError();
+    free(d->err);
+    free(d);
+}
+
+extern "C" void bbx_dev_set_stream(BbxDev* d, void* s) { if (d) d->stream = (cudaStream_t)s; }
+extern "C" const char* bbx_dev_error(BbxDev* d) { return (d && d->has_err) ? d->err : NULL; }
+extern "C" void bbx_dev_clear_error(BbxDev* d) { if (d) { d->has_err = 0; if (d->err) d->err[0] = 0; } }
+
+extern "C" int bbx_dev_synchronize(BbxDev* d)
+{
+    if (!d) return BBX_ERR_BAD_ARGUMENT;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// pack: raw host-layout mirrors -> float4 working state
+// ---------------------------------------------------------------------------
+__global__ void k_pack(BbxDev dv)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= dv.N) return;
+    if (g < dv.NS) {
+        int w = g / dv.cap_s, i = g - w * dv.cap_s;
+        bool valid = i < dv.d_s_count[w];
+        if (!valid) { dv.flags[g] = 0; return; }
+        bool st = dv.r_s_static[g] != 0;
+        float r = dv.r_s_radius[g], m = dv.r_s_mass[g];
+        dv.pos[g] = make_float4(dv.r_s_pos[3 * g], dv.r_s_pos[3 * g + 1], dv.r_s_pos[3 * g + 2], r);
+        dv.lin[g] = make_float4(dv.r_s_vel[3 * g], dv.r_s_vel[3 * g + 1], dv.r_s_vel[3 * g + 2], st ? 0.0f : 1.0f / m);
+        dv.ang[g] = make_float4(dv.r_s_angvel[3 * g], dv.r_s_angvel[3 * g + 1], dv.r_s_angvel[3 * g + 2],
+                                st ? 0.0f : 1.0f / dv.r_s_inertia[g]);
+        dv.mass[g] = m;
+        dv.timer[g] = dv.r_s_timer[g];
+        dv.flags[g] = (unsigned char)(BF_VALID | (st ? BF_STATIC : 0) | (dv.r_s_sleep[g] ? BF_SLEEP : 0) |
+                                      (dv.r_s_hascb[g] ? BF_HASCB : 0));
+        unsigned int rb = __float_as_uint(fmaxf(r, 0.0f));
+        if (!st) atomicMax(&dv.ctr->cut_dyn, rb);
+        atomicMax(&dv.ctr->cut_all, rb);
+    } else {
+        int b = g - dv.NS;
+        int w = b / dv.cap_b, i = b - w * dv.cap_b;
+        bool valid = i < dv.d_b_count[w];
+        if (!valid) { dv.flags[g] = 0; return; }
+        bool st = dv.r_b_static[b] != 0;
+        float m = dv.r_b_mass[b];
+        float3 h = f3(dv.r_b_size[3 * b], dv.r_b_size[3 * b + 1], dv.r_b_size[3 * b + 2]);
+        float4 q = make_float4(dv.r_b_rot[4 * b], dv.r_b_rot[4 * b + 1], dv.r_b_rot[4 * b + 2], dv.r_b_rot[4 * b + 3]);
+        float R = box_bound_radius(h, q);
+        dv.pos[g] = make_float4(dv.r_b_pos[3 * b], dv.r_b_pos[3 * b + 1], dv.r_b_pos[3 * b + 2], R);
+        dv.lin[g] = make_float4(dv.r_b_vel[3 * b], dv.r_b_vel[3 * b + 1], dv.r_b_vel[3 * b + 2], st ? 0.0f : 1.0f / m);
+        dv.ang[g] = make_float4(dv.r_b_angvel[3 * b], dv.r_b_angvel[3 * b + 1], dv.r_b_angvel[3 * b + 2], 0.0f);
+        dv.rot[b] = q;
+        dv.half[b] = make_float4(h.x, h.y, h.z, 0.0f);
+        dv.invI[b] = st ? make_float4(0, 0, 0, 0)
+                        : make_float4(1.0f / dv.r_b_inertia[3 * b], 1.0f / dv.r_b_inertia[3 * b + 1],
+                                      1.0f / dv.r_b_inertia[3 * b + 2], 0.0f);
+        dv.mass[g] = m;
+        dv.timer[g] = dv.r_b_timer[b];
+        dv.flags[g] = (unsigned char)(BF_VALID | (st ? BF_STATIC : 0) | (dv.r_b_sleep[b] ? BF_SLEEP : 0) |
+                                      (dv.r_b_hascb[b] ? BF_HASCB : 0));
+        unsigned int rb = __float_as_uint(R);
+        if (!st) atomicMax(&dv.ctr->cut_dyn, rb);
+        atomicMax(&dv.ctr->cut_all, rb);
+    }
+}
+
+// bodies larger than the largest non-static body bypass the grid
+__global__ void k_choose_cut(BbxDev dv)
+{
+    float cd = __uint_as_float(dv.ctr->cut_dyn), ca = __uint_as_float(dv.ctr->cut_all);
+    float cut = cd > 0.0f ? cd : ca;
+    if (!(cut > 0.0f)) cut = 1.0f;
+    dv.grid->small_cut = cut;
+}
+
+__global__ void k_big_count(BbxDev dv, int* big_cnt)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= dv.N) return;
+    unsigned char f = dv.flags[g];
+    if (!(f & BF_VALID)) return;
+    if ((f & BF_STATIC) && dv.pos[g].w > dv.grid->small_cut) {
+        dv.flags[g] = f | BF_BIG;
+        int w = (g < dv.NS) ? g / dv.cap_s : (g - dv.NS) / dv.cap_b;
+        atomicAdd(&big_cnt[w], 1);
+        atomicAdd(&dv.ctr->n_big, 1);
+    }
+}
+
+__global__ void k_big_fill(BbxDev dv, int* cursor)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= dv.N) return;
+    if (!(dv.flags[g] & BF_BIG)) return;
+    int w = (g < dv.NS) ? g / dv.cap_s : (g - dv.NS) / dv.cap_b;
+    int slot = atomicAdd(&cursor[w], 1);
+    dv.big_list[slot] = g;
+}
+
+__global__ void k_reset_upload_counters(BbxDev dv)
+{
+    dv.ctr->cut_dyn = 0; dv.ctr->cut_all = 0; dv.ctr->n_big = 0;
+}
+
+int bbx_stage_pack(BbxDev* d)
+{
+    int nb = bbx_blocks(d->N, 256);
+    BBX_LAUNCH(d, k_reset_upload_counters, 1, 1, 0, *d);
+    BBX_LAUNCH(d, k_pack, nb, 256, 0, *d);
+    BBX_LAUNCH(d, k_choose_cut, 1, 1, 0, *d);
+    // big-body lists per world: count -> scan -> fill (cell_count/cell_cursor reused as scratch)
+    BBX_CUDA(d, cudaMemsetAsync(d->cell_count, 0, sizeof(int) * (d->n_worlds + 1), d->stream));
+    BBX_LAUNCH(d, k_big_count, nb, 256, 0, *d, d->cell_count);
+    int rc = bbx_scan_exclusive(d, d->cell_count, d->big_start, d->cell_cursor, d->n_worlds + 1, NULL, NULL);
+    if (rc) return rc;
+    BBX_LAUNCH(d, k_big_fill, nb, 256, 0, *d, d->cell_cursor);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bbx_dev_upload(BbxDev* d, const BbxHostBodies* hb)
+{
+    if (!d || !hb) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (hb->n_worlds != d->n_worlds || hb->cap_s != d->cap_s || hb->cap_b != d->cap_b)
+        return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "upload: layout mismatch", __FILE__, __LINE__);
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    size_t NS = d->NS, NB = d->NB;
+    cudaStream_t s = d->stream;
+#define UP(dst, src, bytes) do { if ((bytes) > 0 && (src)) BBX_CUDA(d, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, s)); } while (0)
+    UP(d->d_s_count, hb->s_count, sizeof(int) * d->n_worlds);
+    UP(d->d_b_count, hb->b_count, sizeof(int) * d->n_worlds);
+    UP(d->r_s_pos, hb->s_pos, 12 * NS); UP(d->r_s_radius, hb->s_radius, 4 * NS); UP(d->r_s_vel, hb->s_vel, 12 * NS);
+    UP(d->r_s_force, hb->s_force, 12 * NS); UP(d->r_s_mass, hb->s_mass, 4 * NS); UP(d->r_s_angvel, hb->s_angvel, 12 * NS);
+    UP(d->r_s_torque, hb->s_torque, 12 * NS); UP(d->r_s_inertia, hb->s_inertia, 4 * NS); UP(d->r_s_timer, hb->s_timer, 4 * NS);
+    UP(d->r_s_static, hb->s_static, NS); UP(d->r_s_sleep, hb->s_sleep, NS);
+    if (hb->s_hascb) UP(d->r_s_hascb, hb->s_hascb, NS); else BBX_CUDA(d, cudaMemsetAsync(d->r_s_hascb, 0, NS ? NS : 1, s));
+    UP(d->r_b_pos, hb->b_pos, 12 * NB); UP(d->r_b_size, hb->b_size, 12 * NB); UP(d->r_b_rot, hb->b_rot, 16 * NB);
+    UP(d->r_b_vel, hb->b_vel, 12 * NB); UP(d->r_b_force, hb->b_force, 12 * NB); UP(d->r_b_mass, hb->b_mass, 4 * NB);
+    UP(d->r_b_angvel, hb->b_angvel, 12 * NB); UP(d->r_b_torque, hb->b_torque, 12 * NB); UP(d->r_b_inertia, hb->b_inertia, 12 * NB);
+    UP(d->r_b_timer, hb->b_timer, 4 * NB); UP(d->r_b_static, hb->b_static, NB); UP(d->r_b_sleep, hb->b_sleep, NB);
+    if (hb->b_hascb) UP(d->r_b_hascb, hb->b_hascb, NB); else BBX_CUDA(d, cudaMemsetAsync(d->r_b_hascb, 0, NB ? NB : 1, s));
+#undef UP
+    long long vs = 0, vb = 0;
+    for (int w = 0; w < d->n_worlds; w++) { vs += hb->s_count[w]; vb += hb->b_count[w]; }
+    d->n_valid_spheres = (int)vs; d->n_valid_boxes = (int)vb;
+    return bbx_stage_pack(d);
+}
+
+extern "C" int bbx_dev_upload_forces(BbxDev* d, const BbxHostBodies* hb)
+{
+    if (!d || !hb) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    size_t NS = d->NS, NB = d->NB;
+    if (NS) {
+        BBX_CUDA(d, cudaMemcpyAsync(d->r_s_force, hb->s_force, 12 * NS, cudaMemcpyHostToDevice, d->stream));
+        BBX_CUDA(d, cudaMemcpyAsync(d->r_s_torque, hb->s_torque, 12 * NS, cudaMemcpyHostToDevice, d->stream));
+    }
+    if (NB) {
+        BBX_CUDA(d, cudaMemcpyAsync(d->r_b_force, hb->b_force, 12 * NB, cudaMemcpyHostToDevice, d->stream));
+        BBX_CUDA(d, cudaMemcpyAsync(d->r_b_torque, hb->b_torque, 12 * NB, cudaMemcpyHostToDevice, d->stream));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// unpack: working state -> raw mirrors (only what a step can change)
+// ---------------------------------------------------------------------------
+__global__ void k_unpack(BbxDev dv)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= dv.N) return;
+    unsigned char f = dv.flags[g];
+    if (!(f & BF_VALID)) return;
+    float4 p = dv.pos[g], v = dv.lin[g], w = dv.ang[g];
+    if (g < dv.NS) {
+        dv.r_s_pos[3 * g] = p.x; dv.r_s_pos[3 * g + 1] = p.y; dv.r_s_pos[3 * g + 2] = p.z;
+        dv.r_s_vel[3 * g] = v.x; dv.r_s_vel[3 * g + 1] = v.y; dv.r_s_vel[3 * g + 2] = v.z;
+        dv.r_s_angvel[3 * g] = w.x; dv.r_s_angvel[3 * g + 1] = w.y; dv.r_s_angvel[3 * g + 2] = w.z;
+        dv.r_s_sleep[g] = (f & BF_SLEEP) ? 1 : 0;
+        dv.r_s_timer[g] = dv.timer[g];
+    } else {
+        int b = g - dv.NS;
+        float4 q = dv.rot[b];
+        dv.r_b_pos[3 * b] = p.x; dv.r_b_pos[3 * b + 1] = p.y; dv.r_b_pos[3 * b + 2] = p.z;
+        dv.r_b_vel[3 * b] = v.x; dv.r_b_vel[3 * b + 1] = v.y; dv.r_b_vel[3 * b + 2] = v.z;
+        dv.r_b_angvel[3 * b] = w.x; dv.r_b_angvel[3 * b + 1] = w.y; dv.r_b_angvel[3 * b + 2] = w.z;
+        dv.r_b_rot[4 * b] = q.x; dv.r_b_rot[4 * b + 1] = q.y; dv.r_b_rot[4 * b + 2] = q.z; dv.r_b_rot[4 * b + 3] = q.w;
+        dv.r_b_sleep[b] = (f & BF_SLEEP) ? 1 : 0;
+        dv.r_b_timer[b] = dv.timer[g];
+    }
+}
+
+int bbx_stage_unpack(BbxDev* d)
+{
+    BBX_LAUNCH(d, k_unpack, bbx_blocks(d->N, 256), 256, 0, *d);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bbx_dev_download(BbxDev* d, const BbxHostBodies* hb)
+{
+    if (!d || !hb) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    int rc = bbx_stage_unpack(d);
+    if (rc) return rc;
+    size_t NS = d->NS, NB = d->NB;
+    cudaStream_t s = d->stream;
+#define DN(dst, src, bytes) do { if ((bytes) > 0 && (dst)) BBX_CUDA(d, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s)); } while (0)
+    DN(hb->s_pos, d->r_s_pos, 12 * NS); DN(hb->s_vel, d->r_s_vel, 12 * NS); DN(hb->s_angvel, d->r_s_angvel, 12 * NS);
+    DN(hb->s_sleep, d->r_s_sleep, NS); DN(hb->s_timer, d->r_s_timer, 4 * NS);
+    DN(hb->b_pos, d->r_b_pos, 12 * NB); DN(hb->b_vel, d->r_b_vel, 12 * NB); DN(hb->b_angvel, d->r_b_angvel, 12 * NB);
+    DN(hb->b_rot, d->r_b_rot, 16 * NB); DN(hb->b_sleep, d->r_b_sleep, NB); DN(hb->b_timer, d->r_b_timer, 4 * NB);
+#undef DN
+    BBX_CUDA(d, cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int bbx_dev_stats(BbxDev* d, BallboxStats* out)
+{
+    if (!d || !out) return BBX_ERR_BAD_ARGUMENT;
+    memset(out, 0, sizeof(*out));
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    GridParams gp;
+    BBX_CUDA(d, cudaMemcpy(&gp, d->grid, sizeof(gp), cudaMemcpyDeviceToHost));
+    const StepCounters* c = d->ctr_host;
+    out->steps = d->steps; out->body_steps = d->body_steps; out->kernel_launches = d->launches;
+    out->spheres = d->n_valid_spheres; out->boxes = d->n_valid_boxes;
+    out->candidate_pairs = c->n_ss_tests + c->n_cand_sb + c->n_cand_bb;
+    out->contacts = c->n_contacts; out->solver_contacts = c->n_solver; out->touched_bodies = c->n_touched;
+    out->levels = c->n_levels; out->overflow = c->overflow | (gp.overflow ? 4 : 0); out->grid_cells = gp.n_cells;
+    out->reserved[0] = c->n_cand_sb; out->reserved[1] = c->n_cand_bb; out->reserved[2] = c->n_ss_tests;
+    out->reserved[3] = c->n_big; out->reserved[4] = c->n_events;
+    return 0;
+}

@@ -1,0 +1,125 @@
+// bbx_step.cu -- the step driver (reference PhysicsStep, ballbox.h:1787-1817) and
+// the export of world->constraints in the reference's emission order.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "bbx_dev.cuh"
+
+extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
+{
+    if (!d || !p) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (steps <= 0) return 0;
+    if (p->dt <= 0.0f || p->dt < 1e-6f) return 0;                    // ballbox.h:1791
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    d->last_params = *p; d->have_params = 1;
+    BbxStepParams q = *p;
+    for (int s = 0; s < steps; s++) {
+        int rc;
+        if ((rc = bbx_stage_integrate_velocities(d, &q))) return rc;   // stages 1-2
+        if ((rc = bbx_stage_broadphase(d, &q))) return rc;             // stage 3: pair finding (+ sphere-sphere)
+        if ((rc = bbx_stage_narrowphase(d, &q))) return rc;            // stage 3: contact generation
+        if ((rc = bbx_stage_solve(d, &q))) return rc;                  // stage 4
+        if ((rc = bbx_stage_integrate_positions(d, &q))) return rc;    // stages 5-6
+        q.has_forces = 0;                                              // forces were consumed and cleared by step 0
+        d->steps++;
+        d->body_steps += (long long)d->n_valid_spheres + d->n_valid_boxes;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// export of the constraint list (reference layout, 104-byte records)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void split_gid(const BbxDev& dv, int g, int& type, int& world, int& local)
+{
+    if (g < 0) { type = 2; world = -1; local = 0; return; }
+    if (g < dv.NS) { type = 0; world = g / dv.cap_s; local = g - world * dv.cap_s; }
+    else { int b = g - dv.NS; type = 1; world = b / dv.cap_b; local = b - world * dv.cap_b; }
+}
+
+__global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactConstraint* out, unsigned long long* keys,
+                                                            float restitution, float friction, int solved)
+{
+    int n = min(dv.ctr->n_contacts, dv.cap_contacts);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        int4 id = dv.c_ids[c];
+        float4 pt = dv.c_pt[c], nr = dv.c_nrm[c];
+        float4 l0 = dv.L0[c], l1 = dv.L1[c], l2 = dv.L2[c], l3 = dv.L3[c];
+        int ta, wa, la, tb, wb, lb;
+        split_gid(dv, id.x, ta, wa, la);
+        split_gid(dv, id.y, tb, wb, lb);
+        float3 n3 = make_float3(nr.x, nr.y, nr.z), t1, t2;
+        if (fabsf(n3.x) >= 0.57735f) t1 = f3(n3.y, -n3.x, 0.0f); else t1 = f3(0.0f, n3.z, -n3.y);
+        t1 = v3norm(t1);
+        t2 = v3cross(n3, t1);
+        float jn = 0.0f, jt0 = 0.0f, jt1 = 0.0f;
+        int slot = solved ? dv.slot_of[c] : -1;
+        if (slot >= 0) { float4 m3 = dv.M3[slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
+        else if (solved && friction > 0.0f) {
+            // a constraint between two non-dynamic bodies is never scheduled, but the reference still
+            // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477)
+            jt0 = -0.0f; jt1 = -0.0f;
+        }
+        ContactConstraint r;
+        r.bodyA_type = ta; r.bodyA_index = la; r.bodyB_type = tb; r.bodyB_index = lb;
+        r.contact_point.x = pt.x; r.contact_point.y = pt.y; r.contact_point.z = pt.z;
+        r.contact_normal.x = nr.x; r.contact_normal.y = nr.y; r.contact_normal.z = nr.z;
+        r.penetration = pt.w;
+        r.normal_mass = l1.w; r.tangent_mass[0] = l2.w; r.tangent_mass[1] = l3.w;
+        r.tangent[0].x = t1.x; r.tangent[0].y = t1.y; r.tangent[0].z = t1.z;
+        r.tangent[1].x = t2.x; r.tangent[1].y = t2.y; r.tangent[1].z = t2.z;
+        r.normal_impulse = jn; r.tangent_impulse[0] = jt0; r.tangent_impulse[1] = jt1;
+        r.position_bias = l0.w; r.restitution = restitution; r.friction = friction;
+        out[c] = r;
+        // emission order: world, phase, i, j, k  
+        unsigned long long i = (unsigned long long)la, j = (unsigned long long)lb, k = (unsigned long long)id.z;
+        unsigned long long key;
+        if (dv.n_worlds == 1) key = ((unsigned long long)id.w << 53) | (i << 29) | (j << 5) | k;
+        else key = ((unsigned long long)wa << 51) | ((unsigned long long)id.w << 48) | (i << 26) | (j << 5) | k;
+        keys[c] = key;
+    }
+}
+
+extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, int cap_per_world, int* counts)
+{
+    if (!d || !out || !counts) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    for (int w = 0; w < d->n_worlds; w++) counts[w] = 0;
+    if (!d->have_params) return 0;
+    if (d->n_worlds > 1 && (d->cap_s >= (1 << 21) || d->cap_b >= (1 << 21)))
+        return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "batched export supports < 2^21 bodies per world", __FILE__, __LINE__);
+    if (!d->export_buf) BBX_CUDA(d, cudaMalloc((void**)&d->export_buf, sizeof(ContactConstraint) * (size_t)d->cap_contacts));
+    const BbxStepParams* p = &d->last_params;
+    BBX_LAUNCH(d, k_export_constraints, BBX_NUM_SMS * 8, 256, 0, *d, d->export_buf, d->sort_keys,
+               p->settings.restitution, p->settings.friction, p->settings.solver_iterations > 0 ? 1 : 0);
+    BBX_CUDA(d, cudaGetLastError());
+    BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    if (d->ctr_host->overflow & 3)
+        return bbx_fail(d, BBX_ERR_OVERFLOW, "contact or candidate buffer overflow: raise max_collisions", __FILE__, __LINE__);
+    int n = d->ctr_host->n_contacts;
+    if (n > d->cap_contacts) n = d->cap_contacts;
+    if (n == 0) return 0;
+    std::vector<unsigned long long> keys((size_t)n);
+    std::vector<ContactConstraint> recs((size_t)n);
+    BBX_CUDA(d, cudaMemcpyAsync(keys.data(), d->sort_keys, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaMemcpyAsync(recs.data(), d->export_buf, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    std::vector<int> order((size_t)n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+    int truncated = 0;
+    for (int t = 0; t < n; t++) {
+        int c = order[t];
+        int w = (d->n_worlds == 1) ? 0 : (int)(keys[c] >> 51);
+        if (counts[w] < cap_per_world) out[(size_t)w * cap_per_world + counts[w]++] = recs[c];
+        else truncated = 1;
+    }
+    if (truncated)
+        return bbx_fail(d, BBX_ERR_OVERFLOW, "a world produced more contacts than max_collisions", __FILE__, __LINE__);
+    return 0;
+}

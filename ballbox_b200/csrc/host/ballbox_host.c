@@ -1,0 +1,788 @@
+/*
+ * ballbox_host.c -- the C host library behind ballbox.h.
+ *
+ * Owns the public structs (identical layouts) and the host SoA
+ * arrays users read and write directly; forwards PhysicsStep to the C-ABI CUDA
+ * layer (bbx_cuda.h).  There is NO CPU implementation of the step in this
+ * library: without a CUDA device PhysicsStep records an error and prints it.
+ *
+ * Reference for behaviour: world/body management ballbox.h:301-445, :642-818,
+ * :1629-1693; settings :2483-2544; error convention SURVEY.md section 8b
+ * (NULL / -1 / silent return).
+ *
+ * Every world is a batch of n >= 1 worlds internally: the host arrays of all
+ * worlds of a batch are slices of one pinned allocation, so an upload is one
+ * DMA per array whatever the number of worlds.
+ */
+#include <stdint.h>
+#include "ballbox.h"
+#include "bbx_cuda.h"
+
+#define BBX_MAGIC 0xBA11B0C5u
+
+struct BbxWorldPriv;
+
+struct PhysicsWorldBatch {
+    uint32_t magic;
+    int n_worlds, cap_s, cap_b, cap_c;
+    int single;                         /* created by CreatePhysicsWorld */
+    struct BbxWorldPriv* worlds;
+    /* one allocation per field, n_worlds * cap records */
+    BbxHostBodies hb;
+    int *s_count, *b_count;
+    OnCollision *s_cb, *b_cb;
+    ContactConstraint* constraints;     /* n_worlds * cap_c */
+    int* ccount;
+    int pinned[32];
+    int pinned_constraints;
+    BbxDev* dev;
+    int device;
+    void* stream;
+    int sync_mode, schedule;
+    int sdf_id; float sdf_params[8];
+    int uploaded, forces_dirty, n_callbacks;
+    int has_err; char err[256];
+};
+
+typedef struct BbxWorldPriv {
+    PhysicsWorld pub;                   /* MUST be first: users hold &pub */
+    uint32_t magic;
+    struct PhysicsWorldBatch* batch;
+    int index;
+    SphereSystem spheres;
+    BoxSystem boxes;
+    CollisionCollection collisions;
+    ConstraintCollection constraints;
+} BbxWorldPriv;
+
+/* ------------------------------------------------------------------------- */
+/* small math, reference ballbox.h:501-639                                   */
+/* ------------------------------------------------------------------------- */
+Vec3 Vec3Add(Vec3 a, Vec3 b) { Vec3 r; r.x = a.x + b.x; r.y = a.y + b.y; r.z = a.z + b.z; return r; }
+Vec3 Vec3Sub(Vec3 a, Vec3 b) { Vec3 r; r.x = a.x - b.x; r.y = a.y - b.y; r.z = a.z - b.z; return r; }
+Vec3 Vec3Scale(Vec3 v, float s) { Vec3 r; r.x = v.x * s; r.y = v.y * s; r.z = v.z * s; return r; }
+float Vec3Dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+Vec3 Vec3Cross(Vec3 a, Vec3 b)
+{
+    Vec3 r;
+    r.x = a.y * b.z - a.z * b.y;
+    r.y = a.z * b.x - a.x * b.z;
+    r.z = a.x * b.y - a.y * b.x;
+    return r;
+}
+float Vec3Length(Vec3 v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
+Vec3 Vec3Normalize(Vec3 v)
+{
+    float len = Vec3Length(v);
+    Vec3 zero = {0.0f, 0.0f, 0.0f};
+    return (len < 1e-6f) ? zero : Vec3Scale(v, 1.0f / len);
+}
+Quat QuatIdentity(void) { Quat q = {0.0f, 0.0f, 0.0f, 1.0f}; return q; }
+Quat QuatMultiply(Quat a, Quat b)
+{
+    Quat r;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+    r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    return r;
+}
+Quat QuatNormalize(Quat q)
+{
+    float len = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    if (len == 0.0f) return QuatIdentity();
+    Quat r = { q.x / len, q.y / len, q.z / len, q.w / len };
+    return r;
+}
+Quat QuatConjugate(Quat q) { Quat r = { -q.x, -q.y, -q.z, q.w }; return r; }
+Quat QuatFromAxisAngle(Vec3 axis, float angle)
+{
+    Vec3 n = Vec3Scale(axis, 1.0f / sqrtf(Vec3Dot(axis, axis)));
+    float half = angle * 0.5f;
+    float s = sinf(half);
+    Quat r = { n.x * s, n.y * s, n.z * s, cosf(half) };
+    return r;
+}
+Quat QuatFromEuler(float pitch, float yaw, float roll)
+{
+    float hp = pitch * 0.5f, hy = yaw * 0.5f, hr = roll * 0.5f;
+    float cp = cosf(hp), sp = sinf(hp), cy = cosf(hy), sy = sinf(hy), cr = cosf(hr), sr = sinf(hr);
+    Quat r;
+    r.x = sp * cy * cr - cp * sy * sr;
+    r.y = cp * sy * cr + sp * cy * sr;
+    r.z = cp * cy * sr - sp * sy * cr;
+    r.w = cp * cy * cr + sp * sy * sr;
+    return r;
+}
+void QuatToAxisAngle(Quat q, Vec3* axis, float* angle)
+{
+    q = QuatNormalize(q);
+    if (fabsf(q.w) >= 1.0f) { *angle = 0.0f; axis->x = 0.0f; axis->y = 1.0f; axis->z = 0.0f; return; }
+    *angle = 2.0f * acosf(q.w);
+    float sh = sqrtf(1.0f - q.w * q.w);
+    if (sh < 1e-6f) { axis->x = 0.0f; axis->y = 1.0f; axis->z = 0.0f; }
+    else { axis->x = q.x / sh; axis->y = q.y / sh; axis->z = q.z / sh; }
+}
+Vec3 QuatRotateVec3(Quat q, Vec3 v)
+{
+    Vec3 u = { q.x, q.y, q.z };
+    float s = q.w;
+    Vec3 a = Vec3Scale(v, s * s - Vec3Dot(u, u));
+    Vec3 b = Vec3Scale(u, 2.0f * Vec3Dot(u, v));
+    Vec3 c = Vec3Scale(Vec3Cross(u, v), 2.0f * s);
+    return Vec3Add(Vec3Add(a, b), c);
+}
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                   */
+/* ------------------------------------------------------------------------- */
+static BbxWorldPriv* priv_of(PhysicsWorld* w)
+{
+    BbxWorldPriv* p = (BbxWorldPriv*)w;
+    return (p && p->magic == BBX_MAGIC) ? p : NULL;
+}
+
+static void batch_fail(struct PhysicsWorldBatch* b, const char* msg)
+{
+    if (!b || b->has_err) return;
+    snprintf(b->err, sizeof(b->err), "%s", msg);
+    b->has_err = 1;
+    fprintf(stderr, "ballbox-b200: %s\n", msg);
+}
+
+static int batch_check_dev(struct PhysicsWorldBatch* b, int rc)
+{
+    if (rc == 0) return 0;
+    const char* e = b->dev ? bbx_dev_error(b->dev) : NULL;
+    batch_fail(b, e ? e : "CUDA layer call failed");
+    return rc;
+}
+
+static void* arr_alloc(struct PhysicsWorldBatch* b, int slot, size_t bytes) { return bbx_host_alloc(bytes, &b->pinned[slot]); }
+
+/* ------------------------------------------------------------------------- */
+/* batch / world lifetime                                                    */
+/* ------------------------------------------------------------------------- */
+static void settings_defaults(PhysicsSettings* s)          /* values: reference ballbox.h:2487-2514 */
+{
+    s->linear_damping = 0.98f;  s->angular_damping = 0.98f;
+    s->restitution = 0.0f;      s->friction = 0.1f;       s->solver_iterations = 25;
+    s->baumgarte_bias = 0.3f;   s->allowed_penetration = 0.05f;  s->velocity_threshold = 0.02f;
+    s->sleep_linear_threshold = 0.1f; s->sleep_angular_threshold = 0.1f; s->sleep_time_required = 0.05f;
+    s->manifold_contact_tolerance = 0.01f; s->manifold_penetration_tolerance = -0.5f; s->manifold_max_contacts = 8;
+    s->collision_epsilon = 1e-6f; s->sdf_normal_epsilon = 0.001f;
+    s->vector_normalize_epsilon = 1e-6f; s->quaternion_epsilon = 1e-6f;
+}
+
+static void batch_free(struct PhysicsWorldBatch* b)
+{
+    if (!b) return;
+    if (b->dev) bbx_dev_destroy(b->dev);
+    void* arrs[] = { b->hb.s_pos, b->hb.s_radius, b->hb.s_vel, b->hb.s_force, b->hb.s_mass, b->hb.s_angvel,
+                     b->hb.s_torque, b->hb.s_inertia, b->hb.s_timer, b->hb.s_static, b->hb.s_sleep, b->hb.s_hascb,
+                     b->hb.b_pos, b->hb.b_size, b->hb.b_rot, b->hb.b_vel, b->hb.b_force, b->hb.b_mass, b->hb.b_angvel,
+                     b->hb.b_torque, b->hb.b_inertia, b->hb.b_timer, b->hb.b_static, b->hb.b_sleep, b->hb.b_hascb };
+    for (int i = 0; i < 25; i++) bbx_host_free(arrs[i], b->pinned[i]);
+    bbx_host_free(b->constraints, b->pinned_constraints);
+    if (b->worlds) for (int w = 0; w < b->n_worlds; w++) free(b->worlds[w].collisions.contacts);
+    free(b->s_count); free(b->b_count); free(b->s_cb); free(b->b_cb); free(b->ccount); free(b->worlds);
+    b->magic = 0;
+    free(b);
+}
+
+static struct PhysicsWorldBatch* batch_create(int n, int max_s, int max_b, int max_c, int single)
+{
+    if (n < 1 || max_s < 0 || max_b < 0 || max_c < 0) return NULL;
+    struct PhysicsWorldBatch* b = (struct PhysicsWorldBatch*)calloc(1, sizeof(*b));
+    if (!b) return NULL;
+    b->magic = BBX_MAGIC; b->n_worlds = n; b->cap_s = max_s; b->cap_b = max_b; b->cap_c = max_c; b->single = single;
+    size_t NS = (size_t)n * max_s, NB = (size_t)n * max_b;
+    BbxHostBodies* h = &b->hb;
+    h->n_worlds = n; h->cap_s = max_s; h->cap_b = max_b;
+    int k = 0;
+    h->s_pos = arr_alloc(b, k++, 12 * NS);    h->s_radius = arr_alloc(b, k++, 4 * NS);  h->s_vel = arr_alloc(b, k++, 12 * NS);
+    h->s_force = arr_alloc(b, k++, 12 * NS);  h->s_mass = arr_alloc(b, k++, 4 * NS);    h->s_angvel = arr_alloc(b, k++, 12 * NS);
+    h->s_torque = arr_alloc(b, k++, 12 * NS); h->s_inertia = arr_alloc(b, k++, 4 * NS); h->s_timer = arr_alloc(b, k++, 4 * NS);
+    h->s_static = arr_alloc(b, k++, NS);      h->s_sleep = arr_alloc(b, k++, NS);       h->s_hascb = arr_alloc(b, k++, NS);
+    h->b_pos = arr_alloc(b, k++, 12 * NB);    h->b_size = arr_alloc(b, k++, 12 * NB);   h->b_rot = arr_alloc(b, k++, 16 * NB);
+    h->b_vel = arr_alloc(b, k++, 12 * NB);    h->b_force = arr_alloc(b, k++, 12 * NB);  h->b_mass = arr_alloc(b, k++, 4 * NB);
+    h->b_angvel = arr_alloc(b, k++, 12 * NB); h->b_torque = arr_alloc(b, k++, 12 * NB); h->b_inertia = arr_alloc(b, k++, 12 * NB);
+    h->b_timer = arr_alloc(b, k++, 4 * NB);   h->b_static = arr_alloc(b, k++, NB);      h->b_sleep = arr_alloc(b, k++, NB);
+    h->b_hascb = arr_alloc(b, k++, NB);
+    b->s_count = (int*)calloc((size_t)n, sizeof(int)); b->b_count = (int*)calloc((size_t)n, sizeof(int));
+    b->ccount = (int*)calloc((size_t)n, sizeof(int));
+    h->s_count = b->s_count; h->b_count = b->b_count;
+    b->s_cb = (OnCollision*)calloc(NS ? NS : 1, sizeof(OnCollision));
+    b->b_cb = (OnCollision*)calloc(NB ? NB : 1, sizeof(OnCollision));
+    b->constraints = (ContactConstraint*)bbx_host_alloc(sizeof(ContactConstraint) * (size_t)n * (size_t)(max_c ? max_c : 1),
+                                                        &b->pinned_constraints);
+    b->worlds = (BbxWorldPriv*)calloc((size_t)n, sizeof(BbxWorldPriv));
+    int ok = h->s_pos && h->s_radius && h->s_vel && h->s_force && h->s_mass && h->s_angvel && h->s_torque && h->s_inertia &&
+             h->s_timer && h->s_static && h->s_sleep && h->s_hascb && h->b_pos && h->b_size && h->b_rot && h->b_vel &&
+             h->b_force && h->b_mass && h->b_angvel && h->b_torque && h->b_inertia && h->b_timer && h->b_static &&
+             h->b_sleep && h->b_hascb && b->s_count && b->b_count && b->ccount && b->s_cb && b->b_cb && b->constraints && b->worlds;
+    if (!ok) { batch_free(b); return NULL; }
+
+    /* constructor defaults of the reference (ballbox.h:327-340, :670-684) */
+    for (size_t i = 0; i < NS; i++) { h->s_radius[i] = 1.0f; h->s_mass[i] = 1.0f; h->s_inertia[i] = 1.0f; }
+    for (size_t i = 0; i < NB; i++) {
+        h->b_size[3 * i] = h->b_size[3 * i + 1] = h->b_size[3 * i + 2] = 1.0f;
+        h->b_rot[4 * i + 3] = 1.0f; h->b_mass[i] = 1.0f;
+        h->b_inertia[3 * i] = h->b_inertia[3 * i + 1] = h->b_inertia[3 * i + 2] = 1.0f / 6.0f;
+    }
+    for (int w = 0; w < n; w++) {
+        BbxWorldPriv* p = &b->worlds[w];
+        p->magic = BBX_MAGIC; p->batch = b; p->index = w;
+        size_t so = (size_t)w * max_s, bo = (size_t)w * max_b;
+        SphereSystem* s = &p->spheres;
+        s->positions = (Vec3*)h->s_pos + so; s->radii = h->s_radius + so; s->velocities = (Vec3*)h->s_vel + so;
+        s->forces = (Vec3*)h->s_force + so; s->masses = h->s_mass + so; s->angular_velocities = (Vec3*)h->s_angvel + so;
+        s->torques = (Vec3*)h->s_torque + so; s->inertias = h->s_inertia + so; s->is_static = (bool*)h->s_static + so;
+        s->is_sleeping = (bool*)h->s_sleep + so; s->sleep_timers = h->s_timer + so; s->collision_callbacks = b->s_cb + so;
+        s->count = 0; s->capacity = max_s;
+        BoxSystem* x = &p->boxes;
+        x->positions = (Vec3*)h->b_pos + bo; x->sizes = (Vec3*)h->b_size + bo; x->rotations = (Quat*)h->b_rot + bo;
+        x->velocities = (Vec3*)h->b_vel + bo; x->forces = (Vec3*)h->b_force + bo; x->masses = h->b_mass + bo;
+        x->angular_velocities = (Vec3*)h->b_angvel + bo; x->torques = (Vec3*)h->b_torque + bo;
+        x->inertias = (Vec3*)h->b_inertia + bo; x->is_static = (bool*)h->b_static + bo;
+        x->is_sleeping = (bool*)h->b_sleep + bo; x->sleep_timers = h->b_timer + bo; x->collision_callbacks = b->b_cb + bo;
+        x->count = 0; x->capacity = max_b;
+        p->collisions.contacts = (CollisionContact*)calloc((size_t)(max_c ? max_c : 1), sizeof(CollisionContact));
+        p->collisions.count = 0; p->collisions.capacity = max_c;
+        p->constraints.constraints = b->constraints + (size_t)w * max_c;
+        p->constraints.count = 0; p->constraints.capacity = max_c;
+        if (!p->collisions.contacts) { batch_free(b); return NULL; }
+        PhysicsWorld* pw = &p->pub;
+        pw->spheres = s; pw->boxes = x; pw->collisions = &p->collisions; pw->constraints = &p->constraints;
+        pw->gravity.x = pw->gravity.y = pw->gravity.z = 0.0f;         /* ballbox.h:1653 */
+        pw->dt = 1.0f / 60.0f; pw->usesSDF = false; pw->SDFCollider = NULL;
+        settings_defaults(&pw->settings);
+    }
+    return b;
+}
+
+PhysicsWorld* CreatePhysicsWorld(int max_spheres, int max_boxes, int max_collisions)
+{
+    struct PhysicsWorldBatch* b = batch_create(1, max_spheres, max_boxes, max_collisions, 1);
+    return b ? &b->worlds[0].pub : NULL;
+}
+
+void DestroyPhysicsWorld(PhysicsWorld* world)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return;
+    if (p->batch->single) batch_free(p->batch);      /* worlds of a real batch die with the batch */
+}
+
+PhysicsWorldBatch* CreatePhysicsWorldBatch(int n_worlds, int max_spheres, int max_boxes, int max_collisions)
+{
+    return batch_create(n_worlds, max_spheres, max_boxes, max_collisions, 0);
+}
+void DestroyPhysicsWorldBatch(PhysicsWorldBatch* b) { if (b && b->magic == BBX_MAGIC) batch_free(b); }
+int  BatchWorldCount(PhysicsWorldBatch* b) { return (b && b->magic == BBX_MAGIC) ? b->n_worlds : 0; }
+PhysicsWorld* BatchWorld(PhysicsWorldBatch* b, int i)
+{
+    if (!b || b->magic != BBX_MAGIC || i < 0 || i >= b->n_worlds) return NULL;
+    return &b->worlds[i].pub;
+}
+
+void UseSDF(PhysicsWorld* world, SDFFunction fn)                      /* ballbox.h:1688-1693 */
+{
+    if (!world) return;
+    world->SDFCollider = fn;
+    world->usesSDF = (fn != NULL);
+}
+
+void UseSDFDevice(PhysicsWorld* world, int sdf_id, const float* params8)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return;
+    p->batch->sdf_id = sdf_id;
+    for (int i = 0; i < 8; i++) p->batch->sdf_params[i] = params8 ? params8[i] : 0.0f;
+    world->usesSDF = (sdf_id != BBX_SDF_NONE) || (world->SDFCollider != NULL);
+}
+
+/* ------------------------------------------------------------------------- */
+/* settings, reference ballbox.h:2483-2544                                   */
+/* ------------------------------------------------------------------------- */
+void ResetPhysicsSettingsToDefaults(PhysicsWorld* w) { if (w) settings_defaults(&w->settings); }
+void SetDamping(PhysicsWorld* w, float l, float a) { if (!w) return; w->settings.linear_damping = l; w->settings.angular_damping = a; }
+void SetRestitution(PhysicsWorld* w, float r) { if (w) w->settings.restitution = r; }
+void SetCorrectionParameters(PhysicsWorld* w, float bias, float allowed)
+{
+    if (!w) return;
+    w->settings.baumgarte_bias = bias; w->settings.allowed_penetration = allowed;
+}
+void SetSolverIterations(PhysicsWorld* w, int it) { if (w) w->settings.solver_iterations = it; }
+void SetManifoldSettings(PhysicsWorld* w, float tol, float pen_tol, int max_contacts)
+{
+    if (!w) return;
+    w->settings.manifold_contact_tolerance = tol;
+    w->settings.manifold_penetration_tolerance = pen_tol;
+    w->settings.manifold_max_contacts = max_contacts > MAX_MANIFOLD_CONTACTS ? MAX_MANIFOLD_CONTACTS : max_contacts;
+}
+
+/* ------------------------------------------------------------------------- */
+/* bodies, reference ballbox.h:363-445, :708-818                             */
+/* ------------------------------------------------------------------------- */
+static const Vec3 V0 = {0.0f, 0.0f, 0.0f};
+
+static void note_count(PhysicsWorld* w)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return;
+    p->batch->s_count[p->index] = p->spheres.count;
+    p->batch->b_count[p->index] = p->boxes.count;
+    p->batch->uploaded = 0;             /* topology changed: resident state must be re-uploaded */
+}
+
+int AddSphere(PhysicsWorld* world, Vec3 position, float radius)
+{
+    if (!world || !world->spheres) return -1;
+    SphereSystem* s = world->spheres;
+    if (s->count >= s->capacity) return -1;
+    int i = s->count;
+    s->positions[i] = position; s->radii[i] = radius;
+    s->velocities[i] = V0; s->forces[i] = V0; s->angular_velocities[i] = V0; s->torques[i] = V0;
+    s->masses[i] = 1.0f;
+    s->inertias[i] = (2.0f / 5.0f) * s->masses[i] * radius * radius;
+    s->count++;
+    note_count(world);
+    return i;
+}
+
+void SetSphereMass(PhysicsWorld* world, int i, float mass)
+{
+    if (!world || !world->spheres) return;
+    SphereSystem* s = world->spheres;
+    if (i < 0 || i >= s->count || mass <= 0.0f) return;
+    s->masses[i] = mass;
+    float r = s->radii[i];
+    s->inertias[i] = (2.0f / 5.0f) * mass * r * r;
+}
+
+void SetSphereStatic(PhysicsWorld* world, int i, bool is_static)
+{
+    if (!world || !world->spheres) return;
+    SphereSystem* s = world->spheres;
+    if (i < 0 || i >= s->count) return;
+    s->is_static[i] = is_static;
+    if (is_static) { s->velocities[i] = V0; s->angular_velocities[i] = V0; s->forces[i] = V0; s->torques[i] = V0; }
+}
+
+static void mark_forces(PhysicsWorld* w) { BbxWorldPriv* p = priv_of(w); if (p) p->batch->forces_dirty = 1; }
+
+void AddSphereForce(PhysicsWorld* world, int i, Vec3 f)
+{
+    if (!world || !world->spheres) return;
+    SphereSystem* s = world->spheres;
+    if (i < 0 || i >= s->count) return;
+    if (s->is_sleeping[i]) { s->is_sleeping[i] = false; s->sleep_timers[i] = 0.0f; }
+    s->forces[i] = Vec3Add(s->forces[i], f);
+    mark_forces(world);
+}
+
+void AddSphereTorque(PhysicsWorld* world, int i, Vec3 t)
+{
+    if (!world || !world->spheres) return;
+    SphereSystem* s = world->spheres;
+    if (i < 0 || i >= s->count) return;
+    if (s->is_sleeping[i]) { s->is_sleeping[i] = false; s->sleep_timers[i] = 0.0f; }
+    s->torques[i] = Vec3Add(s->torques[i], t);
+    mark_forces(world);
+}
+
+static Vec3 box_inertia(float m, Vec3 half)
+{
+    float w = half.x * 2.0f, h = half.y * 2.0f, d = half.z * 2.0f;
+    Vec3 I = { (m / 12.0f) * (h * h + d * d), (m / 12.0f) * (w * w + d * d), (m / 12.0f) * (w * w + h * h) };
+    return I;
+}
+
+int AddBox(PhysicsWorld* world, Vec3 position, Vec3 size, Quat rotation)
+{
+    if (!world || !world->boxes) return -1;
+    BoxSystem* b = world->boxes;
+    if (b->count >= b->capacity) return -1;
+    int i = b->count;
+    b->positions[i] = position; b->sizes[i] = size; b->rotations[i] = rotation;
+    b->velocities[i] = V0; b->forces[i] = V0; b->angular_velocities[i] = V0; b->torques[i] = V0;
+    b->masses[i] = 1.0f;
+    b->inertias[i] = box_inertia(b->masses[i], size);
+    b->is_static[i] = false; b->is_sleeping[i] = false; b->sleep_timers[i] = 0.0f;
+    b->count++;
+    note_count(world);
+    return i;
+}
+
+void SetBoxMass(PhysicsWorld* world, int i, float mass)
+{
+    if (!world || !world->boxes) return;
+    BoxSystem* b = world->boxes;
+    if (i < 0 || i >= b->count || mass <= 0.0f) return;
+    b->masses[i] = mass;
+    b->inertias[i] = box_inertia(mass, b->sizes[i]);
+}
+
+void SetBoxStatic(PhysicsWorld* world, int i, bool is_static)
+{
+    if (!world || !world->boxes) return;
+    BoxSystem* b = world->boxes;
+    if (i < 0 || i >= b->count) return;
+    b->is_static[i] = is_static;
+    if (is_static) { b->velocities[i] = V0; b->angular_velocities[i] = V0; b->forces[i] = V0; b->torques[i] = V0; }
+}
+
+void AddBoxForce(PhysicsWorld* world, int i, Vec3 f)
+{
+    if (!world || !world->boxes) return;
+    BoxSystem* b = world->boxes;
+    if (i < 0 || i >= b->count) return;
+    if (b->is_sleeping[i]) { b->is_sleeping[i] = false; b->sleep_timers[i] = 0.0f; }
+    b->forces[i] = Vec3Add(b->forces[i], f);
+    mark_forces(world);
+}
+
+void AddBoxTorque(PhysicsWorld* world, int i, Vec3 t)
+{
+    if (!world || !world->boxes) return;
+    BoxSystem* b = world->boxes;
+    if (i < 0 || i >= b->count) return;
+    if (b->is_sleeping[i]) { b->is_sleeping[i] = false; b->sleep_timers[i] = 0.0f; }
+    b->torques[i] = Vec3Add(b->torques[i], t);
+    mark_forces(world);
+}
+
+static void recount_callbacks(struct PhysicsWorldBatch* b)
+{
+    int n = 0;
+    size_t NS = (size_t)b->n_worlds * b->cap_s, NB = (size_t)b->n_worlds * b->cap_b;
+    for (size_t i = 0; i < NS; i++) { b->hb.s_hascb[i] = b->s_cb[i] != NULL; n += b->hb.s_hascb[i]; }
+    for (size_t i = 0; i < NB; i++) { b->hb.b_hascb[i] = b->b_cb[i] != NULL; n += b->hb.b_hascb[i]; }
+    b->n_callbacks = n;
+}
+
+void SetSphereCollisionCallback(PhysicsWorld* world, int i, OnCollision cb)
+{
+    if (!world || !world->spheres || i < 0 || i >= world->spheres->count) return;
+    world->spheres->collision_callbacks[i] = cb;
+    BbxWorldPriv* p = priv_of(world);
+    if (p) recount_callbacks(p->batch);
+}
+
+void SetBoxCollisionCallback(PhysicsWorld* world, int i, OnCollision cb)
+{
+    if (!world || !world->boxes || i < 0 || i >= world->boxes->count) return;
+    world->boxes->collision_callbacks[i] = cb;
+    BbxWorldPriv* p = priv_of(world);
+    if (p) recount_callbacks(p->batch);
+}
+
+/* standalone systems and constraint collections (API completeness; ballbox.h:301-361, :642-706, :1138-1170) */
+SphereSystem* CreateSphereSystem(int capacity)
+{
+    if (capacity < 0) return NULL;
+    SphereSystem* s = (SphereSystem*)calloc(1, sizeof(SphereSystem));
+    if (!s) return NULL;
+    size_t n = capacity ? (size_t)capacity : 1;
+    s->positions = calloc(n, sizeof(Vec3)); s->radii = calloc(n, 4); s->velocities = calloc(n, sizeof(Vec3));
+    s->forces = calloc(n, sizeof(Vec3)); s->masses = calloc(n, 4); s->angular_velocities = calloc(n, sizeof(Vec3));
+    s->torques = calloc(n, sizeof(Vec3)); s->inertias = calloc(n, 4); s->is_static = calloc(n, 1);
+    s->is_sleeping = calloc(n, 1); s->sleep_timers = calloc(n, 4); s->collision_callbacks = calloc(n, sizeof(OnCollision));
+    s->capacity = capacity;
+    if (!s->positions || !s->radii || !s->velocities || !s->forces || !s->masses || !s->angular_velocities || !s->torques ||
+        !s->inertias || !s->is_static || !s->is_sleeping || !s->sleep_timers || !s->collision_callbacks) {
+        DestroySphereSystem(s); return NULL;
+    }
+    for (int i = 0; i < capacity; i++) { s->radii[i] = 1.0f; s->masses[i] = 1.0f; s->inertias[i] = 1.0f; }
+    return s;
+}
+void DestroySphereSystem(SphereSystem* s)
+{
+    if (!s) return;
+    free(s->positions); free(s->radii); free(s->velocities); free(s->forces); free(s->masses); free(s->angular_velocities);
+    free(s->torques); free(s->inertias); free(s->is_static); free(s->is_sleeping); free(s->sleep_timers);
+    free(s->collision_callbacks); free(s);
+}
+BoxSystem* CreateBoxSystem(int capacity)
+{
+    if (capacity < 0) return NULL;
+    BoxSystem* b = (BoxSystem*)calloc(1, sizeof(BoxSystem));
+    if (!b) return NULL;
+    size_t n = capacity ? (size_t)capacity : 1;
+    b->positions = calloc(n, sizeof(Vec3)); b->sizes = calloc(n, sizeof(Vec3)); b->rotations = calloc(n, sizeof(Quat));
+    b->velocities = calloc(n, sizeof(Vec3)); b->forces = calloc(n, sizeof(Vec3)); b->masses = calloc(n, 4);
+    b->angular_velocities = calloc(n, sizeof(Vec3)); b->torques = calloc(n, sizeof(Vec3)); b->inertias = calloc(n, sizeof(Vec3));
+    b->is_static = calloc(n, 1); b->is_sleeping = calloc(n, 1); b->sleep_timers = calloc(n, 4);
+    b->collision_callbacks = calloc(n, sizeof(OnCollision));
+    b->capacity = capacity;
+    if (!b->positions || !b->sizes || !b->rotations || !b->velocities || !b->forces || !b->masses || !b->angular_velocities ||
+        !b->torques || !b->inertias || !b->is_static || !b->is_sleeping || !b->sleep_timers || !b->collision_callbacks) {
+        DestroyBoxSystem(b); return NULL;
+    }
+    for (int i = 0; i < capacity; i++) {
+        Vec3 one = {1.0f, 1.0f, 1.0f}, in = {1.0f / 6.0f, 1.0f / 6.0f, 1.0f / 6.0f};
+        b->sizes[i] = one; b->rotations[i] = QuatIdentity(); b->masses[i] = 1.0f; b->inertias[i] = in;
+    }
+    return b;
+}
+void DestroyBoxSystem(BoxSystem* b)
+{
+    if (!b) return;
+    free(b->positions); free(b->sizes); free(b->rotations); free(b->velocities); free(b->forces); free(b->masses);
+    free(b->angular_velocities); free(b->torques); free(b->inertias); free(b->is_static); free(b->is_sleeping);
+    free(b->sleep_timers); free(b->collision_callbacks); free(b);
+}
+ConstraintCollection* CreateConstraintCollection(int capacity)
+{
+    if (capacity < 0) return NULL;
+    ConstraintCollection* c = (ConstraintCollection*)calloc(1, sizeof(*c));
+    if (!c) return NULL;
+    c->constraints = (ContactConstraint*)calloc(capacity ? (size_t)capacity : 1, sizeof(ContactConstraint));
+    if (!c->constraints) { free(c); return NULL; }
+    c->capacity = capacity;
+    return c;
+}
+void DestroyConstraintCollection(ConstraintCollection* c) { if (c) { free(c->constraints); free(c); } }
+void ClearConstraints(ConstraintCollection* c) { if (c) c->count = 0; }
+
+/* ------------------------------------------------------------------------- */
+/* device plumbing                                                           */
+/* ------------------------------------------------------------------------- */
+static int batch_ensure_dev(struct PhysicsWorldBatch* b)
+{
+    if (b->has_err) return BBX_ERR_STICKY;
+    if (b->dev) return 0;
+    int rc = bbx_dev_create(&b->dev, b->device, b->n_worlds, b->cap_s, b->cap_b, b->cap_c);
+    if (rc) {
+        const char* e = b->dev ? bbx_dev_error(b->dev) : NULL;
+        batch_fail(b, e ? e : (rc == BBX_ERR_NO_DEVICE
+                               ? "no CUDA device: PhysicsStep needs a B200-class GPU (this library has no CPU path)"
+                               : "bbx_dev_create failed"));
+        if (b->dev) { bbx_dev_destroy(b->dev); b->dev = NULL; }
+        return rc;
+    }
+    bbx_dev_set_stream(b->dev, b->stream);
+    return 0;
+}
+
+static int batch_upload(struct PhysicsWorldBatch* b)
+{
+    int rc = batch_ensure_dev(b);
+    if (rc) return rc;
+    for (int w = 0; w < b->n_worlds; w++) { b->s_count[w] = b->worlds[w].spheres.count; b->b_count[w] = b->worlds[w].boxes.count; }
+    rc = batch_check_dev(b, bbx_dev_upload(b->dev, &b->hb));
+    if (!rc) b->uploaded = 1;
+    return rc;
+}
+
+static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, BbxStepParams* p)
+{
+    PhysicsWorld* w0 = &b->worlds[0].pub;
+    memset(p, 0, sizeof(*p));
+    p->gravity[0] = w0->gravity.x; p->gravity[1] = w0->gravity.y; p->gravity[2] = w0->gravity.z;
+    p->dt = dt; p->settings = w0->settings;
+    p->sdf_id = BBX_SDF_NONE;
+    if (w0->usesSDF) {
+        if (b->sdf_id == BBX_SDF_NONE) {
+            /* reference condition is usesSDF && SDFCollider (ballbox.h:2075); a host pointer cannot run on the GPU */
+            if (w0->SDFCollider) {
+                batch_fail(b, "UseSDF(world, host_function): a host function pointer cannot be evaluated on the GPU; "
+                              "select a device SDF with UseSDFDevice (ballbox_ext.h)");
+                return BBX_ERR_HOST_SDF;
+            }
+        } else {
+            p->sdf_id = b->sdf_id;
+            memcpy(p->sdf_params, b->sdf_params, sizeof(p->sdf_params));
+        }
+    }
+    p->solver_schedule = b->schedule;
+    p->has_forces = has_forces;
+    p->want_callbacks = b->n_callbacks > 0;
+    return 0;
+}
+
+static void zero_host_forces(struct PhysicsWorldBatch* b)
+{
+    for (int w = 0; w < b->n_worlds; w++) {
+        BbxWorldPriv* p = &b->worlds[w];
+        memset(p->spheres.forces, 0, sizeof(Vec3) * (size_t)p->spheres.count);
+        memset(p->spheres.torques, 0, sizeof(Vec3) * (size_t)p->spheres.count);
+        memset(p->boxes.forces, 0, sizeof(Vec3) * (size_t)p->boxes.count);
+        memset(p->boxes.torques, 0, sizeof(Vec3) * (size_t)p->boxes.count);
+    }
+    b->forces_dirty = 0;
+}
+
+static int batch_download(struct PhysicsWorldBatch* b, int what)
+{
+    if (!b->dev) return 0;
+    int rc = 0;
+    if (what & BBX_DL_BODIES) rc = batch_check_dev(b, bbx_dev_download(b->dev, &b->hb));
+    if (!rc && (what & BBX_DL_CONSTRAINTS)) {
+        rc = batch_check_dev(b, bbx_dev_download_constraints(b->dev, b->constraints, b->cap_c, b->ccount));
+        if (!rc) for (int w = 0; w < b->n_worlds; w++) b->worlds[w].constraints.count = b->ccount[w];
+    }
+    return rc;
+}
+
+/* Replay the collision callbacks in the reference's firing order (SURVEY.md 3.3;
+ * ballbox.h:1999-2005, :2034-2044, :2063-2069, :2100-2103).  The constraint list
+ * is already in emission order; the contact handed out is a host copy. */
+static void replay_callbacks(BbxWorldPriv* p)
+{
+    ConstraintCollection* cc = &p->constraints;
+    SphereSystem* S = &p->spheres; BoxSystem* B = &p->boxes;
+    int prev_a = -1, prev_b = -1;
+    for (int i = 0; i < cc->count; i++) {
+        ContactConstraint* c = &cc->constraints[i];
+        CollisionContact k;
+        k.bodyA_type = c->bodyA_type; k.bodyA_index = c->bodyA_index; k.bodyB_type = c->bodyB_type; k.bodyB_index = c->bodyB_index;
+        k.contact_point = c->contact_point; k.contact_normal = c->contact_normal; k.penetration = c->penetration;
+        int a = c->bodyA_index, b = c->bodyB_index;
+        if (c->bodyA_type == 0 && c->bodyB_type == 0) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 0, b, &k);
+            if (S->collision_callbacks[b]) S->collision_callbacks[b](b, 0, a, &k);
+        } else if (c->bodyA_type == 1 && c->bodyB_type == 1) {
+            if (a != prev_a || b != prev_b) {                       /* once per pair, first manifold point */
+                if (B->collision_callbacks[a]) B->collision_callbacks[a](a, 1, b, &k);
+                if (B->collision_callbacks[b]) B->collision_callbacks[b](b, 1, a, &k);
+            }
+            prev_a = a; prev_b = b;
+            continue;
+        } else if (c->bodyA_type == 0 && c->bodyB_type == 1) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 1, b, &k);
+            if (B->collision_callbacks[b]) B->collision_callbacks[b](b, 0, a, &k);
+        } else if (c->bodyA_type == 0 && c->bodyB_type == 2) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 2, 0, &k);
+        }                                                           /* box-SDF: no callback in the reference */
+        prev_a = -1; prev_b = -1;
+    }
+}
+
+static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
+{
+    if (b->has_err) return BBX_ERR_STICKY;
+    if (dt <= 0.0f || dt < 1e-6f) return 0;                        /* ballbox.h:1791 */
+    if (steps <= 0) return 0;
+    int rc;
+    for (int w = 0; w < b->n_worlds; w++) b->worlds[w].pub.dt = dt;
+    if (b->sync_mode == BBX_SYNC_COMPAT) {
+        /* drop-in semantics: whatever the user wrote into the host arrays is what the step sees */
+        for (int s = 0; s < steps; s++) {
+            BbxStepParams prm;
+            if ((rc = batch_upload(b))) return rc;
+            if ((rc = fill_params(b, dt, 1, &prm))) return rc;
+            if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, 1)))) return rc;
+            if ((rc = batch_download(b, BBX_DL_BODIES | BBX_DL_CONSTRAINTS))) return rc;
+            zero_host_forces(b);
+            for (int w = 0; w < b->n_worlds; w++) b->worlds[w].collisions.count = 0;       /* ballbox.h:2310 */
+            if (b->n_callbacks > 0) for (int w = 0; w < b->n_worlds; w++) replay_callbacks(&b->worlds[w]);
+        }
+        return 0;
+    }
+    /* resident */
+    if (!b->uploaded && (rc = batch_upload(b))) return rc;
+    if (b->n_callbacks > 0) {
+        /* callbacks need the contact list of every step on the host */
+        for (int s = 0; s < steps; s++) {
+            BbxStepParams prm;
+            int hf = b->forces_dirty;
+            if (hf && (rc = batch_check_dev(b, bbx_dev_upload_forces(b->dev, &b->hb)))) return rc;
+            if ((rc = fill_params(b, dt, hf, &prm))) return rc;
+            if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, 1)))) return rc;
+            if ((rc = batch_download(b, BBX_DL_CONSTRAINTS))) return rc;
+            if (hf) zero_host_forces(b);
+            for (int w = 0; w < b->n_worlds; w++) replay_callbacks(&b->worlds[w]);
+        }
+        return 0;
+    }
+    BbxStepParams prm;
+    int hf = b->forces_dirty;
+    if (hf && (rc = batch_check_dev(b, bbx_dev_upload_forces(b->dev, &b->hb)))) return rc;
+    if ((rc = fill_params(b, dt, hf, &prm))) return rc;
+    rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, steps));
+    if (hf) zero_host_forces(b);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------- */
+/* public stepping API                                                       */
+/* ------------------------------------------------------------------------- */
+void PhysicsStep(PhysicsWorld* world, float deltaTime)              /* ballbox.h:1787 */
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return;
+    if (p->batch->n_worlds != 1) { batch_fail(p->batch, "PhysicsStep on a member of a batch: use PhysicsStepBatch"); return; }
+    batch_step(p->batch, deltaTime, 1);
+}
+
+int PhysicsStepN(PhysicsWorld* world, float dt, int steps)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return BBX_ERR_BAD_ARGUMENT;
+    if (p->batch->n_worlds != 1) { batch_fail(p->batch, "PhysicsStepN on a member of a batch: use PhysicsStepBatch"); return BBX_ERR_BAD_ARGUMENT; }
+    return batch_step(p->batch, dt, steps);
+}
+
+void BallboxSetSyncMode(PhysicsWorld* w, int mode) { BbxWorldPriv* p = priv_of(w); if (p) { p->batch->sync_mode = mode; p->batch->uploaded = 0; } }
+int  BallboxUpload(PhysicsWorld* w) { BbxWorldPriv* p = priv_of(w); return p ? batch_upload(p->batch) : BBX_ERR_BAD_ARGUMENT; }
+int  BallboxDownload(PhysicsWorld* w, int what) { BbxWorldPriv* p = priv_of(w); return p ? batch_download(p->batch, what) : BBX_ERR_BAD_ARGUMENT; }
+int  BallboxSynchronize(PhysicsWorld* w)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return BBX_ERR_BAD_ARGUMENT;
+    return p->batch->dev ? batch_check_dev(p->batch, bbx_dev_synchronize(p->batch->dev)) : 0;
+}
+int  BallboxSetDevice(PhysicsWorld* w, int device)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return BBX_ERR_BAD_ARGUMENT;
+    if (p->batch->dev) { batch_fail(p->batch, "BallboxSetDevice after the device context was created"); return BBX_ERR_BAD_ARGUMENT; }
+    p->batch->device = device;
+    return 0;
+}
+void BallboxSetStream(PhysicsWorld* w, void* stream)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return;
+    p->batch->stream = stream;
+    if (p->batch->dev) bbx_dev_set_stream(p->batch->dev, stream);
+}
+const char* BallboxGetLastError(PhysicsWorld* w) { BbxWorldPriv* p = priv_of(w); return (p && p->batch->has_err) ? p->batch->err : NULL; }
+void BallboxClearError(PhysicsWorld* w)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return;
+    p->batch->has_err = 0; p->batch->err[0] = 0;
+    if (p->batch->dev) bbx_dev_clear_error(p->batch->dev);
+}
+void BallboxSetSolverSchedule(PhysicsWorld* w, int schedule) { BbxWorldPriv* p = priv_of(w); if (p) p->batch->schedule = schedule; }
+int  BallboxGetStats(PhysicsWorld* w, BallboxStats* out)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p || !out) return BBX_ERR_BAD_ARGUMENT;
+    memset(out, 0, sizeof(*out));
+    return p->batch->dev ? batch_check_dev(p->batch, bbx_dev_stats(p->batch->dev, out)) : 0;
+}
+
+static int batch_ok(PhysicsWorldBatch* b) { return b && b->magic == BBX_MAGIC; }
+int  BatchSetDevice(PhysicsWorldBatch* b, int device) { return batch_ok(b) ? BallboxSetDevice(&b->worlds[0].pub, device) : BBX_ERR_BAD_ARGUMENT; }
+void BatchSetStream(PhysicsWorldBatch* b, void* s) { if (batch_ok(b)) BallboxSetStream(&b->worlds[0].pub, s); }
+int  BatchUpload(PhysicsWorldBatch* b) { return batch_ok(b) ? batch_upload(b) : BBX_ERR_BAD_ARGUMENT; }
+int  BatchDownload(PhysicsWorldBatch* b, int what) { return batch_ok(b) ? batch_download(b, what) : BBX_ERR_BAD_ARGUMENT; }
+int  PhysicsStepBatch(PhysicsWorldBatch* b, float dt, int steps)
+{
+    if (!batch_ok(b)) return BBX_ERR_BAD_ARGUMENT;
+    int keep = b->sync_mode;
+    b->sync_mode = BBX_SYNC_RESIDENT;                /* batches are always device resident */
+    int rc = batch_step(b, dt, steps);
+    b->sync_mode = keep;
+    return rc;
+}
+int  BatchSynchronize(PhysicsWorldBatch* b) { return batch_ok(b) ? BallboxSynchronize(&b->worlds[0].pub) : BBX_ERR_BAD_ARGUMENT; }
+int  BatchGetStats(PhysicsWorldBatch* b, BallboxStats* out) { return batch_ok(b) ? BallboxGetStats(&b->worlds[0].pub, out) : BBX_ERR_BAD_ARGUMENT; }
+const char* BatchGetLastError(PhysicsWorldBatch* b) { return (batch_ok(b) && b->has_err) ? b->err : NULL; }
+
+const char* BallboxBackendName(void) { return "ballbox-b200/cuda-sm_100a"; }
+int BallboxDeviceCount(void) { return bbx_device_count(); }

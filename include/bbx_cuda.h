@@ -1,0 +1,89 @@
+/*
+ * bbx_cuda.h -- the thin C-ABI CUDA layer underneath the Ballbox host library.
+ *
+ * Plain pointers and sizes only: no C++ types, no torch types.  The host
+ * library (ballbox_b200/csrc/host/ballbox_host.c) is the only intended caller;
+ * a maintainer of the reference binds the public API in ballbox.h instead (see
+ * INTEGRATION.md).  Every function returns 0 on success or a non-zero code
+ * (a cudaError_t, or BBX_ERR_*); bbx_dev_error() gives the sticky message.
+ *
+ * What each entry point replaces in the reference (ballbox.h file:line):
+ *   bbx_dev_step        PhysicsStep and its seven stages            :1787-1817
+ *                        ApplyForces + IntegrateVelocities           :1820-1925
+ *                        CollectCollisions (all-pairs loops)         :1979-2115
+ *                        sphere/sphere, sphere/box, SAT + manifold   :451-471, :1565-1626, :1040-1132, :2550-2843
+ *                        SDF probing                                 :2074-2114, :2318-2331, :2413-2477
+ *                        SolveConstraints (generate, presolve, GS)   :1176-1226, :1295-1489
+ *                        IntegratePositions, UpdateSleepStates       :1928-1977, :1696-1784
+ *   bbx_dev_upload      the host SoA arrays of SphereSystem/BoxSystem :62-95 -> HBM
+ *   bbx_dev_download    HBM -> the same host arrays
+ *   bbx_dev_download_constraints   world->constraints as left by the step :1176-1211
+ */
+#ifndef BBX_CUDA_H
+#define BBX_CUDA_H
+
+#include "ballbox.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct BbxDev BbxDev;
+
+#define BBX_ERR_NO_DEVICE     10001
+#define BBX_ERR_BAD_ARGUMENT  10002
+#define BBX_ERR_OVERFLOW      10003
+#define BBX_ERR_HOST_SDF      10004
+#define BBX_ERR_STICKY        10005
+
+/* Host arrays of n_worlds worlds laid out back to back with a fixed stride:
+ * world w owns records [w*cap_s, w*cap_s + s_count[w]) of every sphere array
+ * and [w*cap_b, w*cap_b + b_count[w]) of every box array.  A single world is
+ * n_worlds = 1.  Vec3 arrays are 3 floats per record, Quat arrays 4. */
+typedef struct {
+    int n_worlds, cap_s, cap_b;
+    const int* s_count;
+    const int* b_count;
+    float *s_pos, *s_radius, *s_vel, *s_force, *s_mass, *s_angvel, *s_torque, *s_inertia, *s_timer;
+    unsigned char *s_static, *s_sleep, *s_hascb;     /* s_hascb may be NULL */
+    float *b_pos, *b_size, *b_rot, *b_vel, *b_force, *b_mass, *b_angvel, *b_torque, *b_inertia, *b_timer;
+    unsigned char *b_static, *b_sleep, *b_hascb;     /* b_hascb may be NULL */
+} BbxHostBodies;
+
+typedef struct {
+    float gravity[3];
+    float dt;
+    PhysicsSettings settings;      /* by value, re-read at every step like the reference */
+    int   sdf_id;                  /* BBX_SDF_* of ballbox_ext.h; 0 = no SDF              */
+    float sdf_params[8];
+    int   solver_schedule;         /* BBX_SOLVER_EXACT / BBX_SOLVER_COLOURED               */
+    int   has_forces;              /* 0: force/torque arrays are known to be all zero      */
+    int   want_callbacks;          /* collect callback events                              */
+} BbxStepParams;
+
+int  bbx_device_count(void);
+int  bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_spheres, int cap_boxes,
+                    int cap_contacts_per_world);
+void bbx_dev_destroy(BbxDev* dev);
+void bbx_dev_set_stream(BbxDev* dev, void* cuda_stream);
+int  bbx_dev_upload(BbxDev* dev, const BbxHostBodies* hb);
+/* forces and torques only (AddSphereForce & co. between resident steps) */
+int  bbx_dev_upload_forces(BbxDev* dev, const BbxHostBodies* hb);
+int  bbx_dev_step(BbxDev* dev, const BbxStepParams* params, int steps);
+int  bbx_dev_download(BbxDev* dev, const BbxHostBodies* hb);
+/* per world: out + w*cap_per_world receives that world's constraints sorted
+ * into the reference's emission order; counts[w] their number. */
+int  bbx_dev_download_constraints(BbxDev* dev, ContactConstraint* out, int cap_per_world, int* counts);
+int  bbx_dev_synchronize(BbxDev* dev);
+int  bbx_dev_stats(BbxDev* dev, BallboxStats* out);
+const char* bbx_dev_error(BbxDev* dev);          /* NULL when healthy */
+void bbx_dev_clear_error(BbxDev* dev);
+
+/* pinned host memory for the public arrays (falls back to calloc without a device) */
+void* bbx_host_alloc(size_t bytes, int* pinned);
+void  bbx_host_free(void* p, int pinned);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBX_CUDA_H */
