@@ -212,6 +212,12 @@ class BallboxLib:
             d.BallboxSetSolverSchedule.restype = None
             d.BallboxGetStats.argtypes = [WP, C.POINTER(BallboxStats)]
             d.BallboxDeviceCount.restype = C.c_int
+            d.BallboxSetStageTiming.argtypes = [WP, C.c_int]
+            d.BallboxSetStageTiming.restype = None
+            d.BallboxGetStageTiming.argtypes = [WP, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+            d.BatchSetStageTiming.argtypes = [C.c_void_p, C.c_int]
+            d.BatchSetStageTiming.restype = None
+            d.BatchGetStageTiming.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
             d.CreatePhysicsWorldBatch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
             d.CreatePhysicsWorldBatch.restype = C.c_void_p
             d.DestroyPhysicsWorldBatch.argtypes = [C.c_void_p]
@@ -347,6 +353,22 @@ class World:
         s = BallboxStats()
         self.lib.dll.BallboxGetStats(self.ptr, C.byref(s))
         return s
+
+    STAGES = ("integrate_v", "broadphase", "narrowphase", "presolve_graph", "solve_kernel", "integrate_p_sleep")
+
+    def set_stage_timing(self, on=True):
+        self.lib.dll.BallboxSetStageTiming(self.ptr, 1 if on else 0)
+
+    def stage_timing(self):
+        """(dict stage -> summed ms, steps covered) since the last query."""
+        out = (C.c_float * 6)()
+        n = C.c_int()
+        self.lib.dll.BallboxGetStageTiming(self.ptr, out, C.byref(n))
+        self.check()
+        return {k: float(out[i]) for i, k in enumerate(self.STAGES)}, n.value
+
+    def set_stream(self, cuda_stream: int):
+        self.lib.dll.BallboxSetStream(self.ptr, C.c_void_p(cuda_stream))
 
     def state_hash(self) -> int:
         return int(self.lib.dll.BbxStateHash(self.ptr))

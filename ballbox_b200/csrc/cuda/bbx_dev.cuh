@@ -31,6 +31,8 @@
 #define PH_BSDF 4
 
 #define BBX_NUM_SMS 148
+#define BBX_TIMING_MARKS 7       // step start, after K1, broadphase, narrowphase, presolve+graph, solve kernel, K12
+#define BBX_TIMING_STEPS 256
 
 struct GridParams {
     float ox, oy, oz;        // origin of cell (0,0,0)
@@ -130,6 +132,9 @@ struct BbxDev {
     int n_valid_spheres, n_valid_boxes;
     BbxStepParams last_params;
     int have_params;
+    // optional per-stage timing (CUDA events on the step stream)
+    int timing_on, timing_steps, timing_cap;
+    cudaEvent_t *timing_ev;      // timing_cap * BBX_TIMING_MARKS events
     char *err;                   // 256-byte host buffer (kept out of the by-value kernel argument)
     int has_err;
 };
@@ -145,6 +150,7 @@ int  bbx_fail(BbxDev* d, int code, const char* what, const char* file, int line)
 
 static inline int bbx_blocks(long long n, int block) { long long b = (n + block - 1) / block; return (int)(b < 1 ? 1 : b); }
 
+void bbx_timing_mark(BbxDev* d, int mark);
 // stage entry points (one translation unit each)
 int bbx_stage_pack(BbxDev* d);
 int bbx_stage_unpack(BbxDev* d);

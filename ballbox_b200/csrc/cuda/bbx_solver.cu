@@ -336,7 +336,7 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
     const int G = BBX_NUM_SMS * 8;
     BBX_CUDA(d, cudaMemsetAsync(d->deg, 0, sizeof(int) * ((size_t)d->N + 1), d->stream));
     BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt);
-    if (p->settings.solver_iterations <= 0) { BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
+    if (p->settings.solver_iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);
     if (rc) return rc;
     BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d);
@@ -354,6 +354,7 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
         if (per_sm > 4) per_sm = 4;
         d->coop_blocks = per_sm * sms;
     }
+    bbx_timing_mark(d, 4);
     SolveParams sp;
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;
     sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = p->settings.solver_iterations;

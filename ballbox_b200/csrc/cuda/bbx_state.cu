@@ -138,6 +138,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->queue, d->slot_of, d->level_count, d->M0, d->M1, d->M2, d->M3, d->Mid, d->ctr, d->sort_keys, d->export_buf };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     if (d->ctr_host) cudaFreeHost(d->ctr_host);
+    if (d->timing_ev) { for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventDestroy(d->timing_ev[i]); free(d->timing_ev); }
     cudaGetLastError();
     free(d->err);
     free(d);

@@ -7,6 +7,43 @@
 #include <vector>
 #include "bbx_dev.cuh"
 
+void bbx_timing_mark(BbxDev* d, int mark)
+{
+    if (!d->timing_on || d->timing_steps >= d->timing_cap) return;
+    cudaEventRecord(d->timing_ev[d->timing_steps * BBX_TIMING_MARKS + mark], d->stream);
+}
+
+extern "C" void bbx_dev_set_timing(BbxDev* d, int on)
+{
+    if (!d) return;
+    if (on && !d->timing_ev) {
+        d->timing_cap = BBX_TIMING_STEPS;
+        d->timing_ev = (cudaEvent_t*)calloc((size_t)d->timing_cap * BBX_TIMING_MARKS, sizeof(cudaEvent_t));
+        cudaSetDevice(d->device);
+        for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventCreate(&d->timing_ev[i]);
+    }
+    d->timing_on = on; d->timing_steps = 0;
+}
+
+extern "C" int bbx_dev_get_timing(BbxDev* d, float* out6, int* steps)
+{
+    if (!d || !out6) return BBX_ERR_BAD_ARGUMENT;
+    for (int k = 0; k < 6; k++) out6[k] = 0.0f;
+    if (steps) *steps = 0;
+    if (!d->timing_ev) return 0;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    for (int s = 0; s < d->timing_steps; s++)
+        for (int k = 0; k < 6; k++) {
+            float ms = 0.0f;
+            BBX_CUDA(d, cudaEventElapsedTime(&ms, d->timing_ev[s * BBX_TIMING_MARKS + k], d->timing_ev[s * BBX_TIMING_MARKS + k + 1]));
+            out6[k] += ms;
+        }
+    if (steps) *steps = d->timing_steps;
+    d->timing_steps = 0;
+    return 0;
+}
+
 extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
 {
     if (!d || !p) return BBX_ERR_BAD_ARGUMENT;
@@ -18,11 +55,18 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
     BbxStepParams q = *p;
     for (int s = 0; s < steps; s++) {
         int rc;
+        bbx_timing_mark(d, 0);
         if ((rc = bbx_stage_integrate_velocities(d, &q))) return rc;   // stages 1-2
+        bbx_timing_mark(d, 1);
         if ((rc = bbx_stage_broadphase(d, &q))) return rc;             // stage 3: pair finding (+ sphere-sphere)
+        bbx_timing_mark(d, 2);
         if ((rc = bbx_stage_narrowphase(d, &q))) return rc;            // stage 3: contact generation
-        if ((rc = bbx_stage_solve(d, &q))) return rc;                  // stage 4
+        bbx_timing_mark(d, 3);
+        if ((rc = bbx_stage_solve(d, &q))) return rc;                  // stage 4 (marks 4 inside, before the solve kernel)
+        bbx_timing_mark(d, 5);
         if ((rc = bbx_stage_integrate_positions(d, &q))) return rc;    // stages 5-6
+        bbx_timing_mark(d, 6);
+        if (d->timing_on && d->timing_steps < d->timing_cap) d->timing_steps++;
         q.has_forces = 0;                                              // forces were consumed and cleared by step 0
         d->steps++;
         d->body_steps += (long long)d->n_valid_spheres + d->n_valid_boxes;

@@ -40,7 +40,7 @@ struct PhysicsWorldBatch {
     void* stream;
     int sync_mode, schedule;
     int sdf_id; float sdf_params[8];
-    int uploaded, forces_dirty, n_callbacks;
+    int uploaded, forces_dirty, n_callbacks, timing;
     int has_err; char err[256];
 };
 
@@ -563,6 +563,7 @@ static int batch_ensure_dev(struct PhysicsWorldBatch* b)
         return rc;
     }
     bbx_dev_set_stream(b->dev, b->stream);
+    if (b->timing) bbx_dev_set_timing(b->dev, 1);
     return 0;
 }
 
@@ -766,6 +767,22 @@ int  BallboxGetStats(PhysicsWorld* w, BallboxStats* out)
     return p->batch->dev ? batch_check_dev(p->batch, bbx_dev_stats(p->batch->dev, out)) : 0;
 }
 
+void BallboxSetStageTiming(PhysicsWorld* w, int on)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return;
+    p->batch->timing = on;
+    if (p->batch->dev) bbx_dev_set_timing(p->batch->dev, on);
+}
+int BallboxGetStageTiming(PhysicsWorld* w, float* out6, int* steps)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p || !out6) return BBX_ERR_BAD_ARGUMENT;
+    for (int k = 0; k < 6; k++) out6[k] = 0.0f;
+    if (steps) *steps = 0;
+    return p->batch->dev ? batch_check_dev(p->batch, bbx_dev_get_timing(p->batch->dev, out6, steps)) : 0;
+}
+
 static int batch_ok(PhysicsWorldBatch* b) { return b && b->magic == BBX_MAGIC; }
 int  BatchSetDevice(PhysicsWorldBatch* b, int device) { return batch_ok(b) ? BallboxSetDevice(&b->worlds[0].pub, device) : BBX_ERR_BAD_ARGUMENT; }
 void BatchSetStream(PhysicsWorldBatch* b, void* s) { if (batch_ok(b)) BallboxSetStream(&b->worlds[0].pub, s); }
@@ -782,6 +799,8 @@ int  PhysicsStepBatch(PhysicsWorldBatch* b, float dt, int steps)
 }
 int  BatchSynchronize(PhysicsWorldBatch* b) { return batch_ok(b) ? BallboxSynchronize(&b->worlds[0].pub) : BBX_ERR_BAD_ARGUMENT; }
 int  BatchGetStats(PhysicsWorldBatch* b, BallboxStats* out) { return batch_ok(b) ? BallboxGetStats(&b->worlds[0].pub, out) : BBX_ERR_BAD_ARGUMENT; }
+void BatchSetStageTiming(PhysicsWorldBatch* b, int on) { if (batch_ok(b)) BallboxSetStageTiming(&b->worlds[0].pub, on); }
+int  BatchGetStageTiming(PhysicsWorldBatch* b, float* out6, int* steps) { return batch_ok(b) ? BallboxGetStageTiming(&b->worlds[0].pub, out6, steps) : BBX_ERR_BAD_ARGUMENT; }
 const char* BatchGetLastError(PhysicsWorldBatch* b) { return (batch_ok(b) && b->has_err) ? b->err : NULL; }
 
 const char* BallboxBackendName(void) { return "ballbox-b200/cuda-sm_100a"; }

@@ -68,6 +68,12 @@ typedef struct {
 } BallboxStats;
 int BallboxGetStats(PhysicsWorld* world, BallboxStats* out);
 
+/* ---- per-stage device timing (CUDA events on the step stream).  out6 (ms, summed
+ * over the steps since the last query) = integrate-v, broadphase, narrowphase,
+ * presolve+graph, solve kernel, integrate-p+sleep. ------------------------------ */
+void BallboxSetStageTiming(PhysicsWorld* world, int on);
+int  BallboxGetStageTiming(PhysicsWorld* world, float* out6, int* steps);
+
 /* ---- batches of independent worlds (RL style).  All worlds of a batch share
  * one device context and are stepped by the same kernels; worlds never
  * interact.  Settings, gravity and SDF are taken from world 0. --------------- */
@@ -84,6 +90,8 @@ int  BatchDownload(PhysicsWorldBatch* batch, int what);
 int  PhysicsStepBatch(PhysicsWorldBatch* batch, float deltaTime, int steps);
 int  BatchSynchronize(PhysicsWorldBatch* batch);
 int  BatchGetStats(PhysicsWorldBatch* batch, BallboxStats* out);
+void BatchSetStageTiming(PhysicsWorldBatch* batch, int on);
+int  BatchGetStageTiming(PhysicsWorldBatch* batch, float* out6, int* steps);
 const char* BatchGetLastError(PhysicsWorldBatch* batch);
 
 /* ---- library identity ------------------------------------------------------ */

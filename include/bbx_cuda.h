@@ -76,6 +76,12 @@ int  bbx_dev_download(BbxDev* dev, const BbxHostBodies* hb);
 int  bbx_dev_download_constraints(BbxDev* dev, ContactConstraint* out, int cap_per_world, int* counts);
 int  bbx_dev_synchronize(BbxDev* dev);
 int  bbx_dev_stats(BbxDev* dev, BallboxStats* out);
+/* per-stage device times: when on, every step records CUDA events on the step stream.
+ * bbx_dev_get_timing sums them (ms) into out6 = {integrate-v, broadphase, narrowphase,
+ * presolve+graph, solve kernel, integrate-p+sleep}, reports the number of steps covered
+ * and resets the accumulation. */
+void bbx_dev_set_timing(BbxDev* dev, int on);
+int  bbx_dev_get_timing(BbxDev* dev, float* out6, int* steps);
 const char* bbx_dev_error(BbxDev* dev);          /* NULL when healthy */
 void bbx_dev_clear_error(BbxDev* dev);
 

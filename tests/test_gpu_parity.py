@@ -1,0 +1,221 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI library exactly as a
+reference user would (PhysicsStep(world, dt) with host arrays), against the CPU
+checker on identical scenes.  Bar (BASELINE.json north_star): bit-exact contact
+identities; normals, penetrations and post-solve state within 1e-4 relative over one
+step.  With the exact (level-scheduled) solver everything is in fact bit-identical,
+so most tests assert equality of the bits; test_tolerance_as_stated spells out the
+stated tolerance."""
+import numpy as np
+import pytest
+
+from ballbox_b200 import binding as bb
+from tests import golden_tools, parity
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 60.0
+REL_TOL = 1e-4          # north_star: 1e-4 relative over 1 step
+
+
+def lockstep(product, truth, kind, n, seed, steps, pruned=False, tweak=None, every=1):
+    g, c = product.build_scene(kind, n, seed), truth.build_scene(kind, n, seed)
+    if tweak:
+        tweak(product, g); tweak(truth, c)
+    for s in range(steps):
+        g.step(DT); c.step(DT, pruned=pruned)
+        if s % every == 0 or s == steps - 1:
+            mm = parity.compare_worlds(g, c)
+            assert not mm, f"scene {kind} n={n} step {s}: {mm[:4]}"
+    return g, c
+
+
+@pytest.mark.parametrize("case", list(golden_tools.CASES))
+def test_golden_vectors_on_gpu(product, case):
+    """includes config 1 (README quick start): 933 callbacks replayed in reference order."""
+    golden_tools.check_case(product, case)
+
+
+@pytest.mark.parametrize("kind,n,seed,steps", [
+    (bb.SCENE_BALLS, 800, 3, 150), (bb.SCENE_MIXED, 600, 4, 200), (bb.SCENE_SDF, 500, 5, 200),
+    (bb.SCENE_RLWORLD, 0, 6, 200), (bb.SCENE_MIXED, 64, 7, 300)])
+def test_bit_exact_every_step(product, truth, kind, n, seed, steps):
+    lockstep(product, truth, kind, n, seed, steps)
+
+
+def test_tolerance_as_stated(product, truth):
+    g, c = product.build_scene(bb.SCENE_MIXED, 2000, 12), truth.build_scene(bb.SCENE_MIXED, 2000, 12)
+    for _ in range(30):
+        g.step(DT); c.step(DT, pruned=True)
+    kg, kc = g.constraints(), c.constraints()
+    assert len(kg) == len(kc) > 500
+    for f in ("a_type", "a_index", "b_type", "b_index"):            # contact-pair identities: exact
+        assert np.array_equal(kg[f], kc[f])
+    assert parity.max_rel_err(kg["normal"], kc["normal"]) <= REL_TOL
+    assert parity.max_rel_err(kg["penetration"], kc["penetration"]) <= REL_TOL
+    sg, sc = g.snapshot(), c.snapshot()
+    for f in ("s_pos", "s_vel", "b_pos", "b_vel", "b_rot", "b_angvel"):
+        assert parity.max_rel_err(sg[f], sc[f]) <= REL_TOL, f
+
+
+def test_drift_over_1000_steps_is_zero_with_exact_schedule(product, truth):
+    g, c = product.build_scene(bb.SCENE_MIXED, 250, 21), truth.build_scene(bb.SCENE_MIXED, 250, 21)
+    g.set_sync_mode(bb.SYNC_RESIDENT)
+    g.step_n(DT, 1000); g.download()
+    for _ in range(1000):
+        c.step(DT)
+    assert not parity.compare_worlds(g, c)
+
+
+@pytest.mark.parametrize("kind,n,steps", [(bb.SCENE_BALLS, 100_000, 3), (bb.SCENE_MIXED, 200_000, 3), (bb.SCENE_SDF, 100_000, 3)])
+def test_large_scenes_against_pruned_reference(product, truth, kind, n, steps):
+    """BASELINE configs 2-4 at (or near) full size; the checker runs behind its CPU grid."""
+    lockstep(product, truth, kind, n, 20261019, steps, pruned=True)
+
+
+def test_resident_equals_compat_and_is_deterministic(product):
+    a, b, c = (product.build_scene(bb.SCENE_MIXED, 3000, 8) for _ in range(3))
+    b.set_sync_mode(bb.SYNC_RESIDENT); c.set_sync_mode(bb.SYNC_RESIDENT)
+    for _ in range(40):
+        a.step(DT)
+    b.step_n(DT, 40); b.download()
+    for _ in range(4):
+        c.step_n(DT, 10)
+    c.download()
+    assert not parity.compare_worlds(a, b)
+    assert not parity.compare_worlds(a, c)
+    assert a.state_hash() == b.state_hash() == c.state_hash()
+
+
+def test_batch_equals_independent_worlds(product, truth):
+    d = product.dll
+    n_worlds = 12
+    s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
+    batch = d.CreatePhysicsWorldBatch(n_worlds, s, b, c)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(n_worlds)]
+    singles = []
+    for i, v in enumerate(views):
+        d.BbxSceneBuild(v.ptr, bb.SCENE_RLWORLD, 0, 900 + i)
+        singles.append(truth.build_scene(bb.SCENE_RLWORLD, 0, 900 + i))
+    assert d.PhysicsStepBatch(batch, DT, 60) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    for w in singles:
+        for _ in range(60):
+            w.step(DT)
+    for i, (v, w) in enumerate(zip(views, singles)):
+        mm = parity.compare_worlds(v, w)
+        assert not mm, f"world {i}: {mm[:3]}"
+    d.DestroyPhysicsWorldBatch(batch)
+
+
+# ---------------------------------------------------------------------------- edge cases
+def test_empty_world_and_bad_dt(product):
+    w = product.create_world(4, 4, 16)
+    w.step(DT)
+    w.step(0.0); w.step(-1.0); w.step(1e-7)            # ignored (ballbox.h:1791)
+    assert len(w.constraints()) == 0
+    w.add_sphere((0, 0, 0), 1.0)
+    w.set_gravity((0, -9.8, 0))
+    w.step(0.0)
+    assert w.sphere_arrays()["pos"][0][1] == 0.0
+
+
+def test_static_only_world_emits_static_contacts(product, truth):
+    def build(lib):
+        w = lib.create_world(4, 4, 64)
+        for p in ((0, 0, 0), (1.5, 0.2, 0), (0.5, 1.2, 0.3)):
+            i = w.add_box(p, (1, 1, 1)); lib.dll.SetBoxStatic(w.ptr, i, True)
+        i = w.add_sphere((0.2, 0.1, 0.9), 0.7); lib.dll.SetSphereStatic(w.ptr, i, True)
+        return w
+    g, c = build(product), build(truth)
+    for _ in range(3):
+        g.step(DT); c.step(DT)
+        assert not parity.compare_worlds(g, c)
+    assert len(g.constraints()) > 0
+
+
+def _tweaks():
+    def zero_iter(lib, w): w.w.settings.solver_iterations = 0
+    def one_iter(lib, w): w.w.settings.solver_iterations = 1
+    def no_friction(lib, w): w.w.settings.friction = 0.0
+    def defaults25(lib, w): lib.dll.ResetPhysicsSettingsToDefaults(w.ptr)
+    def manifold4(lib, w): lib.dll.SetManifoldSettings(w.ptr, 0.02, -0.01, 4)
+    def manifold1(lib, w): lib.dll.SetManifoldSettings(w.ptr, 0.01, -0.5, 1)
+    def bouncy(lib, w): lib.dll.SetRestitution(w.ptr, 0.9); w.w.settings.velocity_threshold = 1.0
+    def no_sleep(lib, w): w.w.settings.sleep_time_required = 1e9
+    def heavy(lib, w):
+        for i in range(0, w.n_spheres, 3): lib.dll.SetSphereMass(w.ptr, i, 5.0)
+        for i in range(6, w.n_boxes, 4): lib.dll.SetBoxMass(w.ptr, i, 0.25)
+    return [zero_iter, one_iter, no_friction, defaults25, manifold4, manifold1, bouncy, no_sleep, heavy]
+
+
+@pytest.mark.parametrize("tweak", _tweaks(), ids=lambda f: f.__name__)
+def test_settings_variants(product, truth, tweak):
+    lockstep(product, truth, bb.SCENE_MIXED, 400, 15, 60, tweak=tweak)
+
+
+def test_user_forces_torques_and_direct_velocity_writes(product, truth):
+    g, c = product.build_scene(bb.SCENE_MIXED, 300, 5), truth.build_scene(bb.SCENE_MIXED, 300, 5)
+    for s in range(50):
+        for lib, w in ((product, g), (truth, c)):
+            d = lib.dll
+            if s % 3 == 0:
+                d.AddSphereForce(w.ptr, 3, bb.Vec3(5, 1, -2)); d.AddSphereTorque(w.ptr, 4, bb.Vec3(0.1, 0.2, 0.3))
+                d.AddBoxForce(w.ptr, 9, bb.Vec3(-3, 8, 0.5)); d.AddBoxTorque(w.ptr, 10, bb.Vec3(1, -1, 0.5))
+            if s == 20:
+                w.sphere_arrays()["vel"][7] = (1.0, 2.0, 3.0)          # "direct velocity control" (README.md:154)
+                w.box_arrays()["pos"][8] += np.float32(0.25)
+                w.w.gravity.y = -3.0
+        g.step(DT); c.step(DT)
+        mm = parity.compare_worlds(g, c)
+        assert not mm, f"step {s}: {mm[:3]}"
+
+
+def test_odd_geometry(product, truth):
+    """non-unit static rotation, sphere centre inside a box, a large dynamic box, a far-away body."""
+    def build(lib):
+        w = lib.create_world(64, 64, 4096)
+        w.set_gravity((0, -9.8, 0))
+        d = lib.dll
+        g = w.add_box((0, -1, 0), (8, 1, 8)); d.SetBoxStatic(w.ptr, g, True)
+        t = w.add_box((3, 0.4, 3), (1, 0.5, 1), (0.1, 0.3, 0.0, 1.2)); d.SetBoxStatic(w.ptr, t, True)     # |q| != 1
+        w.add_box((0, 1.5, 0), (2.5, 0.5, 2.5))                                                          # big dynamic
+        w.add_sphere((0.1, 1.4, 0.1), 0.3)                                                               # inside the big box
+        w.add_sphere((500.0, 3.0, -700.0), 0.5)                                                          # far away
+        for i in range(20):
+            w.add_sphere((-3 + 0.35 * i, 2.5 + 0.1 * (i % 3), -2 + 0.2 * i), 0.3 + 0.02 * (i % 5))
+            w.add_box((-3 + 0.3 * i, 4.0, 2 - 0.2 * i), (0.2 + 0.03 * (i % 4), 0.3, 0.25), w.quat_axis_angle((1, i + 1, 2), 0.3 * i))
+        return w
+    g, c = build(product), build(truth)
+    for s in range(120):
+        g.step(DT); c.step(DT)
+        mm = parity.compare_worlds(g, c)
+        assert not mm, f"step {s}: {mm[:3]}"
+
+
+def test_host_sdf_pointer_fails_loudly(product):
+    w = product.build_scene(bb.SCENE_BALLS, 10, 1)
+    fn = bb.SDFFunction(lambda p: p.y)
+    product.dll.UseSDF(w.ptr, bb.C.cast(fn, bb.C.c_void_p))
+    with pytest.raises(bb.BallboxError, match="host function pointer"):
+        w.step(DT)
+
+
+def test_contact_overflow_is_reported(product):
+    w = product.build_scene(bb.SCENE_BALLS, 3000, 2, max_collisions=64)
+    with pytest.raises(bb.BallboxError, match="overflow|max_collisions"):
+        for _ in range(5):
+            w.step(DT)
+
+
+def test_callbacks_all_phases_match_reference(product, truth):
+    logs = []
+    for lib in (product, truth):
+        w = lib.build_scene(bb.SCENE_SDF, 120, 33)
+        log = []
+        for i in range(0, w.n_spheres, 2):
+            w.set_sphere_callback(i, lambda s, t, o, c: log.append(("s", s, t, o, c.contents.penetration, c.contents.contact_point.y)))
+        for i in range(0, w.n_boxes, 2):
+            w.set_box_callback(i, lambda s, t, o, c: log.append(("b", s, t, o, c.contents.penetration, c.contents.contact_point.y)))
+        for _ in range(60):
+            w.step(DT)
+        logs.append(log)
+    assert len(logs[0]) > 50 and logs[0] == logs[1]
