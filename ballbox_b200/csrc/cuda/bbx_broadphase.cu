@@ -103,7 +103,7 @@ __global__ void k_step_reset(BbxDev dv)
 {
     StepCounters* c = dv.ctr;
     c->n_sorted = 0; c->n_cand_sb = 0; c->n_cand_bb = 0; c->n_contacts = 0; c->n_solver = 0; c->n_touched = 0;
-    c->n_levels = 0; c->n_ss_tests = 0; c->n_frontier0 = 0; c->n_events = 0;
+    c->n_levels = 0; c->n_ss_tests = 0; c->n_frontier0 = 0; c->n_events = 0; c->n_mslots = 0; c->n_nodes = 0; c->n_hit_bb = 0;
     c->bounds[0] = c->bounds[1] = c->bounds[2] = 0xffffffffu;
     c->bounds[3] = c->bounds[4] = c->bounds[5] = 0u;
 }
@@ -220,7 +220,7 @@ __device__ __forceinline__ void emit_ss_contact(const BbxDev& dv, int a, float4 
     if (slot >= dv.cap_contacts) { atomicOr(&dv.ctr->overflow, 2); return; }
     float3 nrm = (dist > 1e-6f) ? v3scale(n, 1.0f / dist) : f3(1.0f, 0.0f, 0.0f);
     float3 pt = v3add(xyz(pa), v3scale(nrm, pa.w));
-    dv.c_ids[slot] = make_int4(a, b, 0, PH_SS);
+    dv.c_ids[slot] = make_int4(a, b, RUN_ENC(0, 1), PH_SS);
     dv.c_pt[slot] = make_float4(pt.x, pt.y, pt.z, rs - dist);
     dv.c_nrm[slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.0f);
 }
@@ -254,47 +254,113 @@ __device__ __forceinline__ void route_pair(const BbxDev& dv, int i, float4 pi, i
     }
 }
 
+// Found pairs are buffered per thread and flushed with ONE global atomic per block
+// and list (same-address atomics serialise in L2: one per found pair cost 2 ms at
+// 1M bodies, see profiles/r01a).  Entry = partner gid | list << 28.
+#define FP_CAP 40
+#define FP_SS 0u
+#define FP_SB 1u
+#define FP_BB 2u
+
+__device__ __forceinline__ void fp_consider(const BbxDev& dv, int i, float4 pi, int j, float4 pj, unsigned int* buf, int& nb)
+{
+    bool ib = i >= dv.NS, jb = j >= dv.NS;
+    unsigned int list;
+    if (!ib && !jb) {
+        // the sphere-sphere hit condition itself (ballbox.h:457), symmetric in (i, j)
+        float3 n = v3sub(xyz(pj), xyz(pi));
+        if (!(v3len(n) < pi.w + pj.w)) return;
+        list = FP_SS;
+    } else {
+        if (!bounds_touch(pi, pj)) return;
+        list = (ib && jb) ? FP_BB : FP_SB;
+    }
+    if (nb < FP_CAP) buf[nb++] = (unsigned int)j | (list << 28);
+    else route_pair(dv, i, pi, j, pj);                  // rare overflow: immediate append
+}
+
 __global__ void __launch_bounds__(128) k_find_pairs(BbxDev dv)
 {
+    __shared__ int s_cnt[3], s_base[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int n_sorted = dv.cell_start[dv.grid->n_cells];
-    if (p >= n_sorted) return;
     const GridParams g = *dv.grid;
-    int i = dv.sorted_id[p];
-    float4 pi = dv.sorted_pos[p];
-    int c = dv.body_cell[i];
-    int w = c / g.cells_per_world;
-    int lc = c - w * g.cells_per_world;
-    int cx = lc % g.nx, cy = (lc / g.nx) % g.ny, cz = lc / (g.nx * g.ny);
-    int wbase = w * g.cells_per_world;
-
-    // own cell: partners later in the sorted order
-    {
-        int e = dv.cell_start[c + 1];
-        for (int q = p + 1; q < e; q++) route_pair(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q]);
-    }
-    // 13 forward neighbours: (dz,dy,dx) > (0,0,0) lexicographically
-    for (int dz = 0; dz <= 1; dz++) {
-        int z = cz + dz;
-        if (z >= g.nz) continue;
-        for (int dy = (dz ? -1 : 0); dy <= 1; dy++) {
-            int y = cy + dy;
-            if (y < 0 || y >= g.ny) continue;
-            int x0 = (dz == 0 && dy == 0) ? cx + 1 : cx - 1;
-            int x1 = cx + 1;
-            if (x0 < 0) x0 = 0;
-            if (x1 >= g.nx) x1 = g.nx - 1;
-            if (x0 > x1) continue;
-            int row = wbase + (z * g.ny + y) * g.nx;
-            int s = dv.cell_start[row + x0], e = dv.cell_start[row + x1 + 1];   // consecutive cells: one run
-            for (int q = s; q < e; q++) route_pair(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q]);
+    int n_sorted = dv.cell_start[g.n_cells];
+    unsigned int buf[FP_CAP];
+    int nb = 0, i = -1;
+    float4 pi = make_float4(0, 0, 0, 0);
+    if (p < n_sorted) {
+        i = dv.sorted_id[p];
+        pi = dv.sorted_pos[p];
+        int c = dv.body_cell[i];
+        int w = c / g.cells_per_world;
+        int lc = c - w * g.cells_per_world;
+        int cx = lc % g.nx, cy = (lc / g.nx) % g.ny, cz = lc / (g.nx * g.ny);
+        int wbase = w * g.cells_per_world;
+        // own cell: partners later in the sorted order
+        {
+            int e = dv.cell_start[c + 1];
+            for (int q = p + 1; q < e; q++) fp_consider(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q], buf, nb);
+        }
+        // 13 forward neighbours: (dz,dy,dx) > (0,0,0) lexicographically
+        for (int dz = 0; dz <= 1; dz++) {
+            int z = cz + dz;
+            if (z >= g.nz) continue;
+            for (int dy = (dz ? -1 : 0); dy <= 1; dy++) {
+                int y = cy + dy;
+                if (y < 0 || y >= g.ny) continue;
+                int x0 = (dz == 0 && dy == 0) ? cx + 1 : cx - 1;
+                int x1 = cx + 1;
+                if (x0 < 0) x0 = 0;
+                if (x1 >= g.nx) x1 = g.nx - 1;
+                if (x0 > x1) continue;
+                int row = wbase + (z * g.ny + y) * g.nx;
+                int s = dv.cell_start[row + x0], e = dv.cell_start[row + x1 + 1];   // consecutive cells: one run
+                for (int q = s; q < e; q++) fp_consider(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q], buf, nb);
+            }
+        }
+        // big bodies of this world
+        int bs = dv.big_start[w], be = dv.big_start[w + 1];
+        for (int k = bs; k < be; k++) {
+            int j = dv.big_list[k];
+            fp_consider(dv, i, pi, j, dv.pos[j], buf, nb);
         }
     }
-    // big bodies of this world
-    int bs = dv.big_start[w], be = dv.big_start[w + 1];
-    for (int k = bs; k < be; k++) {
-        int j = dv.big_list[k];
-        route_pair(dv, i, pi, j, dv.pos[j]);
+    // ---- flush: block-aggregated reservation, one global atomic per list ----
+    int cnt[3] = {0, 0, 0};
+    for (int k = 0; k < nb; k++) cnt[buf[k] >> 28]++;
+    int off[3];
+    for (int t = 0; t < 3; t++) off[t] = cnt[t] ? atomicAdd(&s_cnt[t], cnt[t]) : 0;
+    __syncthreads();
+    if (threadIdx.x < 3 && s_cnt[threadIdx.x] > 0) {
+        int* ctr = threadIdx.x == FP_SS ? &dv.ctr->n_contacts : (threadIdx.x == FP_SB ? &dv.ctr->n_cand_sb : &dv.ctr->n_cand_bb);
+        s_base[threadIdx.x] = atomicAdd(ctr, s_cnt[threadIdx.x]);
+    }
+    __syncthreads();
+    for (int k = 0; k < nb; k++) {
+        unsigned int e = buf[k];
+        int j = (int)(e & 0x0fffffffu);
+        unsigned int t = e >> 28;
+        int slot = s_base[t] + off[t]++;
+        if (t == FP_SS) {
+            if (slot >= dv.cap_contacts) { atomicOr(&dv.ctr->overflow, 2); continue; }
+            // CheckSphereCollisionWithData, ballbox.h:451-471, with A = lower index
+            int a = i < j ? i : j, b = i < j ? j : i;
+            float4 pj = dv.pos[j];
+            float4 pa = i < j ? pi : pj, pb = i < j ? pj : pi;
+            float3 n = v3sub(xyz(pb), xyz(pa));
+            float dist = v3len(n), rs = pa.w + pb.w;
+            float3 nrm = (dist > 1e-6f) ? v3scale(n, 1.0f / dist) : f3(1.0f, 0.0f, 0.0f);
+            float3 pt = v3add(xyz(pa), v3scale(nrm, pa.w));
+            dv.c_ids[slot] = make_int4(a, b, RUN_ENC(0, 1), PH_SS);
+            dv.c_pt[slot] = make_float4(pt.x, pt.y, pt.z, rs - dist);
+            dv.c_nrm[slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.0f);
+        } else {
+            if (slot >= dv.cap_cand) { atomicOr(&dv.ctr->overflow, 1); continue; }
+            if (t == FP_BB) dv.cand_bb[slot] = (i < j) ? make_int2(i, j) : make_int2(j, i);
+            else dv.cand_sb[slot] = (i >= dv.NS) ? make_int2(j, i) : make_int2(i, j);       // (sphere, box)
+        }
     }
 }
 

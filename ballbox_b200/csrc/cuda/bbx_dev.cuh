@@ -33,6 +33,7 @@
 #define BBX_NUM_SMS 148
 #define BBX_TIMING_MARKS 7       // step start, after K1, broadphase, narrowphase, presolve+graph, solve kernel, K12
 #define BBX_TIMING_STEPS 256
+#define BBX_NCLS 8               // solver node classes by run length: 1 (no box), 1 (box), 2, 3, 4, 5-6, 7-8, 9+
 
 struct GridParams {
     float ox, oy, oz;        // origin of cell (0,0,0)
@@ -57,7 +58,10 @@ struct StepCounters {
     int n_ss_tests;
     int n_frontier0;
     int n_events;
-    int pad[5];
+    int n_mslots;            // M slots handed out (level-major constraint order)
+    int n_nodes;             // solver nodes (runs of contacts between the same two bodies)
+    int n_hit_bb;            // box-box candidates that passed SAT
+    int pad[2];
     unsigned int bounds[6];  // ordered-int encoded min xyz / max xyz of small bodies
     unsigned int cut_dyn;    // float bits: largest bounding radius among non-static bodies
     unsigned int cut_all;    // float bits: largest bounding radius among all bodies
@@ -87,14 +91,13 @@ struct BbxDev {
 
     // packed working state, one float4 per body slot (spheres first, then boxes)
     float4 *pos;        // xyz, w = bounding radius (sphere: its radius)
-    float4 *lin;        // linear velocity, w = 1/mass (0 when static)
-    float4 *ang;        // angular velocity, w = 1/inertia for spheres (0 when static)
+    float4 *vel;        // 2 per body, one 32-byte sector: [2g] = (linear velocity, 1/mass or 0 when static),
+                        //                                  [2g+1] = (angular velocity, spheres: 1/inertia or 0)
     float  *mass;       // N
     float  *timer;      // N
     unsigned char *flags;   // N
-    float4 *rot;        // NB box rotations
+    float4 *boxq;       // 2 per box, one 32-byte sector: [2b] = rotation, [2b+1] = (1/Ix, 1/Iy, 1/Iz) or 0 when static
     float4 *half;       // NB half extents, w unused
-    float4 *invI;       // NB 1/Ix 1/Iy 1/Iz (0 when static)
 
     // grid
     GridParams *grid;
@@ -106,21 +109,26 @@ struct BbxDev {
 
     // candidates and contacts (unordered append buffers)
     int2 *cand_sb, *cand_bb;
+    int4 *hit_ids; float4 *hit_ax;   // box-box pairs that passed SAT: (A gid, B gid, axis type, -), (axis, |overlap|)
     int4 *c_ids;        // a gid, b gid (-2 = SDF), k, phase
     float4 *c_pt;       // contact point, w = penetration
     float4 *c_nrm;      // contact normal A->B
 
     // solver records in contact order (written by presolve)
-    float4 *L0, *L1, *L2, *L3;   // (n, bias) (rA, mN) (rB, mT0) (jn, jt0, jt1, mT1)
-    int2   *Lid;                 // dynamic gids (or -1)
+    float4 *L;                   // 4 per contact, 64-byte records: (n, bias) (rA, mN) (rB, mT0) (jn, jt0, jt1, mT1)
+    int2   *Lid;                 // per node (first contact of a run): dynamic gids (or -1)
     int *deg, *adj_start, *adj_cursor;           // N (+1)
     unsigned long long *adj;                     // 2*cap_contacts
     int *next_a, *next_b, *indeg;                // cap_contacts
-    int *queue;                                  // cap_contacts: level-major order (contact ids)
-    int *slot_of;                                // cap_contacts: inverse of queue
-    int *level_count;                            // cap_levels+2
+    // level-major node queues, one per size class so that the lanes of a warp sweep equally long runs
+    int  *queue_k[BBX_NCLS];                     // node ids (first contact of the run)
+    int4 *Nd_k[BBX_NCLS];                        // (first M slot, constraint count, dynamic gid A, dynamic gid B)
+    int *slot_of;                                // cap_contacts: contact -> M slot
+    int *level_count;                            // (cap_levels + 4) * BBX_NCLS
+    unsigned long long *level_ns;                // optional trace: globaltimer at the end of each level of iteration 1 (first 4096)
     // level-major copies streamed by iterations >= 1
-    float4 *M0, *M1, *M2, *M3; int2 *Mid;
+    float4 *M;                   // same four float4 fields, plane-major: field r of slot s is M[r*cap_contacts + s]; a node's
+                                 // slots are contiguous, so a warp of equal-length nodes loads each plane coalesced
 
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy
@@ -162,6 +170,18 @@ int bbx_stage_integrate_positions(BbxDev* d, const BbxStepParams* p);
 int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out);
 
 #ifdef __CUDACC__
+// contact-run encoding in c_ids.z: low 8 bits = index k inside the run, bits 8.. = run length
+#define RUN_K(z)   ((z) & 0xff)
+#define RUN_LEN(z) ((z) >> 8)
+#define RUN_ENC(k, len) ((k) | ((len) << 8))
+__host__ __device__ __forceinline__ int bbx_node_class(int m, bool any_box)
+{
+    if (m <= 1) return any_box ? 1 : 0;
+    if (m <= 4) return m;
+    if (m <= 6) return 5;
+    if (m <= 8) return 6;
+    return 7;
+}
 // ---------------------------------------------------------------------------
 // exact vector math (reference ballbox.h:501-535)
 // ---------------------------------------------------------------------------
@@ -201,6 +221,30 @@ __device__ __forceinline__ float3 qrot(float4 q, float3 v)
     return v3add(v3add(a, b), c);
 }
 
+// 256-bit global accesses (sm_100a LDG/STG.E.ENL2.256): one instruction and one 32-byte sector
+// per lane for the packed body state, half the L1TEX wavefronts of two float4 accesses.
+// .cg = cache in L2 only: data another block wrote before a grid barrier is never served stale.
+struct __align__(32) F8 { float4 a, b; };
+__device__ __forceinline__ F8 ld256_cg(const float4* p)
+{
+    F8 r;
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ F8 ld256_nc(const float4* p)          // read-only data
+{
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256_cg(float4* p, float4 a, float4 b)
+{
+    asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
 // order-preserving float <-> uint encoding for atomicMin/atomicMax
 __device__ __forceinline__ unsigned int f2ord(float f)
 {
@@ -234,4 +278,17 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred)
     base = __shfl_sync(mask, base, leader);
     return base + __popc(mask & ((1u << lane) - 1u));
 }
+// full-warp reservation of n slots per lane (n may be 0); all 32 lanes must call
+__device__ __forceinline__ int warp_reserve(int* counter, int n)
+{
+    int lane = threadIdx.x & 31;
+    int incl = n;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - n;
+}
+
 #endif // __CUDACC__

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) k_integrate_velocities(BbxDev dv, float3 
         // ApplyForces: forces += gravity * mass, sleeping bodies included (:1825-1827)
         F = v3add(F, v3scale(g, m));
         if (!(f & BF_SLEEP)) {
-            float4 v4 = dv.lin[i], w4 = dv.ang[i];
+            float4 v4 = dv.vel[2 * i], w4 = dv.vel[2 * i + 1];
             float3 v = xyz(v4), w = xyz(w4);
             float3 acc = v3scale(F, 1.0f / m);                       // :1852
             v = v3add(v, v3scale(acc, dt));                          // :1855
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) k_integrate_velocities(BbxDev dv, float3 
             w = v3add(w, v3scale(alpha, dt));                        // :1863 / :1894
             v = v3scale(v, lin_damp);                                // :1905 / :1912
             w = v3scale(w, ang_damp);
-            dv.lin[i] = make_float4(v.x, v.y, v.z, v4.w);
-            dv.ang[i] = make_float4(w.x, w.y, w.z, w4.w);
+            dv.vel[2 * i] = make_float4(v.x, v.y, v.z, v4.w);
+            dv.vel[2 * i + 1] = make_float4(w.x, w.y, w.z, w4.w);
         }
     }
     if (HAS_FORCES) {                                                // :1917-1924
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, fl
     if (i >= dv.N) return;
     unsigned char f = dv.flags[i];
     if (!(f & BF_VALID) || (f & BF_STATIC)) return;
-    float4 v4 = dv.lin[i], w4 = dv.ang[i];
+    float4 v4 = dv.vel[2 * i], w4 = dv.vel[2 * i + 1];
     float3 v = xyz(v4), w = xyz(w4);
     if (!(f & BF_SLEEP)) {
         float4 p4 = dv.pos[i];
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, fl
         float R = p4.w;
         if (i >= dv.NS) {
             int b = i - dv.NS;
-            float4 q = dv.rot[b];
+            float4 q = dv.boxq[2 * b];
             // q_dot = 0.5 * (w,0) (x) q  (QuatMultiply :543-550 with q1 = (w.x, w.y, w.z, 0))
             float dx = 0.0f * q.x + w.x * q.w + w.y * q.z - w.z * q.y;
             float dy = 0.0f * q.y - w.x * q.z + w.y * q.w + w.z * q.x;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, fl
             float len = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w);     // QuatNormalize :552-562
             if (len == 0.0f) n = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
             else n = make_float4(n.x / len, n.y / len, n.z / len, n.w / len);
-            dv.rot[b] = n;
+            dv.boxq[2 * b] = n;
             R = box_bound_radius(xyz(dv.half[b]), n);
         }
         dv.pos[i] = make_float4(p.x, p.y, p.z, R);
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, fl
         t += dt;
         if (t >= t_req && !(f & BF_SLEEP)) {
             f |= BF_SLEEP;
-            dv.lin[i] = make_float4(0.0f, 0.0f, 0.0f, v4.w);
-            dv.ang[i] = make_float4(0.0f, 0.0f, 0.0f, w4.w);
+            dv.vel[2 * i] = make_float4(0.0f, 0.0f, 0.0f, v4.w);
+            dv.vel[2 * i + 1] = make_float4(0.0f, 0.0f, 0.0f, w4.w);
         }
     } else {
         t = 0.0f;

@@ -12,19 +12,6 @@
 //                         GenerateBoxSDFContacts :2413-2477
 #include "bbx_dev.cuh"
 
-// full-warp reservation of n slots per lane (n may be 0); all 32 lanes must call
-__device__ __forceinline__ int warp_reserve(int* counter, int n)
-{
-    int lane = threadIdx.x & 31;
-    int incl = n;
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    int total = __shfl_sync(0xffffffffu, incl, 31);
-    int base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    return base + incl - n;
-}
-
 __device__ __forceinline__ void store_contact(const BbxDev& dv, int slot, int a, int b, int k, int phase,
                                               float3 pt, float pen, float3 nrm)
 {
@@ -77,11 +64,11 @@ __global__ void __launch_bounds__(256) k_narrow_sb(BbxDev dv)
             pr = dv.cand_sb[t];
             float4 sp = dv.pos[pr.x], bp = dv.pos[pr.y];
             int b = pr.y - dv.NS;
-            hit = sphere_box_contact(xyz(sp), sp.w, xyz(bp), xyz(dv.half[b]), dv.rot[b], pt, nrm, pen);
+            hit = sphere_box_contact(xyz(sp), sp.w, xyz(bp), xyz(dv.half[b]), dv.boxq[2 * b], pt, nrm, pen);
         }
         int slot = warp_reserve(&dv.ctr->n_contacts, hit ? 1 : 0);
         if (hit) {
-            if (slot < dv.cap_contacts) store_contact(dv, slot, pr.x, pr.y, 0, PH_SB, pt, pen, nrm);
+            if (slot < dv.cap_contacts) store_contact(dv, slot, pr.x, pr.y, RUN_ENC(0, 1), PH_SB, pt, pen, nrm);
             else atomicOr(&dv.ctr->overflow, 2);
         }
     }
@@ -212,12 +199,13 @@ __device__ __noinline__ float3 closest_point_between_edges(const Obb& o1, const 
     return cp;
 }
 
-// SATCollision :1040-1111 + the normal flip of CheckBoxCollisionWithData :1121-1129
-__device__ bool sat_contact(const Obb& A, const Obb& B, float3& pt, float3& nrm, float& pen)
+// SATCollision :1040-1086: the 15-axis test.  Returns false at the first separating axis.
+__device__ __forceinline__ bool sat_axes(const Obb& A, const Obb& B, float& minPd, float3& smallest, int& axisType)
 {
-    float minPd = 999999.0f;
-    float3 smallest = f3(0, 0, 0);
-    int axisType = -1, idx = 0;
+    minPd = 999999.0f;
+    smallest = f3(0, 0, 0);
+    axisType = -1;
+    int idx = 0;
 #define SAT_TEST(AXIS) do { float3 ax_ = (AXIS); float pd_ = 0.0f; \
         if (!overlap_on_axis(A, B, ax_, pd_)) return false; \
         if (fabsf(pd_) < fabsf(minPd)) { minPd = pd_; smallest = v3scale(ax_, (pd_ < 0) ? -1.0f : 1.0f); axisType = idx; } \
@@ -233,8 +221,13 @@ __device__ bool sat_contact(const Obb& A, const Obb& B, float3& pt, float3& nrm,
             if (l > 1e-6f) SAT_TEST(v3scale(cr, 1.0f / l));
         }
 #undef SAT_TEST
-    pen = fabsf(minPd);
-    nrm = smallest;
+    return true;
+}
+
+// SATCollision :1088-1108 (contact point by axis type) + the normal flip of
+// CheckBoxCollisionWithData :1121-1129
+__device__ __forceinline__ void sat_point(const Obb& A, const Obb& B, int axisType, float3& nrm, float3& pt)
+{
     if (axisType >= 0 && axisType <= 5) {
         float d1, d2;
         float3 p1 = vertex_face(A, B, d1);
@@ -247,7 +240,6 @@ __device__ bool sat_contact(const Obb& A, const Obb& B, float3& pt, float3& nrm,
     }
     float3 c2c = v3sub(B.c, A.c);
     if (v3dot(nrm, c2c) < 0.0f) nrm = v3scale(nrm, -1.0f);
-    return true;
 }
 
 // is `p` inside box (pos, half, q) grown by tol?  returns the minimum face slack
@@ -264,14 +256,15 @@ __device__ __forceinline__ bool inside_box(float3 p, float3 pos, float3 half, fl
 
 // GenerateBoxBoxManifold + SelectOptimalContactPoints.  Returns the number of
 // manifold points (0 = no collision).
+// `normal` enters as the SAT axis (before the A->B flip), `spen` and `axisType` from sat_axes.
 __device__ int box_box_manifold(float3 posA, float3 hA, float4 qA, float3 posB, float3 hB, float4 qB,
-                                float tol, float pen_tol, int max_contacts,
+                                float tol, float pen_tol, int max_contacts, float spen, int axisType,
                                 float3 out_pt[8], float out_pen[8], float3& normal)
 {
     Obb A = make_obb(posA, hA, qA), B = make_obb(posB, hB, qB);
     float3 cpt[24]; float cpen[24]; int cc = 0;
-    float3 spt; float spen;
-    if (!sat_contact(A, B, spt, normal, spen)) return 0;
+    float3 spt;
+    sat_point(A, B, axisType, normal, spt);
     cpt[0] = spt; cpen[0] = spen; cc = 1;                          // :2583-2585
     float3 vA[8], vB[8];
     obb_vertices(A, vA);
@@ -330,25 +323,52 @@ __device__ int box_box_manifold(float3 posA, float3 hA, float4 qA, float3 posB, 
     return np;
 }
 
-__global__ void __launch_bounds__(128) k_narrow_bb(BbxDev dv, float tol, float pen_tol, int max_contacts)
+// Pass 1: SAT on every candidate (most are rejected at an early axis); survivors are
+// compacted so that pass 2 runs with full warps.  hit_ids = (box A gid, box B gid, axis
+// type, -), hit_ax = (SAT axis, |min overlap|).
+__global__ void __launch_bounds__(256) k_bb_sat(BbxDev dv)
 {
     int n = min(dv.ctr->n_cand_bb, dv.cap_cand);
     int n_round = (n + 31) & ~31;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
-        int np = 0;
-        float3 pts[8]; float pens[8]; float3 normal = f3(0, 0, 0);
-        int2 pr = make_int2(0, 0);
+        bool hit = false;
+        int2 pr = make_int2(0, 0); float minPd = 0.0f; float3 ax = f3(0, 0, 0); int axisType = -1;
         if (t < n) {
             pr = dv.cand_bb[t];
             int a = pr.x - dv.NS, b = pr.y - dv.NS;
-            float4 pa = dv.pos[pr.x], pb = dv.pos[pr.y];
-            np = box_box_manifold(xyz(pa), xyz(dv.half[a]), dv.rot[a], xyz(pb), xyz(dv.half[b]), dv.rot[b],
-                                  tol, pen_tol, max_contacts, pts, pens, normal);
+            Obb A = make_obb(xyz(dv.pos[pr.x]), xyz(dv.half[a]), dv.boxq[2 * a]);
+            Obb B = make_obb(xyz(dv.pos[pr.y]), xyz(dv.half[b]), dv.boxq[2 * b]);
+            hit = sat_axes(A, B, minPd, ax, axisType);
+        }
+        int slot = warp_reserve(&dv.ctr->n_hit_bb, hit ? 1 : 0);
+        if (hit) {                                             // capacity: hits <= candidates <= cap_cand
+            dv.hit_ids[slot] = make_int4(pr.x, pr.y, axisType, 0);
+            dv.hit_ax[slot] = make_float4(ax.x, ax.y, ax.z, fabsf(minPd));
+        }
+    }
+}
+
+// Pass 2: contact point, manifold candidates and point selection for colliding pairs only.
+__global__ void __launch_bounds__(128) k_bb_manifold(BbxDev dv, float tol, float pen_tol, int max_contacts)
+{
+    int n = min(dv.ctr->n_hit_bb, dv.cap_cand);
+    int n_round = (n + 31) & ~31;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
+        int np = 0;
+        float3 pts[8]; float pens[8]; float3 normal = f3(0, 0, 0);
+        int4 h = make_int4(0, 0, 0, 0);
+        if (t < n) {
+            h = dv.hit_ids[t];
+            float4 ax = dv.hit_ax[t];
+            normal = xyz(ax);
+            int a = h.x - dv.NS, b = h.y - dv.NS;
+            np = box_box_manifold(xyz(dv.pos[h.x]), xyz(dv.half[a]), dv.boxq[2 * a], xyz(dv.pos[h.y]), xyz(dv.half[b]),
+                                  dv.boxq[2 * b], tol, pen_tol, max_contacts, ax.w, h.z, pts, pens, normal);
         }
         int slot = warp_reserve(&dv.ctr->n_contacts, np);
         if (np > 0) {
             if (slot + np <= dv.cap_contacts) {
-                for (int k = 0; k < np; k++) store_contact(dv, slot + k, pr.x, pr.y, k, PH_BB, pts[k], pens[k], normal);
+                for (int k = 0; k < np; k++) store_contact(dv, slot + k, h.x, h.y, RUN_ENC(k, np), PH_BB, pts[k], pens[k], normal);
             } else atomicOr(&dv.ctr->overflow, 2);
         }
     }
@@ -389,7 +409,7 @@ __global__ void __launch_bounds__(256) k_sdf_spheres(BbxDev dv, SdfDesc sdf)
         }
         int slot = warp_reserve(&dv.ctr->n_contacts, hit ? 1 : 0);
         if (hit) {
-            if (slot < dv.cap_contacts) store_contact(dv, slot, i, -2, 0, PH_SSDF, pt, pen, nrm);
+            if (slot < dv.cap_contacts) store_contact(dv, slot, i, -2, RUN_ENC(0, 1), PH_SSDF, pt, pen, nrm);
             else atomicOr(&dv.ctr->overflow, 2);
         }
     }
@@ -405,7 +425,7 @@ __global__ void __launch_bounds__(128) k_sdf_boxes(BbxDev dv, SdfDesc sdf)
         float3 vtx[8];
         unsigned int mask = 0;            // which of the 20 probes penetrate
         if (valid) {
-            Obb o = make_obb(xyz(dv.pos[g]), xyz(dv.half[b]), dv.rot[b]);
+            Obb o = make_obb(xyz(dv.pos[g]), xyz(dv.half[b]), dv.boxq[2 * b]);
             obb_vertices(o, vtx);
             for (int k = 0; k < 8; k++) if (sdf_at(sdf, vtx[k]) < -0.001f) mask |= 1u << k;
             for (int e = 0; e < 12; e++) {
@@ -424,7 +444,7 @@ __global__ void __launch_bounds__(128) k_sdf_boxes(BbxDev dv, SdfDesc sdf)
                                       : v3scale(v3add(vtx[edge_pairs[pidx - 8][0]], vtx[edge_pairs[pidx - 8][1]]), 0.5f);
                 float dd = sdf_at(sdf, p);
                 float3 nrm = v3scale(sdf_normal(sdf, p), -1.0f);
-                store_contact(dv, slot + k, g, -2, k, PH_BSDF, p, -dd, nrm);
+                store_contact(dv, slot + k, g, -2, RUN_ENC(k, np), PH_BSDF, p, -dd, nrm);
                 k++;
             }
         }
@@ -436,7 +456,8 @@ int bbx_stage_narrowphase(BbxDev* d, const BbxStepParams* p)
     int mc = p->settings.manifold_max_contacts;
     if (mc < 1) mc = 1;
     if (mc > MAX_MANIFOLD_CONTACTS) mc = MAX_MANIFOLD_CONTACTS;
-    BBX_LAUNCH(d, k_narrow_bb, BBX_NUM_SMS * 8, 128, 0, *d, p->settings.manifold_contact_tolerance,
+    BBX_LAUNCH(d, k_bb_sat, BBX_NUM_SMS * 8, 256, 0, *d);
+    BBX_LAUNCH(d, k_bb_manifold, BBX_NUM_SMS * 8, 128, 0, *d, p->settings.manifold_contact_tolerance,
                p->settings.manifold_penetration_tolerance, mc);
     BBX_LAUNCH(d, k_narrow_sb, BBX_NUM_SMS * 8, 256, 0, *d);
     if (p->sdf_id != BBX_SDF_NONE) {

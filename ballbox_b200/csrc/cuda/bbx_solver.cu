@@ -15,17 +15,26 @@
 // the result is bit-identical to the sequential sweep.  Static bodies and the SDF
 // never receive writes (:1361, :1379, :1407) and are ignored by the graph.
 //
+// NODES.  All contacts between the same two bodies (a box-box manifold of up to 8
+// points, the up to 20 SDF probes of one box) are adjacent in both bodies' orders,
+// so they form one scheduling node: one thread loads the two bodies once, sweeps
+// the node's constraints in reference order in registers, and stores the bodies
+// once.  This divides the graph depth and the body gather traffic by the manifold
+// size without changing a single operation of the sweep.
+//
 // Levels are discovered on the fly during iteration 0 (Kahn's algorithm on the
 // per-body successor links); the visiting order is recorded and the constraint
-// records are rewritten in that level-major order, so iterations 1..I-1 stream
-// them with coalesced float4 loads.  One cooperative persistent kernel runs all
-// iterations; levels are separated by grid-wide barriers, not kernel launches.
+// records are rewritten in that level-major order (64-byte records, a node's
+// constraints contiguous), so iterations 1..I-1 stream them.  One cooperative
+// persistent kernel runs all iterations; levels are separated by grid-wide
+// barriers, not kernel launches.
 #include <cooperative_groups.h>
 #include "bbx_dev.cuh"
 namespace cg = cooperative_groups;
 
 // ---------------------------------------------------------------------------
-// K9 presolve: contact -> solver record (contact order)
+// K9 presolve: contact -> 64-byte solver record (contact order); node heads also
+// get their graph fields
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void tangents_of(float3 n, float3& t1, float3& t2)          // :1329-1336
 {
@@ -54,17 +63,17 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
             unsigned char f = dv.flags[a];
             dynA = !(f & BF_STATIC);
             rA = v3sub(pt, xyz(dv.pos[a]));
-            imA = dv.lin[a].w;                      // 0 for static bodies (:1266)
-            if (a < dv.NS) { float ii = dv.ang[a].w; iA = f3(ii, ii, ii); }
-            else iA = xyz(dv.invI[a - dv.NS]);
+            imA = dv.vel[2 * a].w;                  // 0 for static bodies (:1266)
+            if (a < dv.NS) { float ii = dv.vel[2 * a + 1].w; iA = f3(ii, ii, ii); }
+            else iA = xyz(dv.boxq[2 * (a - dv.NS) + 1]);
         }
         if (b >= 0) {
             unsigned char f = dv.flags[b];
             dynB = !(f & BF_STATIC);
             rB = v3sub(pt, xyz(dv.pos[b]));
-            imB = dv.lin[b].w;
-            if (b < dv.NS) { float ii = dv.ang[b].w; iB = f3(ii, ii, ii); }
-            else iB = xyz(dv.invI[b - dv.NS]);
+            imB = dv.vel[2 * b].w;
+            if (b < dv.NS) { float ii = dv.vel[2 * b + 1].w; iB = f3(ii, ii, ii); }
+            else iB = xyz(dv.boxq[2 * (b - dv.NS) + 1]);
         } else {                                    // SDF: "position" is the contact point (:1310-1311)
             dynB = false; rB = v3sub(pt, pt); imB = 0.0f; iB = f3(0.0f, 0.0f, 0.0f);
         }
@@ -77,38 +86,41 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         float mT0 = (s1 > 0.0f) ? 1.0f / s1 : 0.0f;
         float mT1 = (s2 > 0.0f) ? 1.0f / s2 : 0.0f;
         float bias = (baumgarte / dt) * bb_fmaxf(0.0f, pt4.w - allowed);               // :1352-1354
-        dv.L0[c] = make_float4(nrm.x, nrm.y, nrm.z, bias);
-        dv.L1[c] = make_float4(rA.x, rA.y, rA.z, mN);
-        dv.L2[c] = make_float4(rB.x, rB.y, rB.z, mT0);
-        dv.L3[c] = make_float4(0.0f, 0.0f, 0.0f, mT1);                                  // impulses start at 0 (:1203-1206)
-        dv.Lid[c] = make_int2(dynA ? a : -1, dynB ? b : -1);
-        dv.indeg[c] = (dynA ? 1 : 0) + (dynB ? 1 : 0);
-        dv.next_a[c] = -1; dv.next_b[c] = -1;
+        float4* L = dv.L + 4 * (size_t)c;
+        L[0] = make_float4(nrm.x, nrm.y, nrm.z, bias);
+        L[1] = make_float4(rA.x, rA.y, rA.z, mN);
+        L[2] = make_float4(rB.x, rB.y, rB.z, mT0);
+        L[3] = make_float4(0.0f, 0.0f, 0.0f, mT1);                                      // impulses start at 0 (:1203-1206)
         dv.slot_of[c] = -1;
-        if (dynA) atomicAdd(&dv.deg[a], 1);
-        if (dynB) atomicAdd(&dv.deg[b], 1);
+        if (RUN_K(id.z) == 0) {                                                         // node head
+            dv.Lid[c] = make_int2(dynA ? a : -1, dynB ? b : -1);
+            dv.indeg[c] = (dynA ? 1 : 0) + (dynB ? 1 : 0);
+            dv.next_a[c] = -1; dv.next_b[c] = -1;
+            if (dynA) atomicAdd(&dv.deg[a], 1);
+            if (dynB) atomicAdd(&dv.deg[b], 1);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
-// K10 dependency graph: per-body ordered constraint lists -> successor links
+// K10 dependency graph: per-body ordered node lists -> successor links
 // ---------------------------------------------------------------------------
-// order of a constraint inside ONE body's list: (phase, partner index, point)
+// order of a node inside ONE body's list: (phase, partner index)
 __device__ __forceinline__ unsigned int body_order_key(const BbxDev& dv, int4 id, bool for_a)
 {
     int other = for_a ? id.y : id.x;
     unsigned int partner = 0;
     if (other >= 0) partner = (unsigned int)(other < dv.NS ? other : other - dv.NS);
-    return ((unsigned int)id.w << 29) | (partner << 5) | (unsigned int)id.z;
+    return ((unsigned int)id.w << 29) | (partner << 5);
 }
 
 __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv)
 {
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-        int2 l = dv.Lid[c];
-        if (l.x < 0 && l.y < 0) continue;
         int4 id = dv.c_ids[c];
+        if (RUN_K(id.z) != 0) continue;
+        int2 l = dv.Lid[c];
         if (l.x >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.x], 1);
             dv.adj[slot] = ((unsigned long long)body_order_key(dv, id, true) << 32) | (unsigned int)c;
@@ -138,7 +150,7 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv)
                 lst[j + 1] = v;
             }
             int prev = (int)(unsigned int)lst[0];
-            atomicSub(&dv.indeg[prev], 1);                 // first constraint of this body has no predecessor here
+            atomicSub(&dv.indeg[prev], 1);                 // first node of this body has no predecessor here
             for (int i = 1; i < d; i++) {
                 int cur = (int)(unsigned int)lst[i];
                 if (dv.Lid[prev].x == x) dv.next_a[prev] = cur; else dv.next_b[prev] = cur;
@@ -152,20 +164,32 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv)
 
 __global__ void __launch_bounds__(256) k_frontier0(BbxDev dv)
 {
+    __shared__ int s_solver, s_nodes;
+    if (threadIdx.x == 0) { s_solver = 0; s_nodes = 0; }
+    __syncthreads();
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     int n_round = (n + 31) & ~31;
+    int my_solver = 0, my_nodes = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += gridDim.x * blockDim.x) {
-        bool solver = false, ready = false;
+        int cls = -1;
         if (c < n) {
-            int2 l = dv.Lid[c];
-            solver = (l.x >= 0 || l.y >= 0);
-            ready = solver && dv.indeg[c] == 0;
+            int4 id = dv.c_ids[c];
+            if (RUN_K(id.z) == 0) {
+                int2 l = dv.Lid[c];
+                if (l.x >= 0 || l.y >= 0) {
+                    my_solver += RUN_LEN(id.z); my_nodes++;
+                    if (dv.indeg[c] == 0) cls = bbx_node_class(RUN_LEN(id.z), id.x >= dv.NS || id.y >= dv.NS);
+                }
+            }
         }
-        unsigned int ms = __ballot_sync(0xffffffffu, solver);
-        if ((threadIdx.x & 31) == 0 && ms) atomicAdd(&dv.ctr->n_solver, __popc(ms));
-        int slot = warp_append(&dv.ctr->n_frontier0, ready);
-        if (ready) dv.queue[slot] = c;
+        for (int k = 0; k < BBX_NCLS; k++) {                    // level 0 of every class queue
+            int slot = warp_append(&dv.level_count[k], cls == k);
+            if (cls == k) dv.queue_k[k][slot] = c;
+        }
     }
+    if (my_nodes) { atomicAdd(&s_solver, my_solver); atomicAdd(&s_nodes, my_nodes); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_nodes) { atomicAdd(&dv.ctr->n_solver, s_solver); atomicAdd(&dv.ctr->n_nodes, s_nodes); }
 }
 
 // ---------------------------------------------------------------------------
@@ -179,21 +203,44 @@ struct BodyState {
     float ii;           // spheres: 1/inertia
     float3 iI;          // boxes: 1/diag(I)
     float4 q;           // boxes: rotation
+    float k1, k2;       // boxes: q.w*q.w - |q.xyz|^2 and 2*q.w, the two scalars of QuatRotateVec3 (:635-637)
     bool box;
 };
 
+// QuatRotateVec3 (:630-639) with the body-constant scalars hoisted; `sgn` = -1 rotates by the conjugate
+// (|u|^2 and s are the same for q and its conjugate, so k1 and k2 are shared)
+__device__ __forceinline__ float3 qrot_pre(float3 u, float k1, float k2, float3 v)
+{
+    float3 a = v3scale(v, k1);
+    float3 b = v3scale(u, 2.0f * v3dot(u, v));
+    float3 c = v3scale(v3cross(u, v), k2);
+    return v3add(v3add(a, b), c);
+}
+
 __device__ __forceinline__ void load_body(const BbxDev& dv, int g, BodyState& s)
 {
-    float4 l = __ldcg(&dv.lin[g]), a = __ldcg(&dv.ang[g]);
+    F8 vw = ld256_cg(&dv.vel[2 * g]);
+    float4 l = vw.a, a = vw.b;
     s.v = xyz(l); s.w = xyz(a); s.im = l.w; s.ii = a.w;
     s.box = g >= dv.NS;
-    if (s.box) { s.q = dv.rot[g - dv.NS]; s.iI = xyz(dv.invI[g - dv.NS]); }
+    if (s.box) {
+        int b = g - dv.NS;
+        F8 qi = ld256_nc(&dv.boxq[2 * b]);               // rotation and inverse inertia do not change during the solve
+        s.q = qi.a; s.iI = xyz(qi.b);
+        float3 u = f3(s.q.x, s.q.y, s.q.z);
+        s.k1 = s.q.w * s.q.w - v3dot(u, u); s.k2 = 2.0f * s.q.w;
+    }
 }
 
 __device__ __forceinline__ void store_body(const BbxDev& dv, int g, const BodyState& s)
 {
-    __stcg(&dv.lin[g], make_float4(s.v.x, s.v.y, s.v.z, s.im));
-    __stcg(&dv.ang[g], make_float4(s.w.x, s.w.y, s.w.z, s.ii));
+    st256_cg(&dv.vel[2 * g], make_float4(s.v.x, s.v.y, s.v.z, s.im), make_float4(s.w.x, s.w.y, s.w.z, s.ii));
+}
+
+__device__ __forceinline__ void wake_body(const BbxDev& dv, int g)                      // :1373-1376, :1402-1405
+{
+    unsigned char f = dv.flags[g];
+    if (f & BF_SLEEP) { dv.flags[g] = f & (unsigned char)~BF_SLEEP; dv.timer[g] = 0.0f; }
 }
 
 // ApplyConstraintImpulse :1359-1408
@@ -203,22 +250,19 @@ __device__ __forceinline__ void apply_impulse(BodyState& s, float3 J, float3 L)
     if (!s.box) {
         s.w = v3add(s.w, v3scale(L, s.ii));
     } else {
-        float3 loc = qrot(qconj(s.q), L);
+        float3 u = f3(s.q.x, s.q.y, s.q.z), um = f3(-s.q.x, -s.q.y, -s.q.z);
+        float3 loc = qrot_pre(um, s.k1, s.k2, L);
         float3 dl = v3mul(loc, s.iI);
-        s.w = v3add(s.w, qrot(s.q, dl));
+        s.w = v3add(s.w, qrot_pre(u, s.k1, s.k2, dl));
     }
 }
 
-// one constraint, one Gauss-Seidel visit (:1414-1488)
-__device__ __forceinline__ void solve_constraint(const BbxDev& dv, float4 c0, float4 c1, float4 c2, float4& c3, int2 id,
-                                                 const SolveParams& sp, bool wake)
+// one constraint, one Gauss-Seidel visit (:1414-1488) on bodies held in registers
+__device__ __forceinline__ void solve_constraint(float4 c0, float4 c1, float4 c2, float4& c3, bool hasA, bool hasB,
+                                                 BodyState& A, BodyState& B, const SolveParams& sp)
 {
     float3 n = xyz(c0), rA = xyz(c1), rB = xyz(c2);
     float bias = c0.w, mN = c1.w, mT0 = c2.w, mT1 = c3.w;
-    bool hasA = id.x >= 0, hasB = id.y >= 0;
-    BodyState A, B;
-    if (hasA) load_body(dv, id.x, A);
-    if (hasB) load_body(dv, id.y, B);
     const float3 zero = f3(0.0f, 0.0f, 0.0f);
     float3 vA = hasA ? v3add(A.v, v3cross(A.w, rA)) : zero;                  // :1233-1261
     float3 vB = hasB ? v3add(B.v, v3cross(B.w, rB)) : zero;
@@ -262,70 +306,137 @@ __device__ __forceinline__ void solve_constraint(const BbxDev& dv, float4 c0, fl
             if (hasB) apply_impulse(B, T, v3cross(rB, T));
         }
     }
-    if (hasA) {
-        store_body(dv, id.x, A);
-        if (wake) { unsigned char f = dv.flags[id.x]; if (f & BF_SLEEP) { dv.flags[id.x] = f & (unsigned char)~BF_SLEEP; dv.timer[id.x] = 0.0f; } }   // :1373-1376
-    }
-    if (hasB) {
-        store_body(dv, id.y, B);
-        if (wake) { unsigned char f = dv.flags[id.y]; if (f & BF_SLEEP) { dv.flags[id.y] = f & (unsigned char)~BF_SLEEP; dv.timer[id.y] = 0.0f; } }
-    }
 }
 
-__global__ void __launch_bounds__(256) k_solve_levels(BbxDev dv, SolveParams sp)
+// Per level, the nodes of class k sit in queue_k[k][head_k .. head_k + cnt_k).  The flattened
+// index space pads every class to a multiple of 32 so that a warp never mixes classes.
+struct LevelMap { int head[BBX_NCLS]; int cnt[BBX_NCLS]; int pref[BBX_NCLS + 1]; };
+
+__device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level, bool first_level)
+{
+    // called by one thread; heads advance by the previous level's counts
+    int run = 0;
+    for (int k = 0; k < BBX_NCLS; k++) {
+        if (first_level) lm.head[k] = 0; else lm.head[k] += lm.cnt[k];
+        lm.cnt[k] = __ldcg(&lc_level[k]);
+        lm.pref[k] = run;
+        run += (lm.cnt[k] + 31) & ~31;
+    }
+    lm.pref[BBX_NCLS] = run;
+}
+
+__global__ void __launch_bounds__(256, 3) k_solve_levels(BbxDev dv, SolveParams sp)
 {
     cg::grid_group grid = cg::this_grid();
+    __shared__ LevelMap lm;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
-    int* lc = dv.level_count;
+    int* lc = dv.level_count;                       // lc[level * BBX_NCLS + class]
 
     // ---- iteration 0: discover levels (Kahn) while solving ----
-    int head = 0, cnt = __ldcg(&dv.ctr->n_frontier0), lvl = 0;
-    if (tid == 0) { lc[0] = cnt; }
-    while (cnt > 0) {
-        if (tid == 0) lc[lvl + 2] = 0;
-        int end = head + cnt;
-        int next_base = end;
-        int p_round = head + ((cnt + 31) & ~31);
-        for (int p = head + tid; p < p_round; p += stride) {
-            int sa = -1, sb = -1;
-            if (p < end) {
-                int c = __ldcg(&dv.queue[p]);
-                float4 c0 = dv.L0[c], c1 = dv.L1[c], c2 = dv.L2[c], c3 = dv.L3[c];
-                int2 id = dv.Lid[c];
-                solve_constraint(dv, c0, c1, c2, c3, id, sp, true);
-                dv.M0[p] = c0; dv.M1[p] = c1; dv.M2[p] = c2; dv.M3[p] = c3; dv.Mid[p] = id;
-                dv.slot_of[c] = p;
+    int lvl = 0;
+    if (threadIdx.x == 0) level_map_load(lm, lc, true);
+    __syncthreads();
+    while (lm.pref[BBX_NCLS] > 0) {
+        if (lvl + 2 >= dv.cap_levels) { if (tid == 0) atomicOr(&dv.ctr->overflow, 16); break; }
+        if (tid < BBX_NCLS) lc[(lvl + 2) * BBX_NCLS + tid] = 0;
+        int* lc_next = lc + (lvl + 1) * BBX_NCLS;
+        const int total = lm.pref[BBX_NCLS];
+        for (int t = tid; t < total; t += stride) {
+            int k = 0;
+            #pragma unroll
+            for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
+            int idx = t - lm.pref[k];
+            bool live = idx < lm.cnt[k];
+            int p = lm.head[k] + idx;
+            int sa = -1, sb = -1, m = 0, c = 0;
+            int2 id = make_int2(-1, -1);
+            if (live) {
+                c = __ldcg(&dv.queue_k[k][p]);
+                m = RUN_LEN(dv.c_ids[c].z);
+                id = dv.Lid[c];
+            }
+            int mbase = warp_reserve(&dv.ctr->n_mslots, m);
+            if (live) {
+                __stcs(&dv.Nd_k[k][p], make_int4(mbase, m, id.x, id.y));
+                bool hasA = id.x >= 0, hasB = id.y >= 0;
+                BodyState A, B;
+                if (hasA) load_body(dv, id.x, A);
+                if (hasB) load_body(dv, id.y, B);
+                for (int j = 0; j < m; j++) {
+                    // contact-order records are gathered once (two 256-bit loads), then written plane-major
+                    const float4* L = dv.L + 4 * (size_t)(c + j);
+                    F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+                    float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
+                    solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    float4* M = dv.M + (size_t)(mbase + j);
+                    const size_t PL = (size_t)dv.cap_contacts;
+                    __stcs(M, c0); __stcs(M + PL, c1); __stcs(M + 2 * PL, c2); __stcs(M + 3 * PL, c3);
+                    dv.slot_of[c + j] = mbase + j;
+                }
+                if (hasA) { store_body(dv, id.x, A); wake_body(dv, id.x); }
+                if (hasB) { store_body(dv, id.y, B); wake_body(dv, id.y); }
                 sa = dv.next_a[c]; sb = dv.next_b[c];
                 if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) != 1) sa = -1;
                 if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) != 1) sb = -1;
             }
-            int s1 = warp_append(&lc[lvl + 1], sa >= 0);
-            if (sa >= 0) dv.queue[next_base + s1] = sa;
-            int s2 = warp_append(&lc[lvl + 1], sb >= 0);
-            if (sb >= 0) dv.queue[next_base + s2] = sb;
+            // successors that became ready join the next level of their own class
+            #pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                int sn = side ? sb : sa;
+                int sk = -1;
+                if (sn >= 0) { int4 sid = dv.c_ids[sn]; sk = bbx_node_class(RUN_LEN(sid.z), sid.x >= dv.NS || sid.y >= dv.NS); }
+                unsigned int any = __ballot_sync(0xffffffffu, sn >= 0);
+                if (!any) continue;
+                for (int kk = 0; kk < BBX_NCLS; kk++) {
+                    int slot = warp_append(&lc_next[kk], sk == kk);
+                    if (sk == kk) dv.queue_k[kk][lm.head[kk] + lm.cnt[kk] + slot] = sn;
+                }
+            }
         }
         grid.sync();
-        head = end;
-        cnt = __ldcg(&lc[lvl + 1]);
+        if (threadIdx.x == 0) level_map_load(lm, lc + (lvl + 1) * BBX_NCLS, false);
+        __syncthreads();
         lvl++;
     }
     const int n_levels = lvl;
     if (tid == 0) dv.ctr->n_levels = n_levels;
 
+    if (tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); dv.level_ns[4096 + 1] = ns; }
     // ---- iterations 1..I-1: stream the level-major records ----
     for (int it = 1; it < sp.iterations; it++) {
-        int h = 0;
         for (int l = 0; l < n_levels; l++) {
-            int c_l = __ldcg(&lc[l]);
-            for (int p = h + tid; p < h + c_l; p += stride) {
-                float4 c0 = dv.M0[p], c1 = dv.M1[p], c2 = dv.M2[p], c3 = __ldcg(&dv.M3[p]);
-                int2 id = dv.Mid[p];
-                solve_constraint(dv, c0, c1, c2, c3, id, sp, false);
-                dv.M3[p] = c3;
+            __syncthreads();
+            if (threadIdx.x == 0) level_map_load(lm, lc + l * BBX_NCLS, l == 0);
+            __syncthreads();
+            const int total = lm.pref[BBX_NCLS];
+            for (int t = tid; t < total; t += stride) {
+                int k = 0;
+                #pragma unroll
+                for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
+                int idx = t - lm.pref[k];
+                if (idx >= lm.cnt[k]) continue;
+                int4 nd = __ldcs(&dv.Nd_k[k][lm.head[k] + idx]);
+                bool hasA = nd.z >= 0, hasB = nd.w >= 0;
+                BodyState A, B;
+                if (hasA) load_body(dv, nd.z, A);
+                if (hasB) load_body(dv, nd.w, B);
+                float4* M = dv.M + (size_t)nd.x;
+                const size_t PL = (size_t)dv.cap_contacts;
+                for (int j = 0; j < nd.y; j++, M++) {
+                    float4 c0 = __ldcs(M), c1 = __ldcs(M + PL), c2 = __ldcs(M + 2 * PL), c3 = __ldcs(M + 3 * PL);
+                    solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    __stcs(M + 3 * PL, c3);
+                }
+                if (hasA) store_body(dv, nd.z, A);
+                if (hasB) store_body(dv, nd.w, B);
             }
-            h += c_l;
             grid.sync();
+            if (it == 1 && tid == 0 && l < 4096) {
+                unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+                dv.level_ns[l + 1] = ns;
+                if (l == 0) dv.level_ns[0] = 0;
+            }
         }
     }
 }
@@ -341,7 +452,7 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
     if (rc) return rc;
     BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d);
     BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d);
-    BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 4 * sizeof(int), d->stream));
+    BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 2 * BBX_NCLS * sizeof(int), d->stream));
     BBX_LAUNCH(d, k_frontier0, G, 256, 0, *d);
 
     if (d->coop_blocks == 0) {
@@ -351,7 +462,6 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
         BBX_CUDA(d, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
         BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_levels, 256, 0));
         if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "solver kernel does not fit on an SM", __FILE__, __LINE__);
-        if (per_sm > 4) per_sm = 4;
         d->coop_blocks = per_sm * sms;
     }
     bbx_timing_mark(d, 4);

@@ -96,8 +96,8 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->r_b_hascb, NB);
     DALLOC(d->d_s_count, n_worlds); DALLOC(d->d_b_count, n_worlds);
 
-    DALLOC(d->pos, N); DALLOC(d->lin, N); DALLOC(d->ang, N); DALLOC(d->mass, N); DALLOC(d->timer, N); DALLOC(d->flags, N);
-    DALLOC(d->rot, NB); DALLOC(d->half, NB); DALLOC(d->invI, NB);
+    DALLOC(d->pos, N); DALLOC(d->vel, 2 * (size_t)N); DALLOC(d->mass, N); DALLOC(d->timer, N); DALLOC(d->flags, N);
+    DALLOC(d->boxq, 2 * NB); DALLOC(d->half, NB);
 
     DALLOC(d->grid, 1);
     DALLOC(d->cell_count, d->cap_cells + 1); DALLOC(d->cell_start, d->cap_cells + 1); DALLOC(d->cell_cursor, d->cap_cells + 1);
@@ -106,14 +106,21 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->scan_tmp, 1 << 16);
 
     DALLOC(d->cand_sb, d->cap_cand); DALLOC(d->cand_bb, d->cap_cand);
+    DALLOC(d->hit_ids, d->cap_cand); DALLOC(d->hit_ax, d->cap_cand);
     int C = d->cap_contacts;
     DALLOC(d->c_ids, C); DALLOC(d->c_pt, C); DALLOC(d->c_nrm, C);
-    DALLOC(d->L0, C); DALLOC(d->L1, C); DALLOC(d->L2, C); DALLOC(d->L3, C); DALLOC(d->Lid, C);
+    DALLOC(d->L, 4 * (size_t)C); DALLOC(d->Lid, C);
     DALLOC(d->deg, N + 1); DALLOC(d->adj_start, N + 1); DALLOC(d->adj_cursor, N + 1);
     DALLOC(d->adj, 2 * (size_t)C);
     DALLOC(d->next_a, C); DALLOC(d->next_b, C); DALLOC(d->indeg, C);
-    DALLOC(d->queue, C); DALLOC(d->slot_of, C); DALLOC(d->level_count, C + 4);
-    DALLOC(d->M0, C); DALLOC(d->M1, C); DALLOC(d->M2, C); DALLOC(d->M3, C); DALLOC(d->Mid, C);
+    {
+        static const int min_len[BBX_NCLS] = {1, 1, 2, 3, 4, 5, 7, 9};     // a class-k node holds >= min_len[k] contacts
+        for (int k = 0; k < BBX_NCLS; k++) { DALLOC(d->queue_k[k], C / min_len[k] + 64); DALLOC(d->Nd_k[k], C / min_len[k] + 64); }
+    }
+    d->cap_levels = C < (1 << 20) ? C : (1 << 20);
+    DALLOC(d->slot_of, C); DALLOC(d->level_count, ((size_t)d->cap_levels + 4) * BBX_NCLS);
+    DALLOC(d->M, 4 * (size_t)C);
+    DALLOC(d->level_ns, 4096 + 8);
     DALLOC(d->ctr, 1);
     DALLOC(d->sort_keys, C);
     d->export_buf = NULL;          // allocated on first constraint download
@@ -131,12 +138,13 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
     void* ptrs[] = { d->r_s_pos, d->r_s_radius, d->r_s_vel, d->r_s_force, d->r_s_mass, d->r_s_angvel, d->r_s_torque,
         d->r_s_inertia, d->r_s_timer, d->r_s_static, d->r_s_sleep, d->r_s_hascb, d->r_b_pos, d->r_b_size, d->r_b_rot,
         d->r_b_vel, d->r_b_force, d->r_b_mass, d->r_b_angvel, d->r_b_torque, d->r_b_inertia, d->r_b_timer, d->r_b_static,
-        d->r_b_sleep, d->r_b_hascb, d->d_s_count, d->d_b_count, d->pos, d->lin, d->ang, d->mass, d->timer, d->flags,
-        d->rot, d->half, d->invI, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
-        d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->c_ids, d->c_pt, d->c_nrm,
-        d->L0, d->L1, d->L2, d->L3, d->Lid, d->deg, d->adj_start, d->adj_cursor, d->adj, d->next_a, d->next_b, d->indeg,
-        d->queue, d->slot_of, d->level_count, d->M0, d->M1, d->M2, d->M3, d->Mid, d->ctr, d->sort_keys, d->export_buf };
+        d->r_b_sleep, d->r_b_hascb, d->d_s_count, d->d_b_count, d->pos, d->vel, d->mass, d->timer, d->flags,
+        d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
+        d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
+        d->L, d->Lid, d->deg, d->adj_start, d->adj_cursor, d->adj, d->next_a, d->next_b, d->indeg,
+        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->sort_keys, d->export_buf };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
+    for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
     if (d->ctr_host) cudaFreeHost(d->ctr_host);
     if (d->timing_ev) { for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventDestroy(d->timing_ev[i]); free(d->timing_ev); }
     cudaGetLastError();
@@ -170,8 +178,8 @@ __global__ void k_pack(BbxDev dv)
         bool st = dv.r_s_static[g] != 0;
         float r = dv.r_s_radius[g], m = dv.r_s_mass[g];
         dv.pos[g] = make_float4(dv.r_s_pos[3 * g], dv.r_s_pos[3 * g + 1], dv.r_s_pos[3 * g + 2], r);
-        dv.lin[g] = make_float4(dv.r_s_vel[3 * g], dv.r_s_vel[3 * g + 1], dv.r_s_vel[3 * g + 2], st ? 0.0f : 1.0f / m);
-        dv.ang[g] = make_float4(dv.r_s_angvel[3 * g], dv.r_s_angvel[3 * g + 1], dv.r_s_angvel[3 * g + 2],
+        dv.vel[2 * g] = make_float4(dv.r_s_vel[3 * g], dv.r_s_vel[3 * g + 1], dv.r_s_vel[3 * g + 2], st ? 0.0f : 1.0f / m);
+        dv.vel[2 * g + 1] = make_float4(dv.r_s_angvel[3 * g], dv.r_s_angvel[3 * g + 1], dv.r_s_angvel[3 * g + 2],
                                 st ? 0.0f : 1.0f / dv.r_s_inertia[g]);
         dv.mass[g] = m;
         dv.timer[g] = dv.r_s_timer[g];
@@ -191,11 +199,11 @@ __global__ void k_pack(BbxDev dv)
         float4 q = make_float4(dv.r_b_rot[4 * b], dv.r_b_rot[4 * b + 1], dv.r_b_rot[4 * b + 2], dv.r_b_rot[4 * b + 3]);
         float R = box_bound_radius(h, q);
         dv.pos[g] = make_float4(dv.r_b_pos[3 * b], dv.r_b_pos[3 * b + 1], dv.r_b_pos[3 * b + 2], R);
-        dv.lin[g] = make_float4(dv.r_b_vel[3 * b], dv.r_b_vel[3 * b + 1], dv.r_b_vel[3 * b + 2], st ? 0.0f : 1.0f / m);
-        dv.ang[g] = make_float4(dv.r_b_angvel[3 * b], dv.r_b_angvel[3 * b + 1], dv.r_b_angvel[3 * b + 2], 0.0f);
-        dv.rot[b] = q;
+        dv.vel[2 * g] = make_float4(dv.r_b_vel[3 * b], dv.r_b_vel[3 * b + 1], dv.r_b_vel[3 * b + 2], st ? 0.0f : 1.0f / m);
+        dv.vel[2 * g + 1] = make_float4(dv.r_b_angvel[3 * b], dv.r_b_angvel[3 * b + 1], dv.r_b_angvel[3 * b + 2], 0.0f);
+        dv.boxq[2 * b] = q;
         dv.half[b] = make_float4(h.x, h.y, h.z, 0.0f);
-        dv.invI[b] = st ? make_float4(0, 0, 0, 0)
+        dv.boxq[2 * b + 1] = st ? make_float4(0, 0, 0, 0)
                         : make_float4(1.0f / dv.r_b_inertia[3 * b], 1.0f / dv.r_b_inertia[3 * b + 1],
                                       1.0f / dv.r_b_inertia[3 * b + 2], 0.0f);
         dv.mass[g] = m;
@@ -317,7 +325,7 @@ __global__ void k_unpack(BbxDev dv)
     if (g >= dv.N) return;
     unsigned char f = dv.flags[g];
     if (!(f & BF_VALID)) return;
-    float4 p = dv.pos[g], v = dv.lin[g], w = dv.ang[g];
+    float4 p = dv.pos[g], v = dv.vel[2 * g], w = dv.vel[2 * g + 1];
     if (g < dv.NS) {
         dv.r_s_pos[3 * g] = p.x; dv.r_s_pos[3 * g + 1] = p.y; dv.r_s_pos[3 * g + 2] = p.z;
         dv.r_s_vel[3 * g] = v.x; dv.r_s_vel[3 * g + 1] = v.y; dv.r_s_vel[3 * g + 2] = v.z;
@@ -326,7 +334,7 @@ __global__ void k_unpack(BbxDev dv)
         dv.r_s_timer[g] = dv.timer[g];
     } else {
         int b = g - dv.NS;
-        float4 q = dv.rot[b];
+        float4 q = dv.boxq[2 * b];
         dv.r_b_pos[3 * b] = p.x; dv.r_b_pos[3 * b + 1] = p.y; dv.r_b_pos[3 * b + 2] = p.z;
         dv.r_b_vel[3 * b] = v.x; dv.r_b_vel[3 * b + 1] = v.y; dv.r_b_vel[3 * b + 2] = v.z;
         dv.r_b_angvel[3 * b] = w.x; dv.r_b_angvel[3 * b + 1] = w.y; dv.r_b_angvel[3 * b + 2] = w.z;

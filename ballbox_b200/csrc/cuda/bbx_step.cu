@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
         int4 id = dv.c_ids[c];
         float4 pt = dv.c_pt[c], nr = dv.c_nrm[c];
-        float4 l0 = dv.L0[c], l1 = dv.L1[c], l2 = dv.L2[c], l3 = dv.L3[c];
+        float4 l0 = dv.L[4 * c], l1 = dv.L[4 * c + 1], l2 = dv.L[4 * c + 2], l3 = dv.L[4 * c + 3];
         int ta, wa, la, tb, wb, lb;
         split_gid(dv, id.x, ta, wa, la);
         split_gid(dv, id.y, tb, wb, lb);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         t2 = v3cross(n3, t1);
         float jn = 0.0f, jt0 = 0.0f, jt1 = 0.0f;
         int slot = solved ? dv.slot_of[c] : -1;
-        if (slot >= 0) { float4 m3 = dv.M3[slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
+        if (slot >= 0) { float4 m3 = dv.M[3 * (size_t)dv.cap_contacts + slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
         else if (solved && friction > 0.0f) {
             // a constraint between two non-dynamic bodies is never scheduled, but the reference still
             // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477)
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         r.position_bias = l0.w; r.restitution = restitution; r.friction = friction;
         out[c] = r;
         // emission order: world, phase, i, j, k  
-        unsigned long long i = (unsigned long long)la, j = (unsigned long long)lb, k = (unsigned long long)id.z;
+        unsigned long long i = (unsigned long long)la, j = (unsigned long long)lb, k = (unsigned long long)RUN_K(id.z);
         unsigned long long key;
         if (dv.n_worlds == 1) key = ((unsigned long long)id.w << 53) | (i << 29) | (j << 5) | k;
         else key = ((unsigned long long)wa << 51) | ((unsigned long long)id.w << 48) | (i << 26) | (j << 5) | k;
@@ -165,5 +165,17 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
     }
     if (truncated)
         return bbx_fail(d, BBX_ERR_OVERFLOW, "a world produced more contacts than max_collisions", __FILE__, __LINE__);
+    return 0;
+}
+
+// debug: per-level node counts (per class) and end-of-level timestamps of iteration 1
+extern "C" int bbx_dev_debug_levels(BbxDev* d, int* counts, unsigned long long* ns, int max_levels)
+{
+    if (!d || !counts || !ns) return BBX_ERR_BAD_ARGUMENT;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    int n = max_levels < 4096 ? max_levels : 4096;
+    BBX_CUDA(d, cudaMemcpy(counts, d->level_count, sizeof(int) * (size_t)n * BBX_NCLS, cudaMemcpyDeviceToHost));
+    BBX_CUDA(d, cudaMemcpy(ns, d->level_ns, sizeof(unsigned long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -783,6 +783,13 @@ int BallboxGetStageTiming(PhysicsWorld* w, float* out6, int* steps)
     return p->batch->dev ? batch_check_dev(p->batch, bbx_dev_get_timing(p->batch->dev, out6, steps)) : 0;
 }
 
+int BallboxDebugLevels(PhysicsWorld* w, int* counts8, unsigned long long* ns, int max_levels)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p || !p->batch->dev) return BBX_ERR_BAD_ARGUMENT;
+    return batch_check_dev(p->batch, bbx_dev_debug_levels(p->batch->dev, counts8, ns, max_levels));
+}
+
 static int batch_ok(PhysicsWorldBatch* b) { return b && b->magic == BBX_MAGIC; }
 int  BatchSetDevice(PhysicsWorldBatch* b, int device) { return batch_ok(b) ? BallboxSetDevice(&b->worlds[0].pub, device) : BBX_ERR_BAD_ARGUMENT; }
 void BatchSetStream(PhysicsWorldBatch* b, void* s) { if (batch_ok(b)) BallboxSetStream(&b->worlds[0].pub, s); }

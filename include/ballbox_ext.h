@@ -74,6 +74,8 @@ int BallboxGetStats(PhysicsWorld* world, BallboxStats* out);
 void BallboxSetStageTiming(PhysicsWorld* world, int on);
 int  BallboxGetStageTiming(PhysicsWorld* world, float* out6, int* steps);
 
+int  BallboxDebugLevels(PhysicsWorld* world, int* counts8, unsigned long long* ns, int max_levels);
+
 /* ---- batches of independent worlds (RL style).  All worlds of a batch share
  * one device context and are stepped by the same kernels; worlds never
  * interact.  Settings, gravity and SDF are taken from world 0. --------------- */

@@ -30,3 +30,18 @@ w.step_n(1 / 60, a.steps); w.synchronize()
 torch.cuda.profiler.stop()
 tm, n = w.stage_timing()
 print({k: round(v / max(n, 1), 4) for k, v in tm.items()}, "ms/step over", n, flush=True)
+
+import ctypes as C
+import numpy as np
+L = st.levels if False else w.stats().levels
+cnt = (C.c_int * (8 * 4096))(); ns = (C.c_ulonglong * 4097)()
+lib.dll.BallboxDebugLevels.argtypes = [bb.WP, C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.c_int]
+lib.dll.BallboxDebugLevels(w.ptr, cnt, ns, 4096)
+cnt = np.frombuffer(cnt, dtype=np.int32).reshape(-1, 8)[:L]; ns = np.frombuffer(ns, dtype=np.uint64)[:L + 1].astype(np.int64)
+dt_us = np.diff(ns)[1:] / 1e3
+print("levels", L, "nodes/level (first 12):", cnt.sum(1)[:12].tolist())
+print("class totals:", cnt.sum(0).tolist())
+print("level time us (levels 1..):", np.round(dt_us[:40], 1).tolist())
+print("sum level times (iteration 1) ms:", dt_us.sum() / 1e3, "tail levels (<1000 nodes):", int((cnt.sum(1) < 1000).sum()))
+for l in range(0, L, 4):
+    print(l, cnt[l].tolist(), "us=%.1f" % (dt_us[l - 1] if l >= 1 and l - 1 < len(dt_us) else -1))
