@@ -133,7 +133,9 @@ struct BbxDev {
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy
     unsigned long long *sort_keys;   // export: 64-bit reference-order keys
-    ContactConstraint *export_buf;   // export staging (device)
+    ContactConstraint *export_buf;   // export staging (device), contact order
+    ContactConstraint *export_sorted;   // ... and in emission order
+    unsigned long long *sort_keys_b; unsigned int *sort_vals_a, *sort_vals_b; int *sort_hist, *sort_hist_scan;
 
     // bookkeeping
     long long launches, steps, body_steps;

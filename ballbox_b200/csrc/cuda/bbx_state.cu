@@ -142,7 +142,8 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->Lid, d->deg, d->adj_start, d->adj_cursor, d->adj, d->next_a, d->next_b, d->indeg,
-        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->sort_keys, d->export_buf };
+        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
+        d->sort_hist, d->sort_hist_scan };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
     if (d->ctr_host) cudaFreeHost(d->ctr_host);

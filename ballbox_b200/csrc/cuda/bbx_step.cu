@@ -84,8 +84,12 @@ __device__ __forceinline__ void split_gid(const BbxDev& dv, int g, int& type, in
     else { int b = g - dv.NS; type = 1; world = b / dv.cap_b; local = b - world * dv.cap_b; }
 }
 
+// key = world | phase | i | j | k packed into the fewest bits (fewer radix passes)
+struct KeyBits { int wb, ib, jb; };
+static int bits_for(int n) { int b = 1; while ((1ll << b) < n) b++; return b; }
+
 __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactConstraint* out, unsigned long long* keys,
-                                                            float restitution, float friction, int solved)
+                                                            float restitution, float friction, int solved, KeyBits kb)
 {
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -119,13 +123,29 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         r.position_bias = l0.w; r.restitution = restitution; r.friction = friction;
         out[c] = r;
         // emission order: world, phase, i, j, k  
-        unsigned long long i = (unsigned long long)la, j = (unsigned long long)lb, k = (unsigned long long)RUN_K(id.z);
-        unsigned long long key;
-        if (dv.n_worlds == 1) key = ((unsigned long long)id.w << 53) | (i << 29) | (j << 5) | k;
-        else key = ((unsigned long long)wa << 51) | ((unsigned long long)id.w << 48) | (i << 26) | (j << 5) | k;
+        unsigned long long key = (unsigned long long)wa;
+        key = (key << 3) | (unsigned long long)id.w;
+        key = (key << kb.ib) | (unsigned long long)la;
+        key = (key << kb.jb) | (unsigned long long)lb;
+        key = (key << 5) | (unsigned long long)RUN_K(id.z);
         keys[c] = key;
     }
 }
+
+// sorted[t] = records[order[t]], 26 floats per 104-byte record, coalesced on the write side
+__global__ void __launch_bounds__(256) k_gather_records(const float* src, float* dst, const unsigned int* order, int n)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)n * 26;
+    for (; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int t = (int)(idx / 26), f = (int)(idx - (long long)t * 26);
+        dst[idx] = src[(size_t)order[t] * 26 + f];
+    }
+}
+
+int bbx_radix_sort(BbxDev* d, unsigned long long* keys_a, unsigned int* vals_a, unsigned long long* keys_b,
+                   unsigned int* vals_b, int n, int bits, int* hist, int* hist_scan,
+                   unsigned long long** keys_sorted, unsigned int** vals_sorted);
 
 extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, int cap_per_world, int* counts)
 {
@@ -134,33 +154,59 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
     BBX_CUDA(d, cudaSetDevice(d->device));
     for (int w = 0; w < d->n_worlds; w++) counts[w] = 0;
     if (!d->have_params) return 0;
-    if (d->n_worlds > 1 && (d->cap_s >= (1 << 21) || d->cap_b >= (1 << 21)))
-        return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "batched export supports < 2^21 bodies per world", __FILE__, __LINE__);
-    if (!d->export_buf) BBX_CUDA(d, cudaMalloc((void**)&d->export_buf, sizeof(ContactConstraint) * (size_t)d->cap_contacts));
+    KeyBits kb;
+    kb.wb = bits_for(d->n_worlds); kb.ib = bits_for(d->cap_s > d->cap_b ? d->cap_s : d->cap_b); kb.jb = kb.ib;
+    int total_bits = kb.wb + 3 + kb.ib + kb.jb + 5;
+    if (total_bits > 64) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "export key does not fit 64 bits", __FILE__, __LINE__);
+    size_t C = (size_t)d->cap_contacts;
+    if (!d->export_buf) {
+        size_t tiles = C / 2048 + 2;
+        BBX_CUDA(d, cudaMalloc((void**)&d->export_buf, sizeof(ContactConstraint) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->export_sorted, sizeof(ContactConstraint) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_keys_b, sizeof(unsigned long long) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_vals_a, sizeof(unsigned int) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_vals_b, sizeof(unsigned int) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_hist, sizeof(int) * 256 * tiles));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_hist_scan, sizeof(int) * 256 * tiles));
+    }
     const BbxStepParams* p = &d->last_params;
     BBX_LAUNCH(d, k_export_constraints, BBX_NUM_SMS * 8, 256, 0, *d, d->export_buf, d->sort_keys,
-               p->settings.restitution, p->settings.friction, p->settings.solver_iterations > 0 ? 1 : 0);
+               p->settings.restitution, p->settings.friction, p->settings.solver_iterations > 0 ? 1 : 0, kb);
     BBX_CUDA(d, cudaGetLastError());
     BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
     BBX_CUDA(d, cudaStreamSynchronize(d->stream));
     if (d->ctr_host->overflow & 3)
         return bbx_fail(d, BBX_ERR_OVERFLOW, "contact or candidate buffer overflow: raise max_collisions", __FILE__, __LINE__);
+    if (d->ctr_host->overflow & 16)
+        return bbx_fail(d, BBX_ERR_OVERFLOW, "solver dependency graph deeper than the level table", __FILE__, __LINE__);
     int n = d->ctr_host->n_contacts;
     if (n > d->cap_contacts) n = d->cap_contacts;
     if (n == 0) return 0;
+    unsigned long long* ks; unsigned int* order;
+    int rc = bbx_radix_sort(d, d->sort_keys, d->sort_vals_a, d->sort_keys_b, d->sort_vals_b, n, total_bits,
+                            d->sort_hist, d->sort_hist_scan, &ks, &order);
+    if (rc) return rc;
+    BBX_LAUNCH(d, k_gather_records, BBX_NUM_SMS * 16, 256, 0, (const float*)d->export_buf, (float*)d->export_sorted, order, n);
+    BBX_CUDA(d, cudaGetLastError());
+    if (d->n_worlds == 1) {
+        if (n > cap_per_world)
+            return bbx_fail(d, BBX_ERR_OVERFLOW, "the step produced more contacts than max_collisions", __FILE__, __LINE__);
+        BBX_CUDA(d, cudaMemcpyAsync(out, d->export_sorted, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+        BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+        counts[0] = n;
+        return 0;
+    }
+    // batch: sorted by world first; cut the list at world boundaries on the host
     std::vector<unsigned long long> keys((size_t)n);
     std::vector<ContactConstraint> recs((size_t)n);
-    BBX_CUDA(d, cudaMemcpyAsync(keys.data(), d->sort_keys, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
-    BBX_CUDA(d, cudaMemcpyAsync(recs.data(), d->export_buf, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaMemcpyAsync(keys.data(), ks, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaMemcpyAsync(recs.data(), d->export_sorted, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
     BBX_CUDA(d, cudaStreamSynchronize(d->stream));
-    std::vector<int> order((size_t)n);
-    for (int i = 0; i < n; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
-    int truncated = 0;
+    int wshift = 3 + kb.ib + kb.jb + 5, truncated = 0;
     for (int t = 0; t < n; t++) {
-        int c = order[t];
-        int w = (d->n_worlds == 1) ? 0 : (int)(keys[c] >> 51);
-        if (counts[w] < cap_per_world) out[(size_t)w * cap_per_world + counts[w]++] = recs[c];
+        int w = (int)(keys[t] >> wshift);
+        if (w < 0 || w >= d->n_worlds) continue;
+        if (counts[w] < cap_per_world) out[(size_t)w * cap_per_world + counts[w]++] = recs[t];
         else truncated = 1;
     }
     if (truncated)

@@ -226,7 +226,7 @@ def run_e2e(res, steps):
     el = time.perf_counter() - t0
     ns, nb, C = res["ns"], res["nb"], len(w.constraints())
     h2d = ns * (12 * 5 + 4 * 4 + 2) + nb * (12 * 7 + 16 + 4 * 2 + 2)
-    d2h = ns * (12 * 3 + 4 + 1) + nb * (12 * 3 + 16 + 4 + 1) + C * (104 + 8)
+    d2h = ns * (12 * 3 + 4 + 1) + nb * (12 * 3 + 16 + 4 + 1) + C * 104
     return {"value": res["bodies"] * steps / el, "unit": "body-steps/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": el / steps * 1e3}
 
