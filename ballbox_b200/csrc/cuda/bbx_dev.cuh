@@ -116,10 +116,13 @@ struct BbxDev {
 
     // solver records in contact order (written by presolve)
     float4 *L;                   // 4 per contact, 64-byte records: (n, bias) (rA, mN) (rB, mT0) (jn, jt0, jt1, mT1)
-    int2   *Lid;                 // per node (first contact of a run): dynamic gids (or -1)
+    int4   *node;                // 2 per node head (32-byte sector): [2c] = (dynamic gid A or -1, dynamic gid B or -1,
+                                 // run length, class), [2c+1] = (successor on A, successor on B, -, -); a successor is
+                                 // head contact id | class << 28, or -1
     int *deg, *adj_start, *adj_cursor;           // N (+1)
     unsigned long long *adj;                     // 2*cap_contacts
-    int *next_a, *next_b, *indeg;                // cap_contacts
+    int *indeg;                                  // cap_contacts (node heads)
+    unsigned int *bar;                           // grid barrier counter of the solve kernel
     // level-major node queues, one per size class so that the lanes of a warp sweep equally long runs
     int  *queue_k[BBX_NCLS];                     // node ids (first contact of the run)
     int4 *Nd_k[BBX_NCLS];                        // (first M slot, constraint count, dynamic gid A, dynamic gid B)

@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         L[3] = make_float4(0.0f, 0.0f, 0.0f, mT1);                                      // impulses start at 0 (:1203-1206)
         dv.slot_of[c] = -1;
         if (RUN_K(id.z) == 0) {                                                         // node head
-            dv.Lid[c] = make_int2(dynA ? a : -1, dynB ? b : -1);
+            int m = RUN_LEN(id.z);
+            dv.node[2 * (size_t)c] = make_int4(dynA ? a : -1, dynB ? b : -1, m, bbx_node_class(m, a >= dv.NS || b >= dv.NS));
+            dv.node[2 * (size_t)c + 1] = make_int4(-1, -1, 0, 0);
             dv.indeg[c] = (dynA ? 1 : 0) + (dynB ? 1 : 0);
-            dv.next_a[c] = -1; dv.next_b[c] = -1;
             if (dynA) atomicAdd(&dv.deg[a], 1);
             if (dynB) atomicAdd(&dv.deg[b], 1);
         }
@@ -105,13 +106,14 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
 // ---------------------------------------------------------------------------
 // K10 dependency graph: per-body ordered node lists -> successor links
 // ---------------------------------------------------------------------------
-// order of a node inside ONE body's list: (phase, partner index)
-__device__ __forceinline__ unsigned int body_order_key(const BbxDev& dv, int4 id, bool for_a)
+// order of a node inside ONE body's list: (phase, partner index); the low bits carry the node's
+// class (they cannot affect the order: (phase, partner) is unique within a body's list)
+__device__ __forceinline__ unsigned int body_order_key(const BbxDev& dv, int4 id, bool for_a, int cls)
 {
     int other = for_a ? id.y : id.x;
     unsigned int partner = 0;
     if (other >= 0) partner = (unsigned int)(other < dv.NS ? other : other - dv.NS);
-    return ((unsigned int)id.w << 29) | (partner << 5);
+    return ((unsigned int)id.w << 29) | (partner << 5) | (unsigned int)cls;
 }
 
 __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv)
@@ -120,14 +122,14 @@ __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv)
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
         int4 id = dv.c_ids[c];
         if (RUN_K(id.z) != 0) continue;
-        int2 l = dv.Lid[c];
+        int4 l = dv.node[2 * (size_t)c];
         if (l.x >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.x], 1);
-            dv.adj[slot] = ((unsigned long long)body_order_key(dv, id, true) << 32) | (unsigned int)c;
+            dv.adj[slot] = ((unsigned long long)body_order_key(dv, id, true, l.w) << 32) | (unsigned int)c;
         }
         if (l.y >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.y], 1);
-            dv.adj[slot] = ((unsigned long long)body_order_key(dv, id, false) << 32) | (unsigned int)c;
+            dv.adj[slot] = ((unsigned long long)body_order_key(dv, id, false, l.w) << 32) | (unsigned int)c;
         }
     }
 }
@@ -152,8 +154,11 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv)
             int prev = (int)(unsigned int)lst[0];
             atomicSub(&dv.indeg[prev], 1);                 // first node of this body has no predecessor here
             for (int i = 1; i < d; i++) {
-                int cur = (int)(unsigned int)lst[i];
-                if (dv.Lid[prev].x == x) dv.next_a[prev] = cur; else dv.next_b[prev] = cur;
+                unsigned long long e2 = lst[i];
+                int cur = (int)(unsigned int)e2;
+                int link = cur | ((int)((e2 >> 32) & 7u) << 28);          // successor id | its class
+                int* nx = (int*)&dv.node[2 * (size_t)prev + 1];
+                if (dv.node[2 * (size_t)prev].x == x) nx[0] = link; else nx[1] = link;
                 prev = cur;
             }
         }
@@ -175,10 +180,10 @@ __global__ void __launch_bounds__(256) k_frontier0(BbxDev dv)
         if (c < n) {
             int4 id = dv.c_ids[c];
             if (RUN_K(id.z) == 0) {
-                int2 l = dv.Lid[c];
+                int4 l = dv.node[2 * (size_t)c];
                 if (l.x >= 0 || l.y >= 0) {
-                    my_solver += RUN_LEN(id.z); my_nodes++;
-                    if (dv.indeg[c] == 0) cls = bbx_node_class(RUN_LEN(id.z), id.x >= dv.NS || id.y >= dv.NS);
+                    my_solver += l.z; my_nodes++;
+                    if (dv.indeg[c] == 0) cls = l.w;
                 }
             }
         }
@@ -325,13 +330,38 @@ __device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level
     lm.pref[BBX_NCLS] = run;
 }
 
-__global__ void __launch_bounds__(256, 3) k_solve_levels(BbxDev dv, SolveParams sp)
+// 3 blocks of 256 threads per SM (80 registers).  One 768-thread block per SM was measured
+// slower (6.6 vs 5.8 ms per step at 1M bodies) although it makes the barrier cheaper.
+#define LC_CACHE 512
+#define SOLVE_THREADS 256
+#define SOLVE_BLOCKS_PER_SM 3
+
+// Grid-wide barrier: cooperative-groups grid.sync() measured 1.2 us at 444 x 256 threads on B200,
+// a hand-written arrive/poll barrier 1.7 us (tools/micro/barrier_bench.cu), so we use the former.
+// append to the next level's class queues: lanes are grouped by class with one match_any
+__device__ __forceinline__ void push_successor(const BbxDev& dv, int* lc_next, const LevelMap& lm, int link)
+{
+    bool has = link >= 0;
+    unsigned int active = __ballot_sync(0xffffffffu, has);
+    if (!has) return;
+    int cls = (link >> 28) & 7, node = link & 0x0fffffff;
+    unsigned int peers = __match_any_sync(active, cls);
+    int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&lc_next[cls], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    int slot = base + __popc(peers & ((1u << lane) - 1u));
+    dv.queue_k[cls][lm.head[cls] + lm.cnt[cls] + slot] = node;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_levels(BbxDev dv, SolveParams sp)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ LevelMap lm;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
     int* lc = dv.level_count;                       // lc[level * BBX_NCLS + class]
+    const size_t PL = (size_t)dv.cap_contacts;
 
     // ---- iteration 0: discover levels (Kahn) while solving ----
     int lvl = 0;
@@ -350,19 +380,21 @@ __global__ void __launch_bounds__(256, 3) k_solve_levels(BbxDev dv, SolveParams 
             bool live = idx < lm.cnt[k];
             int p = lm.head[k] + idx;
             int sa = -1, sb = -1, m = 0, c = 0;
-            int2 id = make_int2(-1, -1);
+            int4 nd0 = make_int4(-1, -1, 0, 0);
             if (live) {
                 c = __ldcg(&dv.queue_k[k][p]);
-                m = RUN_LEN(dv.c_ids[c].z);
-                id = dv.Lid[c];
+                F8 rec = ld256_nc((const float4*)&dv.node[2 * (size_t)c]);       // ids, run length, successors: one sector
+                nd0 = make_int4(__float_as_int(rec.a.x), __float_as_int(rec.a.y), __float_as_int(rec.a.z), 0);
+                sa = __float_as_int(rec.b.x); sb = __float_as_int(rec.b.y);
+                m = nd0.z;
             }
             int mbase = warp_reserve(&dv.ctr->n_mslots, m);
             if (live) {
-                __stcs(&dv.Nd_k[k][p], make_int4(mbase, m, id.x, id.y));
-                bool hasA = id.x >= 0, hasB = id.y >= 0;
+                __stcg(&dv.Nd_k[k][p], make_int4(mbase, m, nd0.x, nd0.y));
+                bool hasA = nd0.x >= 0, hasB = nd0.y >= 0;
                 BodyState A, B;
-                if (hasA) load_body(dv, id.x, A);
-                if (hasB) load_body(dv, id.y, B);
+                if (hasA) load_body(dv, nd0.x, A);
+                if (hasB) load_body(dv, nd0.y, B);
                 for (int j = 0; j < m; j++) {
                     // contact-order records are gathered once (two 256-bit loads), then written plane-major
                     const float4* L = dv.L + 4 * (size_t)(c + j);
@@ -370,29 +402,17 @@ __global__ void __launch_bounds__(256, 3) k_solve_levels(BbxDev dv, SolveParams 
                     float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
                     solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     float4* M = dv.M + (size_t)(mbase + j);
-                    const size_t PL = (size_t)dv.cap_contacts;
-                    __stcs(M, c0); __stcs(M + PL, c1); __stcs(M + 2 * PL, c2); __stcs(M + 3 * PL, c3);
+                    __stcg(M, c0); __stcg(M + PL, c1); __stcg(M + 2 * PL, c2); __stcg(M + 3 * PL, c3);
                     dv.slot_of[c + j] = mbase + j;
                 }
-                if (hasA) { store_body(dv, id.x, A); wake_body(dv, id.x); }
-                if (hasB) { store_body(dv, id.y, B); wake_body(dv, id.y); }
-                sa = dv.next_a[c]; sb = dv.next_b[c];
-                if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) != 1) sa = -1;
-                if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) != 1) sb = -1;
+                if (hasA) { store_body(dv, nd0.x, A); wake_body(dv, nd0.x); }
+                if (hasB) { store_body(dv, nd0.y, B); wake_body(dv, nd0.y); }
+                if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) != 1) sa = -1;
+                if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) != 1) sb = -1;
             }
             // successors that became ready join the next level of their own class
-            #pragma unroll 1
-            for (int side = 0; side < 2; side++) {
-                int sn = side ? sb : sa;
-                int sk = -1;
-                if (sn >= 0) { int4 sid = dv.c_ids[sn]; sk = bbx_node_class(RUN_LEN(sid.z), sid.x >= dv.NS || sid.y >= dv.NS); }
-                unsigned int any = __ballot_sync(0xffffffffu, sn >= 0);
-                if (!any) continue;
-                for (int kk = 0; kk < BBX_NCLS; kk++) {
-                    int slot = warp_append(&lc_next[kk], sk == kk);
-                    if (sk == kk) dv.queue_k[kk][lm.head[kk] + lm.cnt[kk] + slot] = sn;
-                }
-            }
+            push_successor(dv, lc_next, lm, sa);
+            push_successor(dv, lc_next, lm, sb);
         }
         grid.sync();
         if (threadIdx.x == 0) level_map_load(lm, lc + (lvl + 1) * BBX_NCLS, false);
@@ -401,13 +421,29 @@ __global__ void __launch_bounds__(256, 3) k_solve_levels(BbxDev dv, SolveParams 
     }
     const int n_levels = lvl;
     if (tid == 0) dv.ctr->n_levels = n_levels;
-
     if (tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); dv.level_ns[4096 + 1] = ns; }
+
     // ---- iterations 1..I-1: stream the level-major records ----
+    // (prefetching the next level's descriptors/records across the barrier was tried and measured
+    //  slower: profiles/r01_notes.md)
+    // the per-level class counts are static from here on: keep the first LC_CACHE levels in shared
+    // memory so that a level does not start with a global round trip
+    __shared__ int lc_cache[LC_CACHE * BBX_NCLS];
+    for (int i = threadIdx.x; i < min(n_levels, LC_CACHE) * BBX_NCLS; i += blockDim.x) lc_cache[i] = __ldcg(&lc[i]);
+    __syncthreads();
     for (int it = 1; it < sp.iterations; it++) {
         for (int l = 0; l < n_levels; l++) {
             __syncthreads();
-            if (threadIdx.x == 0) level_map_load(lm, lc + l * BBX_NCLS, l == 0);
+            if (threadIdx.x == 0) {
+                int run = 0;
+                for (int k = 0; k < BBX_NCLS; k++) {
+                    if (l == 0) lm.head[k] = 0; else lm.head[k] += lm.cnt[k];
+                    lm.cnt[k] = (l < LC_CACHE) ? lc_cache[l * BBX_NCLS + k] : __ldcg(&lc[l * BBX_NCLS + k]);
+                    lm.pref[k] = run;
+                    run += (lm.cnt[k] + 31) & ~31;
+                }
+                lm.pref[BBX_NCLS] = run;
+            }
             __syncthreads();
             const int total = lm.pref[BBX_NCLS];
             for (int t = tid; t < total; t += stride) {
@@ -416,17 +452,16 @@ __global__ void __launch_bounds__(256, 3) k_solve_levels(BbxDev dv, SolveParams 
                 for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
                 int idx = t - lm.pref[k];
                 if (idx >= lm.cnt[k]) continue;
-                int4 nd = __ldcs(&dv.Nd_k[k][lm.head[k] + idx]);
+                int4 nd = __ldcg(&dv.Nd_k[k][lm.head[k] + idx]);
                 bool hasA = nd.z >= 0, hasB = nd.w >= 0;
                 BodyState A, B;
                 if (hasA) load_body(dv, nd.z, A);
                 if (hasB) load_body(dv, nd.w, B);
                 float4* M = dv.M + (size_t)nd.x;
-                const size_t PL = (size_t)dv.cap_contacts;
                 for (int j = 0; j < nd.y; j++, M++) {
-                    float4 c0 = __ldcs(M), c1 = __ldcs(M + PL), c2 = __ldcs(M + 2 * PL), c3 = __ldcs(M + 3 * PL);
+                    float4 c0 = __ldcg(M), c1 = __ldcg(M + PL), c2 = __ldcg(M + 2 * PL), c3 = __ldcg(M + 3 * PL);
                     solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
-                    __stcs(M + 3 * PL, c3);
+                    __stcg(M + 3 * PL, c3);
                 }
                 if (hasA) store_body(dv, nd.z, A);
                 if (hasB) store_body(dv, nd.w, B);
@@ -460,8 +495,9 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
         BBX_CUDA(d, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d->device));
         if (!coop) return bbx_fail(d, BBX_ERR_NO_DEVICE, "device lacks cooperative launch", __FILE__, __LINE__);
         BBX_CUDA(d, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
-        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_levels, 256, 0));
+        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_levels, SOLVE_THREADS, 0));
         if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "solver kernel does not fit on an SM", __FILE__, __LINE__);
+        if (per_sm > SOLVE_BLOCKS_PER_SM) per_sm = SOLVE_BLOCKS_PER_SM;
         d->coop_blocks = per_sm * sms;
     }
     bbx_timing_mark(d, 4);
@@ -470,7 +506,7 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
     sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = p->settings.solver_iterations;
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
-    BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(256), args, 0, d->stream));
+    BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
     d->launches++;
     BBX_CUDA(d, cudaGetLastError());
     return 0;

@@ -109,10 +109,10 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->hit_ids, d->cap_cand); DALLOC(d->hit_ax, d->cap_cand);
     int C = d->cap_contacts;
     DALLOC(d->c_ids, C); DALLOC(d->c_pt, C); DALLOC(d->c_nrm, C);
-    DALLOC(d->L, 4 * (size_t)C); DALLOC(d->Lid, C);
+    DALLOC(d->L, 4 * (size_t)C); DALLOC(d->node, 2 * (size_t)C); DALLOC(d->bar, 8);
     DALLOC(d->deg, N + 1); DALLOC(d->adj_start, N + 1); DALLOC(d->adj_cursor, N + 1);
     DALLOC(d->adj, 2 * (size_t)C);
-    DALLOC(d->next_a, C); DALLOC(d->next_b, C); DALLOC(d->indeg, C);
+    DALLOC(d->indeg, C);
     {
         static const int min_len[BBX_NCLS] = {1, 1, 2, 3, 4, 5, 7, 9};     // a class-k node holds >= min_len[k] contacts
         for (int k = 0; k < BBX_NCLS; k++) { DALLOC(d->queue_k[k], C / min_len[k] + 64); DALLOC(d->Nd_k[k], C / min_len[k] + 64); }
@@ -141,7 +141,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->r_b_sleep, d->r_b_hascb, d->d_s_count, d->d_b_count, d->pos, d->vel, d->mass, d->timer, d->flags,
         d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
-        d->L, d->Lid, d->deg, d->adj_start, d->adj_cursor, d->adj, d->next_a, d->next_b, d->indeg,
+        d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
         d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
