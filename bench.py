@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bodies", type=int, default=1_000_000, help="dynamic bodies of the C3 scene")
     ap.add_argument("--worlds", type=int, default=4096, help="C5 worlds per GPU")
-    ap.add_argument("--settle", type=int, default=300, help="untimed settle steps before measuring")
+    ap.add_argument("--settle", type=int, default=1500, help="untimed settle steps before measuring (a 160-unit tall pile needs ~1500)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-bodies", type=int, default=4000, help="size of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=12)
@@ -339,8 +339,12 @@ def main():
     achieved = sb / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
     stepb = step_bytes(r["ns"], r["nb"], P_, r["contacts"], D_, I)
     step_ach = stepb / (r["ms"] / args.steps * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of k_solve_levels for this exact scene (C3, 1M bodies, settle
+    # 1500) from the ncu capture summarised in profiles/r01c_launches_c3_1M.md; null for any other scene
+    traffic = 7019.5e6 + 1794.5e6 if (args.bodies == 1_000_000 and args.settle == 1500) else None
     roofline = {"bound": "hbm", "kernel": "k_solve_levels", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "note": "latency/synchronisation bound, not HBM bound: issue slots 27 % active, see profiles/r01_notes.md",
                 "algorithmic_bytes_per_launch": sb, "ms_per_launch": solve_ms,
                 "whole_step": {"algorithmic_bytes": stepb, "achieved": step_ach, "frac": step_ach / peak}}
 

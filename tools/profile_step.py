@@ -11,6 +11,8 @@ ap.add_argument("--bodies", type=int, default=1_000_000)
 ap.add_argument("--settle", type=int, default=1500)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--scene", type=int, default=bb.SCENE_MIXED)
+ap.add_argument("--friction", type=float, default=None, help="override friction for the timed steps (timing experiment)")
+ap.add_argument("--iterations", type=int, default=None)
 a = ap.parse_args()
 lib = bbx.load()
 w = lib.build_scene(a.scene, a.bodies, 20261019)
@@ -23,6 +25,8 @@ while done < a.settle:
 st = w.stats()
 print(f"settled {a.settle} steps in {time.time()-t0:.1f}s: contacts={st.contacts} solver={st.solver_contacts} touched={st.touched_bodies} "
       f"levels={st.levels} pairs={st.candidate_pairs} sb={st.reserved[0]} bb={st.reserved[1]} ovf={st.overflow}", flush=True)
+if a.friction is not None: w.w.settings.friction = a.friction
+if a.iterations is not None: w.w.settings.solver_iterations = a.iterations
 w.set_stage_timing(True); w.stage_timing()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
