@@ -133,6 +133,13 @@ struct BbxDev {
     float4 *M;                   // same four float4 fields, plane-major: field r of slot s is M[r*cap_contacts + s]; a node's
                                  // slots are contiguous, so a warp of equal-length nodes loads each plane coalesced
 
+    // callback events (allocated when the first step with want_callbacks runs)
+    int cap_events;
+    unsigned long long *ev_key;  // emission-order key (same packing as the export key)
+    int *ev_step;
+    CollisionContact *ev_contact;
+    int step_in_batch;           // step index since the last event fetch
+
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy
     unsigned long long *sort_keys;   // export: 64-bit reference-order keys
@@ -172,6 +179,7 @@ int bbx_stage_broadphase(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_narrowphase(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_solve(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_integrate_positions(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_collect_events(BbxDev* d, const BbxStepParams* p);
 int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out);
 
 #ifdef __CUDACC__

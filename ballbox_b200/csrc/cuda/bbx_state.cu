@@ -142,7 +142,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
-        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
+        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
@@ -314,6 +314,28 @@ extern "C" int bbx_dev_upload_forces(BbxDev* d, const BbxHostBodies* hb)
         BBX_CUDA(d, cudaMemcpyAsync(d->r_b_force, hb->b_force, 12 * NB, cudaMemcpyHostToDevice, d->stream));
         BBX_CUDA(d, cudaMemcpyAsync(d->r_b_torque, hb->b_torque, 12 * NB, cudaMemcpyHostToDevice, d->stream));
     }
+    return 0;
+}
+
+__global__ void k_set_cb_flags(BbxDev dv)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= dv.N) return;
+    unsigned char f = dv.flags[g];
+    if (!(f & BF_VALID)) return;
+    bool cb = (g < dv.NS) ? dv.r_s_hascb[g] != 0 : dv.r_b_hascb[g - dv.NS] != 0;
+    dv.flags[g] = cb ? (f | BF_HASCB) : (f & (unsigned char)~BF_HASCB);
+}
+
+extern "C" int bbx_dev_upload_callback_flags(BbxDev* d, const BbxHostBodies* hb)
+{
+    if (!d || !hb) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    if (d->NS && hb->s_hascb) BBX_CUDA(d, cudaMemcpyAsync(d->r_s_hascb, hb->s_hascb, d->NS, cudaMemcpyHostToDevice, d->stream));
+    if (d->NB && hb->b_hascb) BBX_CUDA(d, cudaMemcpyAsync(d->r_b_hascb, hb->b_hascb, d->NB, cudaMemcpyHostToDevice, d->stream));
+    BBX_LAUNCH(d, k_set_cb_flags, bbx_blocks(d->N, 256), 256, 0, *d);
+    BBX_CUDA(d, cudaGetLastError());
     return 0;
 }
 

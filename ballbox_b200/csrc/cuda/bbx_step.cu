@@ -61,6 +61,7 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
         if ((rc = bbx_stage_broadphase(d, &q))) return rc;             // stage 3: pair finding (+ sphere-sphere)
         bbx_timing_mark(d, 2);
         if ((rc = bbx_stage_narrowphase(d, &q))) return rc;            // stage 3: contact generation
+        if (q.want_callbacks && (rc = bbx_stage_collect_events(d, &q))) return rc;
         bbx_timing_mark(d, 3);
         if ((rc = bbx_stage_solve(d, &q))) return rc;                  // stage 4 (marks 4 inside, before the solve kernel)
         bbx_timing_mark(d, 5);
@@ -69,6 +70,7 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
         if (d->timing_on && d->timing_steps < d->timing_cap) d->timing_steps++;
         q.has_forces = 0;                                              // forces were consumed and cleared by step 0
         d->steps++;
+        d->step_in_batch++;
         d->body_steps += (long long)d->n_valid_spheres + d->n_valid_boxes;
     }
     return 0;
@@ -130,6 +132,119 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         key = (key << 5) | (unsigned long long)RUN_K(id.z);
         keys[c] = key;
     }
+}
+
+// ---------------------------------------------------------------------------
+// callback events
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long emission_key(const BbxDev& dv, int4 id, KeyBits kb, int& wa, int& ta, int& la, int& tb, int& lb)
+{
+    int wb;
+    split_gid(dv, id.x, ta, wa, la);
+    split_gid(dv, id.y, tb, wb, lb);
+    unsigned long long key = (unsigned long long)wa;
+    key = (key << 3) | (unsigned long long)id.w;
+    key = (key << kb.ib) | (unsigned long long)la;
+    key = (key << kb.jb) | (unsigned long long)lb;
+    key = (key << 5) | (unsigned long long)RUN_K(id.z);
+    return key;
+}
+
+__global__ void __launch_bounds__(256) k_collect_events(BbxDev dv, KeyBits kb, int step)
+{
+    int n = min(dv.ctr->n_contacts, dv.cap_contacts);
+    int n_round = (n + 31) & ~31;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += gridDim.x * blockDim.x) {
+        bool fire = false;
+        int4 id = make_int4(0, 0, 0, 0);
+        if (c < n) {
+            id = dv.c_ids[c];
+            bool cb = (dv.flags[id.x] & BF_HASCB) || (id.y >= 0 && (dv.flags[id.y] & BF_HASCB));
+            // box-box: once per pair with the first manifold point (:2034-2044); box-SDF: never (:2413-2477)
+            fire = cb && id.w != PH_BSDF && (id.w != PH_BB || RUN_K(id.z) == 0);
+        }
+        int slot = warp_append(&dv.ctr->n_events, fire);
+        if (!fire) continue;
+        if (slot >= dv.cap_events) { atomicOr(&dv.ctr->overflow, 8); continue; }
+        int wa, ta, la, tb, lb;
+        dv.ev_key[slot] = emission_key(dv, id, kb, wa, ta, la, tb, lb);
+        dv.ev_step[slot] = step;
+        float4 pt = dv.c_pt[c], nr = dv.c_nrm[c];
+        CollisionContact k;
+        k.bodyA_type = ta; k.bodyA_index = la; k.bodyB_type = tb; k.bodyB_index = lb;
+        k.contact_point.x = pt.x; k.contact_point.y = pt.y; k.contact_point.z = pt.z;
+        k.contact_normal.x = nr.x; k.contact_normal.y = nr.y; k.contact_normal.z = nr.z;
+        k.penetration = pt.w;
+        dv.ev_contact[slot] = k;
+    }
+}
+
+static KeyBits key_bits_of(const BbxDev* d)
+{
+    KeyBits kb;
+    kb.wb = bits_for(d->n_worlds); kb.ib = bits_for(d->cap_s > d->cap_b ? d->cap_s : d->cap_b); kb.jb = kb.ib;
+    return kb;
+}
+
+int bbx_stage_collect_events(BbxDev* d, const BbxStepParams* p)
+{
+    (void)p;
+    if (!d->ev_key) {
+        long long cap = d->cap_contacts < (1 << 22) ? d->cap_contacts : (1 << 22);
+        d->cap_events = (int)cap;
+        BBX_CUDA(d, cudaMalloc((void**)&d->ev_key, sizeof(unsigned long long) * (size_t)cap));
+        BBX_CUDA(d, cudaMalloc((void**)&d->ev_step, sizeof(int) * (size_t)cap));
+        BBX_CUDA(d, cudaMalloc((void**)&d->ev_contact, sizeof(CollisionContact) * (size_t)cap));
+    }
+    BBX_LAUNCH(d, k_collect_events, BBX_NUM_SMS * 8, 256, 0, *d, key_bits_of(d), d->step_in_batch);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bbx_dev_event_capacity(BbxDev* d) { return d ? (d->cap_events ? d->cap_events : (d->cap_contacts < (1 << 22) ? d->cap_contacts : (1 << 22))) : 0; }
+
+__global__ void k_reset_events(BbxDev dv) { dv.ctr->n_events = 0; }
+
+extern "C" int bbx_dev_fetch_events(BbxDev* d, CollisionContact* contacts, int* steps, int* worlds, int max_events, int* count)
+{
+    if (!d || !count) return BBX_ERR_BAD_ARGUMENT;
+    *count = 0;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    d->step_in_batch = 0;
+    if (!d->ev_key) return 0;
+    BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    int n = d->ctr_host->n_events;
+    bool overflow = (d->ctr_host->overflow & 8) != 0 || n > d->cap_events;
+    if (n > d->cap_events) n = d->cap_events;
+    if (n > max_events) { n = max_events; overflow = true; }
+    if (n > 0) {
+        std::vector<unsigned long long> keys((size_t)n);
+        std::vector<int> st((size_t)n);
+        std::vector<CollisionContact> recs((size_t)n);
+        BBX_CUDA(d, cudaMemcpyAsync(keys.data(), d->ev_key, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+        BBX_CUDA(d, cudaMemcpyAsync(st.data(), d->ev_step, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+        BBX_CUDA(d, cudaMemcpyAsync(recs.data(), d->ev_contact, sizeof(CollisionContact) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+        BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+        std::vector<int> order((size_t)n);
+        for (int i = 0; i < n; i++) order[i] = i;
+        // deterministic replay order: step, then the reference's emission order
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return st[a] != st[b] ? st[a] < st[b] : keys[a] < keys[b]; });
+        KeyBits kb = key_bits_of(d);
+        int wshift = 3 + kb.ib + kb.jb + 5;
+        for (int t = 0; t < n; t++) {
+            int e = order[t];
+            contacts[t] = recs[e];
+            if (steps) steps[t] = st[e];
+            if (worlds) worlds[t] = (int)(keys[e] >> wshift);
+        }
+    }
+    BBX_LAUNCH(d, k_reset_events, 1, 1, 0, *d);
+    BBX_CUDA(d, cudaGetLastError());
+    *count = n;
+    if (overflow) return bbx_fail(d, BBX_ERR_OVERFLOW, "callback event buffer overflow: fetch events more often", __FILE__, __LINE__);
+    return 0;
 }
 
 // sorted[t] = records[order[t]], 26 floats per 104-byte record, coalesced on the write side

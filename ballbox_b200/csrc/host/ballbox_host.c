@@ -40,7 +40,8 @@ struct PhysicsWorldBatch {
     void* stream;
     int sync_mode, schedule;
     int sdf_id; float sdf_params[8];
-    int uploaded, forces_dirty, n_callbacks, timing;
+    int uploaded, forces_dirty, n_callbacks, cb_dirty, timing;
+    CollisionContact* ev_contacts; int *ev_steps, *ev_worlds; int ev_cap;
     int has_err; char err[256];
 };
 
@@ -185,6 +186,7 @@ static void batch_free(struct PhysicsWorldBatch* b)
     for (int i = 0; i < 25; i++) bbx_host_free(arrs[i], b->pinned[i]);
     bbx_host_free(b->constraints, b->pinned_constraints);
     if (b->worlds) for (int w = 0; w < b->n_worlds; w++) free(b->worlds[w].collisions.contacts);
+    free(b->ev_contacts); free(b->ev_steps); free(b->ev_worlds);
     free(b->s_count); free(b->b_count); free(b->s_cb); free(b->b_cb); free(b->ccount); free(b->worlds);
     b->magic = 0;
     free(b);
@@ -460,6 +462,7 @@ static void recount_callbacks(struct PhysicsWorldBatch* b)
     for (size_t i = 0; i < NS; i++) { b->hb.s_hascb[i] = b->s_cb[i] != NULL; n += b->hb.s_hascb[i]; }
     for (size_t i = 0; i < NB; i++) { b->hb.b_hascb[i] = b->b_cb[i] != NULL; n += b->hb.b_hascb[i]; }
     b->n_callbacks = n;
+    b->cb_dirty = 1;
 }
 
 void SetSphereCollisionCallback(PhysicsWorld* world, int i, OnCollision cb)
@@ -573,11 +576,11 @@ static int batch_upload(struct PhysicsWorldBatch* b)
     if (rc) return rc;
     for (int w = 0; w < b->n_worlds; w++) { b->s_count[w] = b->worlds[w].spheres.count; b->b_count[w] = b->worlds[w].boxes.count; }
     rc = batch_check_dev(b, bbx_dev_upload(b->dev, &b->hb));
-    if (!rc) b->uploaded = 1;
+    if (!rc) { b->uploaded = 1; b->cb_dirty = 0; }
     return rc;
 }
 
-static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, BbxStepParams* p)
+static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, int want_callbacks, BbxStepParams* p)
 {
     PhysicsWorld* w0 = &b->worlds[0].pub;
     memset(p, 0, sizeof(*p));
@@ -599,7 +602,7 @@ static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, Bb
     }
     p->solver_schedule = b->schedule;
     p->has_forces = has_forces;
-    p->want_callbacks = b->n_callbacks > 0;
+    p->want_callbacks = want_callbacks;
     return 0;
 }
 
@@ -661,6 +664,40 @@ static void replay_callbacks(BbxWorldPriv* p)
     }
 }
 
+/* device event buffer -> callbacks, same dispatch rules as replay_callbacks */
+static int replay_events(struct PhysicsWorldBatch* b)
+{
+    if (!b->ev_contacts) {
+        b->ev_cap = bbx_dev_event_capacity(b->dev);
+        b->ev_contacts = (CollisionContact*)malloc(sizeof(CollisionContact) * (size_t)(b->ev_cap ? b->ev_cap : 1));
+        b->ev_steps = (int*)malloc(sizeof(int) * (size_t)(b->ev_cap ? b->ev_cap : 1));
+        b->ev_worlds = (int*)malloc(sizeof(int) * (size_t)(b->ev_cap ? b->ev_cap : 1));
+        if (!b->ev_contacts || !b->ev_steps || !b->ev_worlds) { batch_fail(b, "out of host memory for callback events"); return BBX_ERR_BAD_ARGUMENT; }
+    }
+    int n = 0;
+    int rc = batch_check_dev(b, bbx_dev_fetch_events(b->dev, b->ev_contacts, b->ev_steps, b->ev_worlds, b->ev_cap, &n));
+    for (int e = 0; e < n; e++) {
+        CollisionContact* k = &b->ev_contacts[e];
+        int w = b->ev_worlds[e];
+        if (w < 0 || w >= b->n_worlds) continue;
+        SphereSystem* S = &b->worlds[w].spheres; BoxSystem* B = &b->worlds[w].boxes;
+        int a = k->bodyA_index, c = k->bodyB_index;
+        if (k->bodyA_type == 0 && k->bodyB_type == 0) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 0, c, k);
+            if (S->collision_callbacks[c]) S->collision_callbacks[c](c, 0, a, k);
+        } else if (k->bodyA_type == 1 && k->bodyB_type == 1) {
+            if (B->collision_callbacks[a]) B->collision_callbacks[a](a, 1, c, k);
+            if (B->collision_callbacks[c]) B->collision_callbacks[c](c, 1, a, k);
+        } else if (k->bodyA_type == 0 && k->bodyB_type == 1) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 1, c, k);
+            if (B->collision_callbacks[c]) B->collision_callbacks[c](c, 0, a, k);
+        } else if (k->bodyA_type == 0 && k->bodyB_type == 2) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 2, 0, k);
+        }
+    }
+    return rc;
+}
+
 static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
 {
     if (b->has_err) return BBX_ERR_STICKY;
@@ -673,7 +710,7 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
         for (int s = 0; s < steps; s++) {
             BbxStepParams prm;
             if ((rc = batch_upload(b))) return rc;
-            if ((rc = fill_params(b, dt, 1, &prm))) return rc;
+            if ((rc = fill_params(b, dt, 1, 0, &prm))) return rc;      /* compat replays from the downloaded list */
             if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, 1)))) return rc;
             if ((rc = batch_download(b, BBX_DL_BODIES | BBX_DL_CONSTRAINTS))) return rc;
             zero_host_forces(b);
@@ -684,24 +721,31 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
     }
     /* resident */
     if (!b->uploaded && (rc = batch_upload(b))) return rc;
+    if (b->cb_dirty) {                       /* Set*CollisionCallback since the last upload */
+        if ((rc = batch_check_dev(b, bbx_dev_upload_callback_flags(b->dev, &b->hb)))) return rc;
+        b->cb_dirty = 0;
+    }
     if (b->n_callbacks > 0) {
-        /* callbacks need the contact list of every step on the host */
-        for (int s = 0; s < steps; s++) {
+        /* Events are appended on the device right after detection and replayed here, after the
+         * steps, in (step, emission) order.  Chunks bound the size of the event buffer. */
+        int done = 0;
+        while (done < steps) {
+            int chunk = steps - done < 8 ? steps - done : 8;
             BbxStepParams prm;
             int hf = b->forces_dirty;
             if (hf && (rc = batch_check_dev(b, bbx_dev_upload_forces(b->dev, &b->hb)))) return rc;
-            if ((rc = fill_params(b, dt, hf, &prm))) return rc;
-            if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, 1)))) return rc;
-            if ((rc = batch_download(b, BBX_DL_CONSTRAINTS))) return rc;
+            if ((rc = fill_params(b, dt, hf, 1, &prm))) return rc;
+            if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, chunk)))) return rc;
             if (hf) zero_host_forces(b);
-            for (int w = 0; w < b->n_worlds; w++) replay_callbacks(&b->worlds[w]);
+            if ((rc = replay_events(b))) return rc;
+            done += chunk;
         }
         return 0;
     }
     BbxStepParams prm;
     int hf = b->forces_dirty;
     if (hf && (rc = batch_check_dev(b, bbx_dev_upload_forces(b->dev, &b->hb)))) return rc;
-    if ((rc = fill_params(b, dt, hf, &prm))) return rc;
+    if ((rc = fill_params(b, dt, hf, 0, &prm))) return rc;
     rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, steps));
     if (hf) zero_host_forces(b);
     return rc;

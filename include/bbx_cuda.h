@@ -74,6 +74,17 @@ int  bbx_dev_download(BbxDev* dev, const BbxHostBodies* hb);
 /* per world: out + w*cap_per_world receives that world's constraints sorted
  * into the reference's emission order; counts[w] their number. */
 int  bbx_dev_download_constraints(BbxDev* dev, ContactConstraint* out, int cap_per_world, int* counts);
+/* Collision-callback events (reference ballbox.h:1999-2005, :2034-2044, :2063-2069, :2100-2103):
+ * while params->want_callbacks is set, every step appends one record per contact (per PAIR for
+ * box-box) that involves a body with a registered callback to a device buffer.
+ * bbx_dev_fetch_events copies them out sorted by (step, emission order) and empties the buffer:
+ * contacts[e] is the contact, steps[e] the step index since the last fetch, worlds[e] the world.
+ * Returns BBX_ERR_OVERFLOW if more than the buffer capacity were produced (the first `capacity`
+ * in arrival order are kept). */
+int  bbx_dev_event_capacity(BbxDev* dev);
+int  bbx_dev_fetch_events(BbxDev* dev, CollisionContact* contacts, int* steps, int* worlds, int max_events, int* count);
+/* refresh the has-callback bits after Set*CollisionCallback on a resident world */
+int  bbx_dev_upload_callback_flags(BbxDev* dev, const BbxHostBodies* hb);
 int  bbx_dev_synchronize(BbxDev* dev);
 int  bbx_dev_stats(BbxDev* dev, BallboxStats* out);
 /* per-stage device times: when on, every step records CUDA events on the step stream.

@@ -219,3 +219,54 @@ def test_callbacks_all_phases_match_reference(product, truth):
             w.step(DT)
         logs.append(log)
     assert len(logs[0]) > 50 and logs[0] == logs[1]
+
+
+def _log_callbacks(lib, w, log, every=2):
+    for i in range(0, w.n_spheres, every):
+        w.set_sphere_callback(i, lambda s, t, o, c: log.append(("s", s, t, o, c.contents.bodyA_index, c.contents.bodyB_index,
+                                                                c.contents.penetration, c.contents.contact_point.y)))
+    for i in range(0, w.n_boxes, every):
+        w.set_box_callback(i, lambda s, t, o, c: log.append(("b", s, t, o, c.contents.bodyA_index, c.contents.bodyB_index,
+                                                             c.contents.penetration, c.contents.contact_point.y)))
+
+
+def test_resident_callbacks_use_device_event_buffer(product, truth):
+    """PhysicsStepN on a resident world: events are collected on the device and replayed
+    afterwards in (step, emission) order -- the concatenated log equals the reference's."""
+    ref_log, gpu_log = [], []
+    c = truth.build_scene(bb.SCENE_SDF, 150, 44)
+    _log_callbacks(truth, c, ref_log)
+    for _ in range(45):
+        c.step(DT)
+    g = product.build_scene(bb.SCENE_SDF, 150, 44)
+    g.set_sync_mode(bb.SYNC_RESIDENT)
+    g.upload()
+    _log_callbacks(product, g, gpu_log)            # registered AFTER the upload: flags are refreshed lazily
+    g.step_n(DT, 20); g.step_n(DT, 25)             # chunks of 8 inside
+    assert len(ref_log) > 100
+    assert gpu_log == ref_log
+    g.download()
+    assert not parity.compare_worlds(g, c, constraints=False)
+
+
+def test_batch_callbacks(product, truth):
+    d = product.dll
+    s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
+    batch = d.CreatePhysicsWorldBatch(3, s, b, c)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(3)]
+    logs = [[] for _ in range(3)]
+    ref_logs = [[] for _ in range(3)]
+    singles = []
+    for i, v in enumerate(views):
+        d.BbxSceneBuild(v.ptr, bb.SCENE_RLWORLD, 0, 300 + i)
+        _log_callbacks(product, v, logs[i], every=5)
+        w = truth.build_scene(bb.SCENE_RLWORLD, 0, 300 + i)
+        _log_callbacks(truth, w, ref_logs[i], every=5)
+        singles.append(w)
+    assert d.PhysicsStepBatch(batch, DT, 30) == 0, d.BatchGetLastError(batch)
+    for w in singles:
+        for _ in range(30):
+            w.step(DT)
+    for i in range(3):
+        assert len(ref_logs[i]) > 10 and logs[i] == ref_logs[i], f"world {i}"
+    d.DestroyPhysicsWorldBatch(batch)
