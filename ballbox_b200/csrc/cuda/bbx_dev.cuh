@@ -140,6 +140,10 @@ struct BbxDev {
     CollisionContact *ev_contact;
     int step_in_batch;           // step index since the last event fetch
 
+    // snapshot for per-world resets (allocated by bbx_dev_snapshot)
+    float4 *snap_pos, *snap_vel, *snap_boxq; float *snap_timer; unsigned char *snap_flags; int *reset_ids;
+    int forces_on_device;        // accumulators were written through the device views
+
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy
     unsigned long long *sort_keys;   // export: 64-bit reference-order keys

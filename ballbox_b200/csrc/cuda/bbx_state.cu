@@ -142,7 +142,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
-        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
+        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
@@ -410,5 +410,107 @@ extern "C" int bbx_dev_stats(BbxDev* d, BallboxStats* out)
     out->levels = c->n_levels; out->overflow = c->overflow | (gp.overflow ? 4 : 0); out->grid_cells = gp.n_cells;
     out->reserved[0] = c->n_cand_sb; out->reserved[1] = c->n_cand_bb; out->reserved[2] = c->n_ss_tests;
     out->reserved[3] = c->n_big; out->reserved[4] = c->n_events;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// zero-copy views, device-side wrench application, per-world reset
+// ---------------------------------------------------------------------------
+extern "C" int bbx_dev_views(BbxDev* d, BbxDeviceViews* out)
+{
+    if (!d || !out) return BBX_ERR_BAD_ARGUMENT;
+    out->n_worlds = d->n_worlds; out->cap_spheres = d->cap_s; out->cap_boxes = d->cap_b;
+    out->pos = d->pos; out->vel = d->vel; out->box_rot = d->boxq; out->flags = d->flags;
+    out->sphere_force = d->r_s_force; out->sphere_torque = d->r_s_torque;
+    out->box_force = d->r_b_force; out->box_torque = d->r_b_torque;
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_add_wrench(BbxDev dv, const float* sf, const float* st, const float* bf, const float* bt)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= dv.N) return;
+    unsigned char f = dv.flags[g];
+    if (!(f & BF_VALID)) return;
+    bool box = g >= dv.NS;
+    int i = box ? g - dv.NS : g;
+    const float* fi = box ? bf : sf; const float* ti = box ? bt : st;
+    float* fa = box ? dv.r_b_force : dv.r_s_force; float* ta = box ? dv.r_b_torque : dv.r_s_torque;
+    bool nz = false;
+    if (fi) { float x = fi[3 * i], y = fi[3 * i + 1], z = fi[3 * i + 2];
+              if (x != 0.0f || y != 0.0f || z != 0.0f) { nz = true; fa[3 * i] += x; fa[3 * i + 1] += y; fa[3 * i + 2] += z; } }
+    if (ti) { float x = ti[3 * i], y = ti[3 * i + 1], z = ti[3 * i + 2];
+              if (x != 0.0f || y != 0.0f || z != 0.0f) { nz = true; ta[3 * i] += x; ta[3 * i + 1] += y; ta[3 * i + 2] += z; } }
+    if (nz && (f & BF_SLEEP)) { dv.flags[g] = f & (unsigned char)~BF_SLEEP; dv.timer[g] = 0.0f; }
+}
+
+extern "C" int bbx_dev_add_wrench(BbxDev* d, const float* sf, const float* st, const float* bf, const float* bt)
+{
+    if (!d) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_LAUNCH(d, k_add_wrench, bbx_blocks(d->N, 256), 256, 0, *d, sf, st, bf, bt);
+    BBX_CUDA(d, cudaGetLastError());
+    d->forces_on_device = 1;
+    return 0;
+}
+
+extern "C" int bbx_dev_snapshot(BbxDev* d)
+{
+    if (!d) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    size_t N = d->N, NB = d->NB;
+    if (!d->snap_pos) {
+        BBX_CUDA(d, cudaMalloc((void**)&d->snap_pos, sizeof(float4) * (N ? N : 1)));
+        BBX_CUDA(d, cudaMalloc((void**)&d->snap_vel, sizeof(float4) * 2 * (N ? N : 1)));
+        BBX_CUDA(d, cudaMalloc((void**)&d->snap_boxq, sizeof(float4) * 2 * (NB ? NB : 1)));
+        BBX_CUDA(d, cudaMalloc((void**)&d->snap_timer, sizeof(float) * (N ? N : 1)));
+        BBX_CUDA(d, cudaMalloc((void**)&d->snap_flags, N ? N : 1));
+        BBX_CUDA(d, cudaMalloc((void**)&d->reset_ids, sizeof(int) * (size_t)d->n_worlds));
+    }
+    cudaStream_t s = d->stream;
+    BBX_CUDA(d, cudaMemcpyAsync(d->snap_pos, d->pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, s));
+    BBX_CUDA(d, cudaMemcpyAsync(d->snap_vel, d->vel, sizeof(float4) * 2 * N, cudaMemcpyDeviceToDevice, s));
+    BBX_CUDA(d, cudaMemcpyAsync(d->snap_boxq, d->boxq, sizeof(float4) * 2 * NB, cudaMemcpyDeviceToDevice, s));
+    BBX_CUDA(d, cudaMemcpyAsync(d->snap_timer, d->timer, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+    BBX_CUDA(d, cudaMemcpyAsync(d->snap_flags, d->flags, N, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// one block per (world in the list); threads stride over that world's sphere and box slots
+__global__ void __launch_bounds__(256) k_restore_worlds(BbxDev dv, int n)
+{
+    int w = dv.reset_ids[blockIdx.x];
+    if (blockIdx.x >= n || w < 0 || w >= dv.n_worlds) return;
+    for (int i = threadIdx.x; i < dv.cap_s + dv.cap_b; i += blockDim.x) {
+        bool box = i >= dv.cap_s;
+        int g = box ? dv.NS + w * dv.cap_b + (i - dv.cap_s) : w * dv.cap_s + i;
+        dv.pos[g] = dv.snap_pos[g];
+        dv.vel[2 * g] = dv.snap_vel[2 * g]; dv.vel[2 * g + 1] = dv.snap_vel[2 * g + 1];
+        dv.timer[g] = dv.snap_timer[g];
+        dv.flags[g] = dv.snap_flags[g];
+        if (box) {
+            int b = g - dv.NS;
+            dv.boxq[2 * b] = dv.snap_boxq[2 * b]; dv.boxq[2 * b + 1] = dv.snap_boxq[2 * b + 1];
+            for (int k = 0; k < 3; k++) { dv.r_b_force[3 * b + k] = 0.0f; dv.r_b_torque[3 * b + k] = 0.0f; }
+        } else {
+            for (int k = 0; k < 3; k++) { dv.r_s_force[3 * g + k] = 0.0f; dv.r_s_torque[3 * g + k] = 0.0f; }
+        }
+    }
+}
+
+extern "C" int bbx_dev_restore_worlds(BbxDev* d, const int* world_ids, int n)
+{
+    if (!d || (n > 0 && !world_ids)) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (!d->snap_pos) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "restore without a snapshot", __FILE__, __LINE__);
+    if (n <= 0) return 0;
+    if (n > d->n_worlds) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "restore: more ids than worlds", __FILE__, __LINE__);
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaMemcpyAsync(d->reset_ids, world_ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, d->stream));
+    BBX_LAUNCH(d, k_restore_worlds, n, 256, 0, *d, n);
+    BBX_CUDA(d, cudaGetLastError());
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));      // world_ids is caller memory
     return 0;
 }

@@ -53,6 +53,7 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
     BBX_CUDA(d, cudaSetDevice(d->device));
     d->last_params = *p; d->have_params = 1;
     BbxStepParams q = *p;
+    if (d->forces_on_device) { q.has_forces = 1; d->forces_on_device = 0; }
     for (int s = 0; s < steps; s++) {
         int rc;
         bbx_timing_mark(d, 0);

@@ -854,5 +854,39 @@ void BatchSetStageTiming(PhysicsWorldBatch* b, int on) { if (batch_ok(b)) Ballbo
 int  BatchGetStageTiming(PhysicsWorldBatch* b, float* out6, int* steps) { return batch_ok(b) ? BallboxGetStageTiming(&b->worlds[0].pub, out6, steps) : BBX_ERR_BAD_ARGUMENT; }
 const char* BatchGetLastError(PhysicsWorldBatch* b) { return (batch_ok(b) && b->has_err) ? b->err : NULL; }
 
+int BatchGetDeviceViews(PhysicsWorldBatch* b, BallboxDeviceViews* out)
+{
+    if (!batch_ok(b) || !out) return BBX_ERR_BAD_ARGUMENT;
+    int rc = batch_ensure_dev(b);
+    if (rc) return rc;
+    BbxDeviceViews v;
+    rc = batch_check_dev(b, bbx_dev_views(b->dev, &v));
+    if (rc) return rc;
+    out->n_worlds = v.n_worlds; out->cap_spheres = v.cap_spheres; out->cap_boxes = v.cap_boxes;
+    out->pos = v.pos; out->vel = v.vel; out->box_rot = v.box_rot; out->flags = v.flags;
+    out->sphere_force = v.sphere_force; out->sphere_torque = v.sphere_torque;
+    out->box_force = v.box_force; out->box_torque = v.box_torque;
+    return 0;
+}
+int BatchAddWrenchDevice(PhysicsWorldBatch* b, const float* sf, const float* st, const float* bf, const float* bt)
+{
+    if (!batch_ok(b)) return BBX_ERR_BAD_ARGUMENT;
+    int rc;
+    if (!b->uploaded && (rc = batch_upload(b))) return rc;
+    return batch_check_dev(b, bbx_dev_add_wrench(b->dev, sf, st, bf, bt));
+}
+int BatchSnapshot(PhysicsWorldBatch* b)
+{
+    if (!batch_ok(b)) return BBX_ERR_BAD_ARGUMENT;
+    int rc;
+    if (!b->uploaded && (rc = batch_upload(b))) return rc;
+    return batch_check_dev(b, bbx_dev_snapshot(b->dev));
+}
+int BatchResetWorlds(PhysicsWorldBatch* b, const int* ids, int n)
+{
+    if (!batch_ok(b) || !b->dev) return BBX_ERR_BAD_ARGUMENT;
+    return batch_check_dev(b, bbx_dev_restore_worlds(b->dev, ids, n));
+}
+
 const char* BallboxBackendName(void) { return "ballbox-b200/cuda-sm_100a"; }
 int BallboxDeviceCount(void) { return bbx_device_count(); }

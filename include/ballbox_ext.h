@@ -96,6 +96,21 @@ void BatchSetStageTiming(PhysicsWorldBatch* batch, int on);
 int  BatchGetStageTiming(PhysicsWorldBatch* batch, float* out6, int* steps);
 const char* BatchGetLastError(PhysicsWorldBatch* batch);
 
+/* ---- zero-copy batch interface (RL style).  BatchGetDeviceViews exposes the device arrays
+ * (layout documented at BbxDeviceViews in bbx_cuda.h) so that observations can be read and
+ * forces written without touching the host; BatchAddWrenchDevice adds per-body force/torque
+ * arrays that already live on the device; BatchSnapshot / BatchResetWorlds implement episode
+ * resets on the device. ------------------------------------------------------------------- */
+typedef struct {
+    int   n_worlds, cap_spheres, cap_boxes;
+    void *pos, *vel, *box_rot, *flags, *sphere_force, *sphere_torque, *box_force, *box_torque;
+} BallboxDeviceViews;
+int BatchGetDeviceViews(PhysicsWorldBatch* batch, BallboxDeviceViews* out);
+int BatchAddWrenchDevice(PhysicsWorldBatch* batch, const float* d_sphere_force, const float* d_sphere_torque,
+                         const float* d_box_force, const float* d_box_torque);
+int BatchSnapshot(PhysicsWorldBatch* batch);
+int BatchResetWorlds(PhysicsWorldBatch* batch, const int* world_ids, int n);
+
 /* ---- library identity ------------------------------------------------------ */
 const char* BallboxBackendName(void);   /* "ballbox-b200/cuda-sm_100a" */
 int         BallboxDeviceCount(void);   /* 0 when no CUDA device is visible */

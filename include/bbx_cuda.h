@@ -99,6 +99,29 @@ int  bbx_dev_debug_levels(BbxDev* dev, int* counts, unsigned long long* ns, int 
 const char* bbx_dev_error(BbxDev* dev);          /* NULL when healthy */
 void bbx_dev_clear_error(BbxDev* dev);
 
+/* ---- zero-copy access for batched / RL use ------------------
+ * Raw device pointers of the working state.  N = n_worlds*(cap_s+cap_b) body slots, spheres
+ * first: sphere (w,i) = w*cap_s + i, box (w,i) = n_worlds*cap_s + w*cap_b + i. */
+typedef struct {
+    int   n_worlds, cap_spheres, cap_boxes;
+    void* pos;          /* float4[N]   xyz, bounding radius                                  */
+    void* vel;          /* float4[2N]  [2g] = (v, 1/m), [2g+1] = (w, sphere 1/I)             */
+    void* box_rot;      /* float4[2NB] [2b] = rotation, [2b+1] = 1/diag(I)                   */
+    void* flags;        /* uint8[N]    1 static, 2 sleeping, 4 valid, 8 callback, 16 big     */
+    void* sphere_force; /* float[3NS]  force accumulators, consumed and cleared by a step    */
+    void* sphere_torque;
+    void* box_force;    /* float[3NB] */
+    void* box_torque;
+} BbxDeviceViews;
+int  bbx_dev_views(BbxDev* dev, BbxDeviceViews* out);
+/* accumulators += the given DEVICE arrays (any may be NULL); bodies that receive a non-zero
+ * force or torque are woken like AddSphereForce does (ballbox.h:420-423) */
+int  bbx_dev_add_wrench(BbxDev* dev, const float* d_sphere_force, const float* d_sphere_torque,
+                        const float* d_box_force, const float* d_box_torque);
+/* keep a device copy of the current state / restore the listed worlds from it */
+int  bbx_dev_snapshot(BbxDev* dev);
+int  bbx_dev_restore_worlds(BbxDev* dev, const int* world_ids, int n);
+
 /* pinned host memory for the public arrays (falls back to calloc without a device) */
 void* bbx_host_alloc(size_t bytes, int* pinned);
 void  bbx_host_free(void* p, int pinned);

@@ -270,3 +270,43 @@ def test_batch_callbacks(product, truth):
     for i in range(3):
         assert len(ref_logs[i]) > 10 and logs[i] == ref_logs[i], f"world {i}"
     d.DestroyPhysicsWorldBatch(batch)
+
+
+def test_zero_copy_batch_interface(product, truth):
+    """Device views alias the library's state; forces written on the device act exactly like
+    AddSphereForce/AddBoxTorque on the host; per-world resets restore the uploaded state."""
+    import torch
+    from ballbox_b200.rl import BatchEnv
+    W = 6
+    env = BatchEnv(product, W, seed_base=500)
+    refs = [truth.build_scene(bb.SCENE_RLWORLD, 0, 500 + i) for i in range(W)]
+    sf = torch.zeros(W, env.cap_spheres, 3, device="cuda"); bt = torch.zeros(W, env.cap_boxes, 3, device="cuda")
+    for s in range(30):
+        sf.zero_(); bt.zero_()
+        sf[:, 5, 0] = 3.0 + s * 0.1; sf[:, 7, 1] = 12.0
+        bt[:, 9, 2] = 0.5
+        env.add_wrench(sphere_force=sf, box_torque=bt)
+        env.step(DT, 1)
+        for w in refs:
+            truth.dll.AddSphereForce(w.ptr, 5, bb.Vec3(3.0 + s * 0.1, 0, 0)); truth.dll.AddSphereForce(w.ptr, 7, bb.Vec3(0, 12.0, 0))
+            truth.dll.AddBoxTorque(w.ptr, 9, bb.Vec3(0, 0, 0.5))
+            w.step(DT)
+    # observations straight from HBM
+    obs = env.sphere_pos[:, :, :3].cpu().numpy()
+    for i, w in enumerate(refs):
+        n = w.n_spheres
+        assert np.array_equal(obs[i, :n].view(np.uint32), w.sphere_arrays()["pos"].view(np.uint32)), f"world {i}"
+    env.download()
+    for i, w in enumerate(refs):
+        assert not parity.compare_worlds(env.worlds[i], w, constraints=False), f"world {i}"
+    # episode reset of worlds 1 and 4 on the device
+    env.reset([1, 4])
+    env.step(DT, 10)
+    env.download()
+    fresh = {i: truth.build_scene(bb.SCENE_RLWORLD, 0, 500 + i) for i in (1, 4)}
+    for i in range(W):
+        w = fresh.get(i, refs[i])
+        for _ in range(10):
+            w.step(DT)
+        assert not parity.compare_worlds(env.worlds[i], w, constraints=False), f"after reset, world {i}"
+    env.close()
