@@ -116,7 +116,30 @@ __device__ __forceinline__ unsigned int body_order_key(const BbxDev& dv, int4 id
     return ((unsigned int)id.w << 29) | (partner << 5) | (unsigned int)cls;
 }
 
-__global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv)
+// COLOURED schedule (BBX_SOLVER_COLOURED): the per-body order is a hash of the node identity
+// instead of the emission order.  Orienting every conflict (two nodes sharing a dynamic body)
+// from the smaller to the larger hash gives a DAG whose Kahn levels are independent sets, i.e.
+// a graph colouring with far fewer classes than the emission-order levels; the sweep visits the
+// classes in order, so no atomics are needed inside a class.  This REORDERS the Gauss-Seidel
+// sweep: results are deterministic but no longer equal to the reference's.
+__device__ __forceinline__ unsigned int node_hash29(int4 id)
+{
+    unsigned int h = (unsigned int)id.x * 0x9E3779B1u ^ ((unsigned int)(id.y + 3) * 0x85EBCA77u) ^ ((unsigned int)id.w * 0xC2B2AE3Du);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h >> 3;
+}
+__device__ __forceinline__ unsigned int coloured_key(int4 id, int cls) { return (node_hash29(id) << 3) | (unsigned int)cls; }
+
+// total order used to break hash ties deterministically: (phase, A gid, B gid)
+__device__ __forceinline__ bool node_before(const BbxDev& dv, int c1, int c2)
+{
+    int4 a = dv.c_ids[c1], b = dv.c_ids[c2];
+    if (a.w != b.w) return a.w < b.w;
+    if (a.x != b.x) return a.x < b.x;
+    return a.y < b.y;
+}
+
+__global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int coloured)
 {
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -125,11 +148,13 @@ __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv)
         int4 l = dv.node[2 * (size_t)c];
         if (l.x >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.x], 1);
-            dv.adj[slot] = ((unsigned long long)body_order_key(dv, id, true, l.w) << 32) | (unsigned int)c;
+            unsigned int key = coloured ? coloured_key(id, l.w) : body_order_key(dv, id, true, l.w);
+            dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;
         }
         if (l.y >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.y], 1);
-            dv.adj[slot] = ((unsigned long long)body_order_key(dv, id, false, l.w) << 32) | (unsigned int)c;
+            unsigned int key = coloured ? coloured_key(id, l.w) : body_order_key(dv, id, false, l.w);
+            dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;
         }
     }
 }
@@ -148,7 +173,12 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv)
             for (int i = 1; i < d; i++) {
                 unsigned long long v = lst[i];
                 int j = i - 1;
-                while (j >= 0 && lst[j] > v) { lst[j + 1] = lst[j]; j--; }
+                // equal 32-bit keys can only happen in the coloured schedule (hash collision): fall back to
+                // the deterministic total order so that the result never depends on the contact numbering
+                while (j >= 0 && ((lst[j] >> 32) > (v >> 32) ||
+                                  ((lst[j] >> 32) == (v >> 32) && node_before(dv, (int)(unsigned int)v, (int)(unsigned int)lst[j])))) {
+                    lst[j + 1] = lst[j]; j--;
+                }
                 lst[j + 1] = v;
             }
             int prev = (int)(unsigned int)lst[0];
@@ -360,6 +390,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     __shared__ LevelMap lm;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
+    // work index of this thread: consecutive 32-node chunks go round-robin over the BLOCKS, so a level
+    // with few nodes is spread over all SMs instead of filling the first few blocks
+    const int wtid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
     int* lc = dv.level_count;                       // lc[level * BBX_NCLS + class]
     const size_t PL = (size_t)dv.cap_contacts;
 
@@ -372,7 +405,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
         if (tid < BBX_NCLS) lc[(lvl + 2) * BBX_NCLS + tid] = 0;
         int* lc_next = lc + (lvl + 1) * BBX_NCLS;
         const int total = lm.pref[BBX_NCLS];
-        for (int t = tid; t < total; t += stride) {
+        for (int t = wtid; t < total; t += stride) {
             int k = 0;
             #pragma unroll
             for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
@@ -446,7 +479,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
             }
             __syncthreads();
             const int total = lm.pref[BBX_NCLS];
-            for (int t = tid; t < total; t += stride) {
+            for (int t = wtid; t < total; t += stride) {
                 int k = 0;
                 #pragma unroll
                 for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
@@ -485,7 +518,7 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
     if (p->settings.solver_iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);
     if (rc) return rc;
-    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d);
+    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0);
     BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d);
     BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 2 * BBX_NCLS * sizeof(int), d->stream));
     BBX_LAUNCH(d, k_frontier0, G, 256, 0, *d);
