@@ -339,3 +339,82 @@ def test_coloured_schedule_is_deterministic_and_only_changes_the_solve(product, 
     sc = c.snapshot()
     err = np.abs(sa["s_pos"].astype(np.float64) - sc["s_pos"]).max()
     assert 0 < err < 1.0
+
+
+def test_dense_cluster_exercises_overflow_paths(product, truth):
+    """120 spheres and 40 boxes dropped into one small region: > 40 neighbours per body (pair-buffer
+    overflow path), > 32 solver nodes per body (long per-body lists)."""
+    def build(lib):
+        w = lib.create_world(160, 64, 60000)
+        w.set_gravity((0, -9.8, 0))
+        w.w.settings.solver_iterations = 6
+        g = w.add_box((0, -1, 0), (6, 1, 6)); lib.dll.SetBoxStatic(w.ptr, g, True)
+        s = 12345
+        def u():
+            nonlocal s
+            s = (s * 1664525 + 1013904223) & 0xffffffff
+            return (s >> 8) / 16777216.0
+        for i in range(120):
+            w.add_sphere((u() * 1.2 - 0.6, 0.6 + u() * 1.2, u() * 1.2 - 0.6), 0.45 + 0.1 * u())
+        for i in range(40):
+            w.add_box((u() * 1.2 - 0.6, 0.6 + u() * 1.2, u() * 1.2 - 0.6), (0.3 + 0.2 * u(), 0.3, 0.35),
+                      w.quat_axis_angle((u() + 0.1, u(), u()), 3.0 * u()))
+        return w
+    g, c = build(product), build(truth)
+    for s in range(25):
+        g.step(DT); c.step(DT)
+        mm = parity.compare_worlds(g, c)
+        assert not mm, f"step {s}: {mm[:3]}"
+        if s == 0:
+            k = g.constraints()
+            per_body = np.bincount(k["a_index"][k["a_type"] == 0], minlength=120)
+            assert per_body.max() > 40 and len(k) > 5000
+
+
+def test_boxes_sunk_into_sdf_produce_long_runs(product, truth):
+    """boxes entirely below the SDF surface: all 20 probes fire (the duplicated face-centre probes of
+    ballbox.h:2454-2458 included), one solver node of 20 constraints per box."""
+    def build(lib):
+        w = lib.create_world(8, 16, 2048)
+        w.set_gravity((0, -9.8, 0))
+        for i in range(10):
+            w.add_box((i * 1.7 - 8, -1.5 - 0.1 * i, 0.3 * i), (0.4, 0.3 + 0.02 * i, 0.5), w.quat_axis_angle((1, 0.3 * i, 0.2), 0.4 * i))
+        w.add_sphere((0, -3, 0), 0.5); w.add_sphere((2, 0.2, 1), 0.5)
+        w.use_sdf(bb.SDF_PLANE_Y)
+        return w
+    g, c = build(product), build(truth)
+    for s in range(20):
+        g.step(DT); c.step(DT)
+        mm = parity.compare_worlds(g, c)
+        assert not mm, f"step {s}: {mm[:3]}"
+        if s == 0:
+            k = g.constraints()
+            assert ((k["a_type"] == 1) & (k["b_type"] == 2)).sum() == 200      # 10 boxes x 20 probes
+
+
+def test_ragged_batch(product, truth):
+    """worlds of a batch with different (including zero) body counts"""
+    d = product.dll
+    batch = d.CreatePhysicsWorldBatch(5, 40, 24, 2048)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(5)]
+    singles = [truth.create_world(40, 24, 2048) for _ in range(5)]
+    sizes = [0, 7, 40, 1, 23]
+    for wi, n in enumerate(sizes):
+        for lib, w in ((product, views[wi]), (truth, singles[wi])):
+            w.set_gravity((0, -9.8, 0))
+            w.w.settings.solver_iterations = 8
+            if n:
+                g = w.add_box((0, -1, 0), (5, 1, 5)); lib.dll.SetBoxStatic(w.ptr, g, True)
+            for i in range(n):
+                w.add_sphere(((i % 5) * 0.8 - 1.6, 0.4 + (i // 5) * 0.9, (i % 3) * 0.7), 0.45)
+                if i < 23:
+                    w.add_box(((i % 4) * 0.9 - 1.5, 5.0 + i * 0.3, (i % 2) * 0.8), (0.3, 0.25, 0.35), w.quat_axis_angle((1, i, 2), 0.2 * i))
+    # gravity/settings come from world 0 of the batch
+    assert d.PhysicsStepBatch(batch, DT, 50) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    for wi in range(5):
+        for _ in range(50):
+            singles[wi].step(DT)
+        mm = parity.compare_worlds(views[wi], singles[wi])
+        assert not mm, f"world {wi} ({sizes[wi]} bodies): {mm[:3]}"
+    d.DestroyPhysicsWorldBatch(batch)
