@@ -192,6 +192,14 @@ class BallboxLib:
         d.BbxStateHash.argtypes = [WP]
         d.BbxStateHash.restype = C.c_ulonglong
         d.BallboxBackendName.restype = C.c_char_p
+        self.stage_names = ("ApplyForces", "IntegrateVelocities", "CollectCollisions", "GenerateContactConstraints",
+                            "PreSolveConstraints", "SolveVelocityConstraints", "SolveConstraints", "IntegratePositions",
+                            "UpdateSleepStates", "CleanupPhysics")
+        self.has_stages = all(hasattr(d, n) for n in self.stage_names)
+        if self.has_stages:
+            for n in self.stage_names:
+                getattr(d, n).argtypes = [WP]
+                getattr(d, n).restype = None
         if product:
             d.BallboxSetSyncMode.argtypes = [WP, C.c_int]
             d.BallboxSetSyncMode.restype = None
@@ -327,6 +335,11 @@ class World:
             (d.RefPhysicsStepPruned if hasattr(d, "RefPhysicsStepPruned") else d.OraclePhysicsStepPruned)(self.ptr, dt)
         else:
             d.PhysicsStep(self.ptr, dt)
+        self.check()
+
+    def stage(self, name):
+        """Call one of the reference's public stage functions (ballbox.h:217-229)."""
+        getattr(self.lib.dll, name)(self.ptr)
         self.check()
 
     def step_n(self, dt, n):

@@ -143,6 +143,7 @@ struct BbxDev {
     // snapshot for per-world resets (allocated by bbx_dev_snapshot)
     float4 *snap_pos, *snap_vel, *snap_boxq; float *snap_timer; unsigned char *snap_flags; int *reset_ids;
     int forces_on_device;        // accumulators were written through the device views
+    int imported_list;           // the device contact list was imported from the host in array order
 
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy
@@ -182,6 +183,11 @@ int bbx_stage_integrate_velocities(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_broadphase(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_narrowphase(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_solve(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int iterations, int imported);
+int bbx_stage_apply_forces_only(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_integrate_velocities_only(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_positions_only(BbxDev* d, const BbxStepParams* p);
+int bbx_stage_sleep_only(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_integrate_positions(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_collect_events(BbxDev* d, const BbxStepParams* p);
 int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out);

@@ -14,7 +14,9 @@
 // to hold zeros, so F = 0 + g*m and T = 0 without touching them (24+24 bytes per
 // body saved each way).
 // ---------------------------------------------------------------------------
-template <bool HAS_FORCES>
+// GRAVITY / INTEGRATE select the two public stages separately (ApplyForces, IntegrateVelocities);
+// PhysicsStep runs both fused.
+template <bool HAS_FORCES, bool GRAVITY, bool INTEGRATE>
 __global__ void __launch_bounds__(256) k_integrate_velocities(BbxDev dv, float3 g, float dt, float lin_damp, float ang_damp)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,8 +35,8 @@ __global__ void __launch_bounds__(256) k_integrate_velocities(BbxDev dv, float3 
     if (!(f & BF_STATIC)) {
         float m = dv.mass[i];
         // ApplyForces: forces += gravity * mass, sleeping bodies included (:1825-1827)
-        F = v3add(F, v3scale(g, m));
-        if (!(f & BF_SLEEP)) {
+        if (GRAVITY) F = v3add(F, v3scale(g, m));
+        if (INTEGRATE && !(f & BF_SLEEP)) {
             float4 v4 = dv.vel[2 * i], w4 = dv.vel[2 * i + 1];
             float3 v = xyz(v4), w = xyz(w4);
             float3 acc = v3scale(F, 1.0f / m);                       // :1852
@@ -58,11 +60,15 @@ __global__ void __launch_bounds__(256) k_integrate_velocities(BbxDev dv, float3 
             dv.vel[2 * i + 1] = make_float4(w.x, w.y, w.z, w4.w);
         }
     }
-    if (HAS_FORCES) {                                                // :1917-1924
+    if (HAS_FORCES && INTEGRATE) {                                   // :1917-1924
         float* fp = is_box ? dv.r_b_force + 3 * b : dv.r_s_force + 3 * i;
         float* tp = is_box ? dv.r_b_torque + 3 * b : dv.r_s_torque + 3 * i;
         fp[0] = 0.0f; fp[1] = 0.0f; fp[2] = 0.0f;
         tp[0] = 0.0f; tp[1] = 0.0f; tp[2] = 0.0f;
+    }
+    if (HAS_FORCES && !INTEGRATE) {                                  // ApplyForces alone: publish F
+        float* fp = is_box ? dv.r_b_force + 3 * b : dv.r_s_force + 3 * i;
+        fp[0] = F.x; fp[1] = F.y; fp[2] = F.z;
     }
 }
 
@@ -71,9 +77,26 @@ int bbx_stage_integrate_velocities(BbxDev* d, const BbxStepParams* p)
     float3 g = make_float3(p->gravity[0], p->gravity[1], p->gravity[2]);
     int nb = bbx_blocks(d->N, 256);
     if (p->has_forces)
-        BBX_LAUNCH(d, k_integrate_velocities<true>, nb, 256, 0, *d, g, p->dt, p->settings.linear_damping, p->settings.angular_damping);
+        BBX_LAUNCH(d, (k_integrate_velocities<true, true, true>), nb, 256, 0, *d, g, p->dt, p->settings.linear_damping, p->settings.angular_damping);
     else
-        BBX_LAUNCH(d, k_integrate_velocities<false>, nb, 256, 0, *d, g, p->dt, p->settings.linear_damping, p->settings.angular_damping);
+        BBX_LAUNCH(d, (k_integrate_velocities<false, true, true>), nb, 256, 0, *d, g, p->dt, p->settings.linear_damping, p->settings.angular_damping);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+
+// the public stages ApplyForces (:1820) and IntegrateVelocities (:1841) on their own
+int bbx_stage_apply_forces_only(BbxDev* d, const BbxStepParams* p)
+{
+    float3 g = make_float3(p->gravity[0], p->gravity[1], p->gravity[2]);
+    BBX_LAUNCH(d, (k_integrate_velocities<true, true, false>), bbx_blocks(d->N, 256), 256, 0, *d, g, p->dt, 1.0f, 1.0f);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+int bbx_stage_integrate_velocities_only(BbxDev* d, const BbxStepParams* p)
+{
+    float3 g = make_float3(0.0f, 0.0f, 0.0f);
+    BBX_LAUNCH(d, (k_integrate_velocities<true, false, true>), bbx_blocks(d->N, 256), 256, 0, *d, g, p->dt,
+               p->settings.linear_damping, p->settings.angular_damping);
     BBX_CUDA(d, cudaGetLastError());
     return 0;
 }
@@ -81,6 +104,7 @@ int bbx_stage_integrate_velocities(BbxDev* d, const BbxStepParams* p)
 // ---------------------------------------------------------------------------
 // K12.  IntegratePositions then UpdateSleepStates, fused per body.
 // ---------------------------------------------------------------------------
+template <bool POSITIONS, bool SLEEP>
 __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, float dt, float lin_thr, float ang_thr, float t_req)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,7 +113,7 @@ __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, fl
     if (!(f & BF_VALID) || (f & BF_STATIC)) return;
     float4 v4 = dv.vel[2 * i], w4 = dv.vel[2 * i + 1];
     float3 v = xyz(v4), w = xyz(w4);
-    if (!(f & BF_SLEEP)) {
+    if (POSITIONS && !(f & BF_SLEEP)) {
         float4 p4 = dv.pos[i];
         float3 p = v3add(xyz(p4), v3scale(v, dt));                   // :1939 / :1950
         float R = p4.w;
@@ -111,6 +135,7 @@ __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, fl
         }
         dv.pos[i] = make_float4(p.x, p.y, p.z, R);
     }
+    if (!SLEEP) return;
     // UpdateSleepStates :1714-1742 / :1745-1783
     float ls = v3len(v), as = v3len(w);
     float t = dv.timer[i];
@@ -132,7 +157,22 @@ __global__ void __launch_bounds__(256) k_integrate_positions_sleep(BbxDev dv, fl
 
 int bbx_stage_integrate_positions(BbxDev* d, const BbxStepParams* p)
 {
-    BBX_LAUNCH(d, k_integrate_positions_sleep, bbx_blocks(d->N, 256), 256, 0, *d, p->dt,
+    BBX_LAUNCH(d, (k_integrate_positions_sleep<true, true>), bbx_blocks(d->N, 256), 256, 0, *d, p->dt,
+               p->settings.sleep_linear_threshold, p->settings.sleep_angular_threshold, p->settings.sleep_time_required);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+
+// the public stages IntegratePositions (:1928) and UpdateSleepStates (:1696) on their own
+int bbx_stage_positions_only(BbxDev* d, const BbxStepParams* p)
+{
+    BBX_LAUNCH(d, (k_integrate_positions_sleep<true, false>), bbx_blocks(d->N, 256), 256, 0, *d, p->dt, 0.0f, 0.0f, 0.0f);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
+}
+int bbx_stage_sleep_only(BbxDev* d, const BbxStepParams* p)
+{
+    BBX_LAUNCH(d, (k_integrate_positions_sleep<false, true>), bbx_blocks(d->N, 256), 256, 0, *d, p->dt,
                p->settings.sleep_linear_threshold, p->settings.sleep_angular_threshold, p->settings.sleep_time_required);
     BBX_CUDA(d, cudaGetLastError());
     return 0;

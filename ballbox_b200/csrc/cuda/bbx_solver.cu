@@ -50,7 +50,11 @@ __device__ __forceinline__ float inv_mass_sum(float imA, float imB, float3 rA, f
     return imA + imB + v3dot(ra, v3mul(ra, iA)) + v3dot(rb, v3mul(rb, iB));             // :1323-1325
 }
 
-__global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, float allowed, float dt)
+// mode 0: PhysicsStep (everything computed, impulses zeroed)            -- :1176-1211 + :1295-1356
+// mode 1: PreSolveConstraints on an imported list (impulses kept)         -- :1295-1356
+// mode 2: SolveVelocityConstraints on an imported list: only n, rA, rB are derived; effective
+//         masses, bias and accumulated impulses are the ones found in the host records
+__global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, float allowed, float dt, int mode)
 {
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -87,10 +91,13 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         float mT1 = (s2 > 0.0f) ? 1.0f / s2 : 0.0f;
         float bias = (baumgarte / dt) * bb_fmaxf(0.0f, pt4.w - allowed);               // :1352-1354
         float4* L = dv.L + 4 * (size_t)c;
+        float4 keep = L[3];
+        if (mode == 2) { bias = L[0].w; mN = L[1].w; mT0 = L[2].w; mT1 = keep.w; }
         L[0] = make_float4(nrm.x, nrm.y, nrm.z, bias);
         L[1] = make_float4(rA.x, rA.y, rA.z, mN);
         L[2] = make_float4(rB.x, rB.y, rB.z, mT0);
-        L[3] = make_float4(0.0f, 0.0f, 0.0f, mT1);                                      // impulses start at 0 (:1203-1206)
+        if (mode == 0) L[3] = make_float4(0.0f, 0.0f, 0.0f, mT1);                       // impulses start at 0 (:1203-1206)
+        else           L[3] = make_float4(keep.x, keep.y, keep.z, mT1);
         dv.slot_of[c] = -1;
         if (RUN_K(id.z) == 0) {                                                         // node head
             int m = RUN_LEN(id.z);
@@ -139,7 +146,8 @@ __device__ __forceinline__ bool node_before(const BbxDev& dv, int c1, int c2)
     return a.y < b.y;
 }
 
-__global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int coloured)
+// order: 0 emission order from (phase, partner); 1 coloured (hash); 2 imported list (array index)
+__global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int order)
 {
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -148,12 +156,12 @@ __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int coloured)
         int4 l = dv.node[2 * (size_t)c];
         if (l.x >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.x], 1);
-            unsigned int key = coloured ? coloured_key(id, l.w) : body_order_key(dv, id, true, l.w);
+            unsigned int key = order == 1 ? coloured_key(id, l.w) : (order == 2 ? (((unsigned int)c << 3) | (unsigned int)l.w) : body_order_key(dv, id, true, l.w));
             dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;
         }
         if (l.y >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.y], 1);
-            unsigned int key = coloured ? coloured_key(id, l.w) : body_order_key(dv, id, false, l.w);
+            unsigned int key = order == 1 ? coloured_key(id, l.w) : (order == 2 ? (((unsigned int)c << 3) | (unsigned int)l.w) : body_order_key(dv, id, false, l.w));
             dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;
         }
     }
@@ -510,15 +518,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
 }
 
 // touched-body statistics and sanity for the host
-int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
+int bbx_stage_solve(BbxDev* d, const BbxStepParams* p) { return bbx_stage_solve_ex(d, p, 0, p->settings.solver_iterations, 0); }
+
+// presolve_mode: see k_presolve; iterations: Gauss-Seidel sweeps; imported: the contact list came from
+// the host in array order (public stage functions), so the per-body order is the array index
+int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int iterations, int imported)
 {
     const int G = BBX_NUM_SMS * 8;
     BBX_CUDA(d, cudaMemsetAsync(d->deg, 0, sizeof(int) * ((size_t)d->N + 1), d->stream));
-    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt);
-    if (p->settings.solver_iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
+    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode);
+    if (iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);
     if (rc) return rc;
-    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0);
+    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0));
     BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d);
     BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 2 * BBX_NCLS * sizeof(int), d->stream));
     BBX_LAUNCH(d, k_frontier0, G, 256, 0, *d);
@@ -536,7 +548,7 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p)
     bbx_timing_mark(d, 4);
     SolveParams sp;
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;
-    sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = p->settings.solver_iterations;
+    sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = iterations;
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
     BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));

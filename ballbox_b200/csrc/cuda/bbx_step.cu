@@ -53,6 +53,7 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
     BBX_CUDA(d, cudaSetDevice(d->device));
     d->last_params = *p; d->have_params = 1;
     BbxStepParams q = *p;
+    d->imported_list = 0;
     if (d->forces_on_device) { q.has_forces = 1; d->forces_on_device = 0; }
     for (int s = 0; s < steps; s++) {
         int rc;
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         if (fabsf(n3.x) >= 0.57735f) t1 = f3(n3.y, -n3.x, 0.0f); else t1 = f3(0.0f, n3.z, -n3.y);
         t1 = v3norm(t1);
         t2 = v3cross(n3, t1);
-        float jn = 0.0f, jt0 = 0.0f, jt1 = 0.0f;
+        // not scheduled (or no sweep ran): the accumulated impulses are whatever the record held (0 in PhysicsStep)
+        float jn = l3.x, jt0 = l3.y, jt1 = l3.z;
         int slot = solved ? dv.slot_of[c] : -1;
         if (slot >= 0) { float4 m3 = dv.M[3 * (size_t)dv.cap_contacts + slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
         else if (solved && friction > 0.0f) {
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(256) k_gather_records(const float* src, float*
     }
 }
 
+static int ensure_export_buffers(BbxDev* d);
 int bbx_radix_sort(BbxDev* d, unsigned long long* keys_a, unsigned int* vals_a, unsigned long long* keys_b,
                    unsigned int* vals_b, int n, int bits, int* hist, int* hist_scan,
                    unsigned long long** keys_sorted, unsigned int** vals_sorted);
@@ -274,17 +277,7 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
     kb.wb = bits_for(d->n_worlds); kb.ib = bits_for(d->cap_s > d->cap_b ? d->cap_s : d->cap_b); kb.jb = kb.ib;
     int total_bits = kb.wb + 3 + kb.ib + kb.jb + 5;
     if (total_bits > 64) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "export key does not fit 64 bits", __FILE__, __LINE__);
-    size_t C = (size_t)d->cap_contacts;
-    if (!d->export_buf) {
-        size_t tiles = C / 2048 + 2;
-        BBX_CUDA(d, cudaMalloc((void**)&d->export_buf, sizeof(ContactConstraint) * C));
-        BBX_CUDA(d, cudaMalloc((void**)&d->export_sorted, sizeof(ContactConstraint) * C));
-        BBX_CUDA(d, cudaMalloc((void**)&d->sort_keys_b, sizeof(unsigned long long) * C));
-        BBX_CUDA(d, cudaMalloc((void**)&d->sort_vals_a, sizeof(unsigned int) * C));
-        BBX_CUDA(d, cudaMalloc((void**)&d->sort_vals_b, sizeof(unsigned int) * C));
-        BBX_CUDA(d, cudaMalloc((void**)&d->sort_hist, sizeof(int) * 256 * tiles));
-        BBX_CUDA(d, cudaMalloc((void**)&d->sort_hist_scan, sizeof(int) * 256 * tiles));
-    }
+    { int rc0 = ensure_export_buffers(d); if (rc0) return rc0; }
     const BbxStepParams* p = &d->last_params;
     BBX_LAUNCH(d, k_export_constraints, BBX_NUM_SMS * 8, 256, 0, *d, d->export_buf, d->sort_keys,
                p->settings.restitution, p->settings.friction, p->settings.solver_iterations > 0 ? 1 : 0, kb);
@@ -328,6 +321,221 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
     if (truncated)
         return bbx_fail(d, BBX_ERR_OVERFLOW, "a world produced more contacts than max_collisions", __FILE__, __LINE__);
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// public stage functions (reference ballbox.h:217-229): import / export of host lists
+// ---------------------------------------------------------------------------
+__global__ void k_import_reset(BbxDev dv, int n)
+{
+    StepCounters* c = dv.ctr;
+    c->n_contacts = n; c->n_cand_sb = 0; c->n_cand_bb = 0; c->n_hit_bb = 0; c->n_solver = 0; c->n_touched = 0;
+    c->n_levels = 0; c->n_frontier0 = 0; c->n_mslots = 0; c->n_nodes = 0;
+}
+
+struct ImportRec { int ta, ia, tb, ib; };
+__device__ __forceinline__ ImportRec import_ids(const CollisionContact* cs, const ContactConstraint* ks, int i)
+{
+    ImportRec r;
+    if (cs) { r.ta = cs[i].bodyA_type; r.ia = cs[i].bodyA_index; r.tb = cs[i].bodyB_type; r.ib = cs[i].bodyB_index; }
+    else    { r.ta = ks[i].bodyA_type; r.ia = ks[i].bodyA_index; r.tb = ks[i].bodyB_type; r.ib = ks[i].bodyB_index; }
+    return r;
+}
+__device__ __forceinline__ bool same_pair(ImportRec a, ImportRec b) { return a.ta == b.ta && a.ia == b.ia && a.tb == b.tb && a.ib == b.ib; }
+
+// Host list (array order) -> device contact arrays.  Consecutive records of the same body pair form
+// one solver node (they are adjacent in both bodies' orders by construction); runs are cut at 255.
+__global__ void __launch_bounds__(256) k_import_list(BbxDev dv, const CollisionContact* cs, const ContactConstraint* ks, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        ImportRec me = import_ids(cs, ks, i);
+        int back = 0;
+        while (back < 4096 && i - back - 1 >= 0 && same_pair(me, import_ids(cs, ks, i - back - 1))) back++;
+        int fwd = 0;
+        while (fwd < 4096 && i + fwd + 1 < n && same_pair(me, import_ids(cs, ks, i + fwd + 1))) fwd++;
+        int k = back % 255;
+        int chunk_start = back - k;
+        int len = min(255, back + 1 + fwd - chunk_start);
+        int a = (me.ta == 0) ? me.ia : ((me.ta == 1) ? dv.NS + me.ia : -2);
+        int b = (me.tb == 0) ? me.ib : ((me.tb == 1) ? dv.NS + me.ib : -2);
+        int phase = (me.ta == 0 && me.tb == 0) ? PH_SS : (me.ta == 1 && me.tb == 1) ? PH_BB : (me.ta == 0 && me.tb == 1) ? PH_SB
+                  : (me.ta == 0 && me.tb == 2) ? PH_SSDF : (me.ta == 1 && me.tb == 2) ? PH_BSDF : 5;
+        Vec3 pt = cs ? cs[i].contact_point : ks[i].contact_point;
+        Vec3 nr = cs ? cs[i].contact_normal : ks[i].contact_normal;
+        float pen = cs ? cs[i].penetration : ks[i].penetration;
+        dv.c_ids[i] = make_int4(a, b, RUN_ENC(k, len), phase);
+        dv.c_pt[i] = make_float4(pt.x, pt.y, pt.z, pen);
+        dv.c_nrm[i] = make_float4(nr.x, nr.y, nr.z, 0.0f);
+        float4* L = dv.L + 4 * (size_t)i;
+        if (ks) {
+            L[0] = make_float4(0, 0, 0, ks[i].position_bias);
+            L[1] = make_float4(0, 0, 0, ks[i].normal_mass);
+            L[2] = make_float4(0, 0, 0, ks[i].tangent_mass[0]);
+            L[3] = make_float4(ks[i].normal_impulse, ks[i].tangent_impulse[0], ks[i].tangent_impulse[1], ks[i].tangent_mass[1]);
+        } else {
+            L[3] = make_float4(0, 0, 0, 0);
+        }
+    }
+}
+
+static int ensure_export_buffers(BbxDev* d)
+{
+    size_t C = (size_t)d->cap_contacts;
+    if (!d->export_buf) {
+        size_t tiles = C / 2048 + 2;
+        BBX_CUDA(d, cudaMalloc((void**)&d->export_buf, sizeof(ContactConstraint) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->export_sorted, sizeof(ContactConstraint) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_keys_b, sizeof(unsigned long long) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_vals_a, sizeof(unsigned int) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_vals_b, sizeof(unsigned int) * C));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_hist, sizeof(int) * 256 * tiles));
+        BBX_CUDA(d, cudaMalloc((void**)&d->sort_hist_scan, sizeof(int) * 256 * tiles));
+    }
+    return 0;
+}
+
+extern "C" int bbx_dev_import_list(BbxDev* d, const CollisionContact* contacts, const ContactConstraint* constraints, int n)
+{
+    if (!d || n < 0 || ((contacts != NULL) == (constraints != NULL) && n > 0)) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (d->n_worlds != 1) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "stage functions work on single worlds", __FILE__, __LINE__);
+    if (n > d->cap_contacts) return bbx_fail(d, BBX_ERR_OVERFLOW, "imported list longer than max_collisions", __FILE__, __LINE__);
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    int rc = ensure_export_buffers(d);
+    if (rc) return rc;
+    const CollisionContact* dcs = NULL; const ContactConstraint* dks = NULL;
+    if (n > 0) {
+        if (contacts) { BBX_CUDA(d, cudaMemcpyAsync(d->export_sorted, contacts, sizeof(CollisionContact) * (size_t)n, cudaMemcpyHostToDevice, d->stream));
+                        dcs = (const CollisionContact*)d->export_sorted; }
+        else          { BBX_CUDA(d, cudaMemcpyAsync(d->export_sorted, constraints, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyHostToDevice, d->stream));
+                        dks = d->export_sorted; }
+    }
+    BBX_LAUNCH(d, k_import_reset, 1, 1, 0, *d, n);
+    if (n > 0) BBX_LAUNCH(d, k_import_list, bbx_blocks(n, 256), 256, 0, *d, dcs, dks, n);
+    BBX_CUDA(d, cudaGetLastError());
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));          // the host list may be pageable user memory
+    d->imported_list = 1;
+    return 0;
+}
+
+extern "C" int bbx_dev_export_list(BbxDev* d, ContactConstraint* out, int n, float restitution, float friction, int solved)
+{
+    if (!d || (n > 0 && !out)) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (n <= 0) return 0;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    int rc = ensure_export_buffers(d);
+    if (rc) return rc;
+    KeyBits kb = key_bits_of(d);
+    BBX_LAUNCH(d, k_export_constraints, BBX_NUM_SMS * 8, 256, 0, *d, d->export_buf, d->sort_keys, restitution, friction, solved, kb);
+    BBX_CUDA(d, cudaGetLastError());
+    BBX_CUDA(d, cudaMemcpyAsync(out, d->export_buf, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_export_contacts(BbxDev dv, CollisionContact* out, unsigned long long* keys, KeyBits kb)
+{
+    int n = min(dv.ctr->n_contacts, dv.cap_contacts);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        int4 id = dv.c_ids[c];
+        int wa, ta, la, tb, lb;
+        keys[c] = emission_key(dv, id, kb, wa, ta, la, tb, lb);
+        float4 pt = dv.c_pt[c], nr = dv.c_nrm[c];
+        CollisionContact k;
+        k.bodyA_type = ta; k.bodyA_index = la; k.bodyB_type = tb; k.bodyB_index = lb;
+        k.contact_point.x = pt.x; k.contact_point.y = pt.y; k.contact_point.z = pt.z;
+        k.contact_normal.x = nr.x; k.contact_normal.y = nr.y; k.contact_normal.z = nr.z;
+        k.penetration = pt.w;
+        out[c] = k;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_words(const float* src, float* dst, const unsigned int* order, int n, int words)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)n * words;
+    for (; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int t = (int)(idx / words), f = (int)(idx - (long long)t * words);
+        dst[idx] = src[(size_t)order[t] * words + f];
+    }
+}
+
+// after COLLECT: the contact list in the reference's emission order; like the reference it is cut at `cap`
+extern "C" int bbx_dev_download_contacts(BbxDev* d, CollisionContact* out, int cap, int* count)
+{
+    if (!d || !count) return BBX_ERR_BAD_ARGUMENT;
+    *count = 0;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    int rc = ensure_export_buffers(d);
+    if (rc) return rc;
+    BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    if (d->ctr_host->overflow & 3)
+        return bbx_fail(d, BBX_ERR_OVERFLOW, "contact or candidate buffer overflow: raise max_collisions", __FILE__, __LINE__);
+    int n = d->ctr_host->n_contacts;
+    if (n <= 0) return 0;
+    KeyBits kb = key_bits_of(d);
+    BBX_LAUNCH(d, k_export_contacts, BBX_NUM_SMS * 8, 256, 0, *d, (CollisionContact*)d->export_buf, d->sort_keys, kb);
+    unsigned long long* ks; unsigned int* order;
+    rc = bbx_radix_sort(d, d->sort_keys, d->sort_vals_a, d->sort_keys_b, d->sort_vals_b, n, kb.wb + 3 + kb.ib + kb.jb + 5,
+                        d->sort_hist, d->sort_hist_scan, &ks, &order);
+    if (rc) return rc;
+    BBX_LAUNCH(d, k_gather_words, BBX_NUM_SMS * 8, 256, 0, (const float*)d->export_buf, (float*)d->export_sorted, order, n, 11);
+    BBX_CUDA(d, cudaGetLastError());
+    int take = n < cap ? n : cap;                      // :1988, :2020, :2052: the reference stops adding at capacity
+    if (take > 0 && out)
+        BBX_CUDA(d, cudaMemcpyAsync(out, d->export_sorted, sizeof(CollisionContact) * (size_t)take, cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    *count = take;
+    return 0;
+}
+
+extern "C" int bbx_dev_download_forces(BbxDev* d, const BbxHostBodies* hb)
+{
+    if (!d || !hb) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    size_t NS = d->NS, NB = d->NB;
+    if (NS) { BBX_CUDA(d, cudaMemcpyAsync(hb->s_force, d->r_s_force, 12 * NS, cudaMemcpyDeviceToHost, d->stream));
+              BBX_CUDA(d, cudaMemcpyAsync(hb->s_torque, d->r_s_torque, 12 * NS, cudaMemcpyDeviceToHost, d->stream)); }
+    if (NB) { BBX_CUDA(d, cudaMemcpyAsync(hb->b_force, d->r_b_force, 12 * NB, cudaMemcpyDeviceToHost, d->stream));
+              BBX_CUDA(d, cudaMemcpyAsync(hb->b_torque, d->r_b_torque, 12 * NB, cudaMemcpyDeviceToHost, d->stream)); }
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+extern "C" int bbx_dev_run_stage(BbxDev* d, const BbxStepParams* p, int stage)
+{
+    if (!d || !p) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (d->n_worlds != 1) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "stage functions work on single worlds", __FILE__, __LINE__);
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    d->last_params = *p; d->have_params = 1;
+    int rc = 0;
+    switch (stage) {
+    case BBX_STAGE_APPLY_FORCES: rc = bbx_stage_apply_forces_only(d, p); break;
+    case BBX_STAGE_INTEGRATE_V:  rc = bbx_stage_integrate_velocities_only(d, p); break;
+    case BBX_STAGE_COLLECT:
+        d->imported_list = 0;
+        if ((rc = bbx_stage_broadphase(d, p))) break;
+        rc = bbx_stage_narrowphase(d, p);
+        break;
+    case BBX_STAGE_PRESOLVE:
+        if (!d->imported_list) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "PRESOLVE needs an imported list", __FILE__, __LINE__);
+        rc = bbx_stage_solve_ex(d, p, 1, 0, 1); break;
+    case BBX_STAGE_SOLVE_SWEEP:
+        if (!d->imported_list) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "SOLVE_SWEEP needs an imported list", __FILE__, __LINE__);
+        rc = bbx_stage_solve_ex(d, p, 2, 1, 1); break;
+    case BBX_STAGE_SOLVE_ALL:
+        if (!d->imported_list) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "SOLVE_ALL needs an imported list", __FILE__, __LINE__);
+        rc = bbx_stage_solve_ex(d, p, 0, p->settings.solver_iterations, 1); break;
+    case BBX_STAGE_INTEGRATE_P:  rc = bbx_stage_positions_only(d, p); break;
+    case BBX_STAGE_SLEEP:        rc = bbx_stage_sleep_only(d, p); break;
+    default: return BBX_ERR_BAD_ARGUMENT;
+    }
+    return rc;
 }
 
 // debug: per-level node counts (per class) and end-of-level timestamps of iteration 1

@@ -752,6 +752,144 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
 }
 
 /* ------------------------------------------------------------------------- */
+/* public stage functions, reference ballbox.h:217-229                       */
+/* ------------------------------------------------------------------------- */
+static struct PhysicsWorldBatch* stage_begin(PhysicsWorld* world, BbxStepParams* prm)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return NULL;
+    struct PhysicsWorldBatch* b = p->batch;
+    if (b->has_err) return NULL;
+    if (b->n_worlds != 1) { batch_fail(b, "stage functions work on single worlds, not on members of a batch"); return NULL; }
+    if (batch_upload(b)) return NULL;                       /* host arrays are the truth between stages */
+    if (fill_params(b, world->dt, 1, 0, prm)) return NULL;
+    return b;
+}
+
+void ApplyForces(PhysicsWorld* world)                                /* :1820 */
+{
+    BbxStepParams prm; struct PhysicsWorldBatch* b = stage_begin(world, &prm);
+    if (!b) return;
+    if (batch_check_dev(b, bbx_dev_run_stage(b->dev, &prm, BBX_STAGE_APPLY_FORCES))) return;
+    batch_check_dev(b, bbx_dev_download_forces(b->dev, &b->hb));
+}
+
+void IntegrateVelocities(PhysicsWorld* world)                        /* :1841 */
+{
+    BbxStepParams prm; struct PhysicsWorldBatch* b = stage_begin(world, &prm);
+    if (!b) return;
+    if (batch_check_dev(b, bbx_dev_run_stage(b->dev, &prm, BBX_STAGE_INTEGRATE_V))) return;
+    if (batch_download(b, BBX_DL_BODIES)) return;
+    zero_host_forces(b);                                             /* :1917-1924 */
+}
+
+/* callbacks from a contact list in emission order (same rules as replay_callbacks) */
+static void replay_contact_callbacks(BbxWorldPriv* p)
+{
+    CollisionCollection* cc = &p->collisions;
+    SphereSystem* S = &p->spheres; BoxSystem* B = &p->boxes;
+    int prev_a = -1, prev_b = -1;
+    for (int i = 0; i < cc->count; i++) {
+        CollisionContact* k = &cc->contacts[i];
+        int a = k->bodyA_index, c = k->bodyB_index;
+        if (k->bodyA_type == 1 && k->bodyB_type == 1) {
+            if (a != prev_a || c != prev_b) {
+                if (B->collision_callbacks[a]) B->collision_callbacks[a](a, 1, c, k);
+                if (B->collision_callbacks[c]) B->collision_callbacks[c](c, 1, a, k);
+            }
+            prev_a = a; prev_b = c;
+            continue;
+        }
+        prev_a = -1; prev_b = -1;
+        if (k->bodyA_type == 0 && k->bodyB_type == 0) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 0, c, k);
+            if (S->collision_callbacks[c]) S->collision_callbacks[c](c, 0, a, k);
+        } else if (k->bodyA_type == 0 && k->bodyB_type == 1) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 1, c, k);
+            if (B->collision_callbacks[c]) B->collision_callbacks[c](c, 0, a, k);
+        } else if (k->bodyA_type == 0 && k->bodyB_type == 2) {
+            if (S->collision_callbacks[a]) S->collision_callbacks[a](a, 2, 0, k);
+        }
+    }
+}
+
+void CollectCollisions(PhysicsWorld* world)                          /* :1979 */
+{
+    if (!world || !world->collisions) return;
+    BbxStepParams prm; struct PhysicsWorldBatch* b = stage_begin(world, &prm);
+    if (!b) return;
+    world->collisions->count = 0;
+    if (batch_check_dev(b, bbx_dev_run_stage(b->dev, &prm, BBX_STAGE_COLLECT))) return;
+    int n = 0;
+    if (batch_check_dev(b, bbx_dev_download_contacts(b->dev, world->collisions->contacts, world->collisions->capacity, &n))) return;
+    world->collisions->count = n;
+    if (b->n_callbacks > 0) replay_contact_callbacks(&b->worlds[0]);
+}
+
+void GenerateContactConstraints(PhysicsWorld* world)                 /* :1176-1211: a field-by-field copy, no arithmetic */
+{
+    if (!world || !world->collisions || !world->constraints) return;
+    ConstraintCollection* K = world->constraints; CollisionCollection* C = world->collisions;
+    K->count = 0;
+    for (int i = 0; i < C->count && K->count < K->capacity; i++) {
+        CollisionContact* s = &C->contacts[i]; ContactConstraint* c = &K->constraints[K->count++];
+        c->bodyA_type = s->bodyA_type; c->bodyA_index = s->bodyA_index; c->bodyB_type = s->bodyB_type; c->bodyB_index = s->bodyB_index;
+        c->contact_point = s->contact_point; c->contact_normal = s->contact_normal; c->penetration = s->penetration;
+        c->restitution = world->settings.restitution; c->friction = world->settings.friction;
+        c->normal_impulse = 0.0f; c->tangent_impulse[0] = 0.0f; c->tangent_impulse[1] = 0.0f;
+    }
+}
+
+/* the device sweep uses one restitution / friction for the whole list (what GenerateContactConstraints writes) */
+static int uniform_materials(struct PhysicsWorldBatch* b, ConstraintCollection* K, float* rest, float* fric)
+{
+    *rest = b->worlds[0].pub.settings.restitution; *fric = b->worlds[0].pub.settings.friction;
+    if (K->count > 0) { *rest = K->constraints[0].restitution; *fric = K->constraints[0].friction; }
+    for (int i = 1; i < K->count; i++)
+        if (K->constraints[i].restitution != *rest || K->constraints[i].friction != *fric) {
+            batch_fail(b, "per-constraint restitution/friction are not supported by the device solver stages");
+            return 0;
+        }
+    return 1;
+}
+
+static void solver_stage(PhysicsWorld* world, int stage, int solved, int download_bodies)
+{
+    if (!world || !world->constraints) return;
+    BbxStepParams prm; struct PhysicsWorldBatch* b = stage_begin(world, &prm);
+    if (!b) return;
+    ConstraintCollection* K = world->constraints;
+    float rest, fric;
+    if (!uniform_materials(b, K, &rest, &fric)) return;
+    prm.settings.restitution = rest; prm.settings.friction = fric;
+    if (batch_check_dev(b, bbx_dev_import_list(b->dev, NULL, K->constraints, K->count))) return;
+    if (batch_check_dev(b, bbx_dev_run_stage(b->dev, &prm, stage))) return;
+    if (batch_check_dev(b, bbx_dev_export_list(b->dev, K->constraints, K->count, rest, fric, solved))) return;
+    if (download_bodies) batch_download(b, BBX_DL_BODIES);
+}
+
+void PreSolveConstraints(PhysicsWorld* world)      { solver_stage(world, BBX_STAGE_PRESOLVE, 0, 0); }     /* :1295 */
+void SolveVelocityConstraints(PhysicsWorld* world) { solver_stage(world, BBX_STAGE_SOLVE_SWEEP, 1, 1); }  /* :1410 */
+
+void SolveConstraints(PhysicsWorld* world)                           /* :1213-1226 */
+{
+    if (!world || !world->constraints) return;
+    GenerateContactConstraints(world);
+    solver_stage(world, BBX_STAGE_SOLVE_ALL, world->settings.solver_iterations > 0, 1);
+}
+
+static void body_stage(PhysicsWorld* world, int stage)
+{
+    BbxStepParams prm; struct PhysicsWorldBatch* b = stage_begin(world, &prm);
+    if (!b) return;
+    if (batch_check_dev(b, bbx_dev_run_stage(b->dev, &prm, stage))) return;
+    batch_download(b, BBX_DL_BODIES);
+}
+void IntegratePositions(PhysicsWorld* world) { body_stage(world, BBX_STAGE_INTEGRATE_P); }               /* :1928 */
+void UpdateSleepStates(PhysicsWorld* world)  { body_stage(world, BBX_STAGE_SLEEP); }                      /* :1696 */
+void CleanupPhysics(PhysicsWorld* world) { if (world && world->collisions) world->collisions->count = 0; } /* :2305 */
+
+/* ------------------------------------------------------------------------- */
 /* public stepping API                                                       */
 /* ------------------------------------------------------------------------- */
 void PhysicsStep(PhysicsWorld* world, float deltaTime)              /* ballbox.h:1787 */

@@ -193,6 +193,23 @@ void ResetPhysicsSettingsToDefaults(PhysicsWorld* world);
 /* ---- the hot path (ref :215, :1787) ---------------------------------------- */
 void PhysicsStep(PhysicsWorld* world, float deltaTime);
 
+/* ---- the stages of PhysicsStep, callable one by one (ref :217-229, order of use :1797-1816).
+ * Each call uploads the host arrays, runs that stage on the GPU and downloads what it changed;
+ * CollectCollisions leaves the contact list in world->collisions (emission order) and fires the
+ * callbacks; the solver stages read world->collisions / world->constraints from the HOST in array
+ * order, so lists edited between stages are honoured.  ResolveCollisions and PositionalCorrection
+ * are declared but never defined by the reference (:221, :239) and are not provided. */
+void ApplyForces(PhysicsWorld* world);
+void IntegrateVelocities(PhysicsWorld* world);
+void CollectCollisions(PhysicsWorld* world);
+void GenerateContactConstraints(PhysicsWorld* world);
+void PreSolveConstraints(PhysicsWorld* world);
+void SolveVelocityConstraints(PhysicsWorld* world);
+void SolveConstraints(PhysicsWorld* world);
+void IntegratePositions(PhysicsWorld* world);
+void UpdateSleepStates(PhysicsWorld* world);          /* defined (not declared) by the reference, :1696 */
+void CleanupPhysics(PhysicsWorld* world);
+
 /* ---- constraint collection management (ref :232-234) ----------------------- */
 ConstraintCollection* CreateConstraintCollection(int capacity);
 void DestroyConstraintCollection(ConstraintCollection* constraints);

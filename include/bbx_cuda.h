@@ -71,6 +71,31 @@ int  bbx_dev_upload(BbxDev* dev, const BbxHostBodies* hb);
 int  bbx_dev_upload_forces(BbxDev* dev, const BbxHostBodies* hb);
 int  bbx_dev_step(BbxDev* dev, const BbxStepParams* params, int steps);
 int  bbx_dev_download(BbxDev* dev, const BbxHostBodies* hb);
+
+/* ---- the reference's public stage functions (ballbox.h:217-229), single world only -----------
+ * bbx_dev_run_stage runs ONE stage on the state uploaded before it:
+ *   APPLY_FORCES   ApplyForces :1820           INTEGRATE_V  IntegrateVelocities :1841
+ *   COLLECT        CollectCollisions :1979     PRESOLVE     PreSolveConstraints :1295 (imported list)
+ *   SOLVE_SWEEP    SolveVelocityConstraints :1410, one sweep (imported list with solver fields)
+ *   SOLVE_ALL      SolveConstraints :1213 = generate + presolve + solver_iterations sweeps (imported contacts)
+ *   INTEGRATE_P    IntegratePositions :1928    SLEEP        UpdateSleepStates :1696
+ * Host contact lists are imported in ARRAY order, whatever the user did to them between stages. */
+#define BBX_STAGE_APPLY_FORCES 1
+#define BBX_STAGE_INTEGRATE_V  2
+#define BBX_STAGE_COLLECT      3
+#define BBX_STAGE_PRESOLVE     4
+#define BBX_STAGE_SOLVE_SWEEP  5
+#define BBX_STAGE_SOLVE_ALL    6
+#define BBX_STAGE_INTEGRATE_P  7
+#define BBX_STAGE_SLEEP        8
+int  bbx_dev_run_stage(BbxDev* dev, const BbxStepParams* params, int stage);
+int  bbx_dev_download_forces(BbxDev* dev, const BbxHostBodies* hb);
+/* after COLLECT: contacts in emission order (44-byte records) */
+int  bbx_dev_download_contacts(BbxDev* dev, CollisionContact* out, int cap, int* count);
+/* host list -> device (array order).  Exactly one of contacts / constraints is non-NULL. */
+int  bbx_dev_import_list(BbxDev* dev, const CollisionContact* contacts, const ContactConstraint* constraints, int n);
+/* device list -> host records in array order (after PRESOLVE / SOLVE_SWEEP / SOLVE_ALL) */
+int  bbx_dev_export_list(BbxDev* dev, ContactConstraint* out, int n, float restitution, float friction, int solved);
 /* per world: out + w*cap_per_world receives that world's constraints sorted
  * into the reference's emission order; counts[w] their number. */
 int  bbx_dev_download_constraints(BbxDev* dev, ContactConstraint* out, int cap_per_world, int* counts);
