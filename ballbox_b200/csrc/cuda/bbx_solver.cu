@@ -372,7 +372,7 @@ __device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level
 // slower (6.6 vs 5.8 ms per step at 1M bodies) although it makes the barrier cheaper.
 #define LC_CACHE 512
 #define SOLVE_THREADS 256
-#define SOLVE_BLOCKS_PER_SM 3
+#define SOLVE_BLOCKS_PER_SM 2
 
 // Grid-wide barrier: cooperative-groups grid.sync() measured 1.2 us at 444 x 256 threads on B200,
 // a hand-written arrive/poll barrier 1.7 us (tools/micro/barrier_bench.cu), so we use the former.
@@ -436,11 +436,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 BodyState A, B;
                 if (hasA) load_body(dv, nd0.x, A);
                 if (hasB) load_body(dv, nd0.y, B);
-                for (int j = 0; j < m; j++) {
-                    // contact-order records are gathered once (two 256-bit loads), then written plane-major
-                    const float4* L = dv.L + 4 * (size_t)(c + j);
-                    F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+                // contact-order records are gathered once (two 256-bit loads, the next record in flight while
+                // the current constraint is swept), then written plane-major
+                const float4* L = dv.L + 4 * (size_t)c;
+                F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+                for (int j = 0; j < m; j++, L += 4) {
                     float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
+                    if (j + 1 < m) { lo = ld256_nc(L + 4); hi = ld256_nc(L + 6); }
                     solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     float4* M = dv.M + (size_t)(mbase + j);
                     __stcg(M, c0); __stcg(M + PL, c1); __stcg(M + 2 * PL, c2); __stcg(M + 3 * PL, c3);
@@ -499,8 +501,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 if (hasA) load_body(dv, nd.z, A);
                 if (hasB) load_body(dv, nd.w, B);
                 float4* M = dv.M + (size_t)nd.x;
+                // software pipeline: the record of constraint j+1 is in flight while constraint j is swept
+                float4 n0 = __ldcg(M), n1 = __ldcg(M + PL), n2 = __ldcg(M + 2 * PL), n3 = __ldcg(M + 3 * PL);
                 for (int j = 0; j < nd.y; j++, M++) {
-                    float4 c0 = __ldcg(M), c1 = __ldcg(M + PL), c2 = __ldcg(M + 2 * PL), c3 = __ldcg(M + 3 * PL);
+                    float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+                    if (j + 1 < nd.y) { n0 = __ldcg(M + 1); n1 = __ldcg(M + 1 + PL); n2 = __ldcg(M + 1 + 2 * PL); n3 = __ldcg(M + 1 + 3 * PL); }
                     solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     __stcg(M + 3 * PL, c3);
                 }
@@ -515,6 +520,181 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Batched small worlds: one WARP per world.
+//
+// Independent worlds never share a body, so a world can be swept by one warp with its body
+// velocities in shared memory and __syncwarp() between levels: no grid barrier and no L2 round
+// trip for body state.  A level of a 256-body world holds ~30 nodes, i.e. one warp's worth; eight
+// worlds share a block and 24 worlds are resident per SM, so a 4096-world batch runs in about one
+// wave with enough warps per scheduler to hide the instruction latency of the sweep (one block per
+// world was measured slower than the grid-wide kernel: a single active warp per block).
+// The schedule is the same order-preserving level schedule (Kahn on the same successor links), so
+// results stay bit-identical to the single-world path and to the reference.  Impulses accumulate
+// in place in the contact-order records L; a world's visiting order is written to its slice of the
+// queue array and replayed by iterations 1..I-1.
+// ---------------------------------------------------------------------------
+#define WW_WARPS     8            // worlds per block
+#define WW_BODY_MAX  512          // cap_s + cap_b of a world
+#define WW_LMAX      512          // dependency levels of a world
+
+__global__ void __launch_bounds__(256) k_frontier0_worlds(BbxDev dv, int* wq, int* wq_count)
+{
+    __shared__ int s_solver, s_nodes;
+    if (threadIdx.x == 0) { s_solver = 0; s_nodes = 0; }
+    __syncthreads();
+    int n = min(dv.ctr->n_contacts, dv.cap_contacts);
+    int my_solver = 0, my_nodes = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        int4 id = dv.c_ids[c];
+        if (RUN_K(id.z) != 0) continue;
+        int4 l = dv.node[2 * (size_t)c];
+        if (l.x < 0 && l.y < 0) continue;
+        my_solver += l.z; my_nodes++;
+        if (dv.indeg[c] == 0) {
+            int w = id.x < dv.NS ? id.x / dv.cap_s : (id.x - dv.NS) / dv.cap_b;
+            int slot = atomicAdd(&wq_count[w], 1);
+            if (slot < dv.cap_contacts_world) wq[(size_t)w * dv.cap_contacts_world + slot] = c;
+        }
+    }
+    if (my_nodes) { atomicAdd(&s_solver, my_solver); atomicAdd(&s_nodes, my_nodes); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_nodes) { atomicAdd(&dv.ctr->n_solver, s_solver); atomicAdd(&dv.ctr->n_nodes, s_nodes); }
+}
+
+__device__ __forceinline__ int ww_local(const BbxDev& dv, int w, int g)
+{
+    return g < dv.NS ? g - w * dv.cap_s : dv.cap_s + (g - dv.NS - w * dv.cap_b);
+}
+
+__device__ __forceinline__ void ww_load_body(const BbxDev& dv, const float4* vel, int w, int g, BodyState& s)
+{
+    int li = ww_local(dv, w, g);
+    float4 l = vel[2 * li], a = vel[2 * li + 1];
+    s.v = xyz(l); s.w = xyz(a); s.im = l.w; s.ii = a.w;
+    s.box = g >= dv.NS;
+    if (s.box) {
+        int b = g - dv.NS;
+        F8 qi = ld256_nc(&dv.boxq[2 * b]);
+        s.q = qi.a; s.iI = xyz(qi.b);
+        float3 u = f3(s.q.x, s.q.y, s.q.z);
+        s.k1 = s.q.w * s.q.w - v3dot(u, u); s.k2 = 2.0f * s.q.w;
+    }
+}
+
+__device__ __forceinline__ void ww_store_body(const BbxDev& dv, float4* vel, int w, int g, const BodyState& s)
+{
+    int li = ww_local(dv, w, g);
+    vel[2 * li] = make_float4(s.v.x, s.v.y, s.v.z, s.im);
+    vel[2 * li + 1] = make_float4(s.w.x, s.w.y, s.w.z, s.ii);
+}
+
+// sweep one node (all its constraints, in order) with bodies in shared memory, impulses in L
+__device__ __forceinline__ void ww_sweep_node(const BbxDev& dv, float4* vel, int w, int c, int4 nd, const SolveParams& sp, bool wake)
+{
+    bool hasA = nd.x >= 0, hasB = nd.y >= 0;
+    BodyState A, B;
+    if (hasA) ww_load_body(dv, vel, w, nd.x, A);
+    if (hasB) ww_load_body(dv, vel, w, nd.y, B);
+    float4* L = dv.L + 4 * (size_t)c;
+    F8 lo = ld256_cg(L), hi = ld256_cg(L + 2);
+    for (int j = 0; j < nd.z; j++, L += 4) {
+        float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
+        if (j + 1 < nd.z) { lo = ld256_cg(L + 4); hi = ld256_cg(L + 6); }       // next record in flight
+        solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+        __stcg(L + 3, c3);
+    }
+    if (hasA) { ww_store_body(dv, vel, w, nd.x, A); if (wake) wake_body(dv, nd.x); }
+    if (hasB) { ww_store_body(dv, vel, w, nd.y, B); if (wake) wake_body(dv, nd.y); }
+}
+
+// dynamic shared memory: per warp [ vel: 2*nb float4 | level_start: WW_LMAX+1 ints | next_count, bad ]
+__global__ void __launch_bounds__(WW_WARPS * 32, 2) k_solve_worlds(BbxDev dv, SolveParams sp, int* wq, const int* wq_count, int warp_bytes)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * WW_WARPS + wib;
+    if (w >= dv.n_worlds) return;
+    const int nb = dv.cap_s + dv.cap_b;
+    unsigned char* base = smem_raw + (size_t)wib * warp_bytes;
+    float4* vel = reinterpret_cast<float4*>(base);
+    int* level_start = reinterpret_cast<int*>(base + (size_t)nb * 32);
+    int* next_count = level_start + WW_LMAX + 1;
+    int n0 = min(wq_count[w], dv.cap_contacts_world);
+    if (n0 == 0) return;                                              // no dynamic contact in this world
+    int* queue = wq + (size_t)w * dv.cap_contacts_world;              // this world's visiting order
+    const int qcap = dv.cap_contacts_world;
+    // ---- stage the world's velocities ----
+    for (int i = lane; i < nb; i += 32) {
+        int g = i < dv.cap_s ? w * dv.cap_s + i : dv.NS + w * dv.cap_b + (i - dv.cap_s);
+        F8 v = ld256_cg(&dv.vel[2 * g]);
+        vel[2 * i] = v.a; vel[2 * i + 1] = v.b;
+    }
+    if (lane == 0) { next_count[0] = 0; level_start[0] = 0; }
+    __syncwarp();
+    // ---- iteration 0: Kahn levels ----
+    int head = 0, tail = n0, lvl = 0;
+    bool bad = false;
+    while (head < tail) {
+        for (int p0 = head; p0 < tail; p0 += 32) {
+            int p = p0 + lane;
+            if (p < tail) {
+                int c = __ldcg(&queue[p]);
+                F8 rec = ld256_nc((const float4*)&dv.node[2 * (size_t)c]);
+                int4 nd = make_int4(__float_as_int(rec.a.x), __float_as_int(rec.a.y), __float_as_int(rec.a.z), 0);
+                int sa = __float_as_int(rec.b.x), sb = __float_as_int(rec.b.y);
+                ww_sweep_node(dv, vel, w, c, nd, sp, true);
+                if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) == 1) {
+                    int q = tail + atomicAdd(next_count, 1);
+                    if (q < qcap) __stcg(&queue[q], sa & 0x0fffffff);
+                }
+                if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) == 1) {
+                    int q = tail + atomicAdd(next_count, 1);
+                    if (q < qcap) __stcg(&queue[q], sb & 0x0fffffff);
+                }
+            }
+        }
+        __syncwarp();
+        int pushed = next_count[0];
+        __syncwarp();
+        head = tail; tail += pushed; lvl++;
+        if (tail > qcap || lvl > WW_LMAX) { bad = true; break; }
+        if (lane == 0) { next_count[0] = 0; level_start[lvl] = head; }
+        __syncwarp();
+    }
+    if (bad) { if (lane == 0) atomicOr(&dv.ctr->overflow, 32); return; }
+    const int n_levels = lvl;
+    if (lane == 0) atomicMax(&dv.ctr->n_levels, n_levels);
+    // ---- iterations 1..I-1: replay the visiting order ----
+    for (int it = 1; it < sp.iterations; it++) {
+        for (int l = 0; l < n_levels; l++) {
+            int s0 = level_start[l], s1 = (l + 1 < n_levels) ? level_start[l + 1] : tail;
+            for (int p0 = s0; p0 < s1; p0 += 32) {
+                int p = p0 + lane;
+                if (p < s1) {
+                    int c = __ldcg(&queue[p]);
+                    int4 nd = dv.node[2 * (size_t)c];
+                    ww_sweep_node(dv, vel, w, c, nd, sp, false);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // ---- write the velocities back ----
+    for (int i = lane; i < nb; i += 32) {
+        int g = i < dv.cap_s ? w * dv.cap_s + i : dv.NS + w * dv.cap_b + (i - dv.cap_s);
+        st256_cg(&dv.vel[2 * g], vel[2 * i], vel[2 * i + 1]);
+    }
+}
+
+static int world_warp_bytes(const BbxDev* d) { return (d->cap_s + d->cap_b) * 32 + (WW_LMAX + 1 + 3) * 4; }
+
+static bool use_world_warps(const BbxDev* d, int imported)
+{
+    return !imported && d->n_worlds >= 16 && d->cap_s + d->cap_b <= WW_BODY_MAX && d->cap_s > 0 && d->cap_b > 0 &&
+           WW_WARPS * world_warp_bytes(d) <= 220 * 1024;
 }
 
 // touched-body statistics and sanity for the host
@@ -532,6 +712,25 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     if (rc) return rc;
     BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0));
     BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d);
+    if (use_world_warps(d, imported)) {
+        // batched small worlds: per-world frontier, then one warp per world (no grid barrier)
+        int* wq = d->queue_k[0];                       // capacity cap_contacts = n_worlds * cap_contacts_world
+        int* wq_count = d->adj_cursor;                 // free again after k_adj_link; N + 1 >= n_worlds ints
+        BBX_CUDA(d, cudaMemsetAsync(wq_count, 0, sizeof(int) * (size_t)d->n_worlds, d->stream));
+        BBX_LAUNCH(d, k_frontier0_worlds, G, 256, 0, *d, wq, wq_count);
+        bbx_timing_mark(d, 4);
+        SolveParams spw;
+        spw.restitution = p->settings.restitution; spw.friction = p->settings.friction;
+        spw.vel_threshold = p->settings.velocity_threshold; spw.iterations = iterations;
+        int wbytes = world_warp_bytes(d), smem = WW_WARPS * wbytes;
+        if (!d->wb_attr_set) {
+            BBX_CUDA(d, cudaFuncSetAttribute(k_solve_worlds, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            d->wb_attr_set = 1;
+        }
+        BBX_LAUNCH(d, k_solve_worlds, (d->n_worlds + WW_WARPS - 1) / WW_WARPS, WW_WARPS * 32, smem, *d, spw, wq, wq_count, wbytes);
+        BBX_CUDA(d, cudaGetLastError());
+        return 0;
+    }
     BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 2 * BBX_NCLS * sizeof(int), d->stream));
     BBX_LAUNCH(d, k_frontier0, G, 256, 0, *d);
 

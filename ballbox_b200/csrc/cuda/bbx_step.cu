@@ -113,8 +113,10 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         if (slot >= 0) { float4 m3 = dv.M[3 * (size_t)dv.cap_contacts + slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
         else if (solved && friction > 0.0f) {
             // a constraint between two non-dynamic bodies is never scheduled, but the reference still
-            // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477)
-            jt0 = -0.0f; jt1 = -0.0f;
+            // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477).
+            // (In the block-per-world path scheduled constraints keep their impulses in L: slot < 0 too.)
+            int4 hd = dv.node[2 * (size_t)(c - RUN_K(id.z))];
+            if (hd.x < 0 && hd.y < 0) { jt0 = -0.0f; jt1 = -0.0f; }
         }
         ContactConstraint r;
         r.bodyA_type = ta; r.bodyA_index = la; r.bodyB_type = tb; r.bodyB_index = lb;

@@ -418,3 +418,29 @@ def test_ragged_batch(product, truth):
         mm = parity.compare_worlds(views[wi], singles[wi])
         assert not mm, f"world {wi} ({sizes[wi]} bodies): {mm[:3]}"
     d.DestroyPhysicsWorldBatch(batch)
+
+
+def test_world_block_solver_path(product, truth):
+    """>= 16 small worlds take the block-per-world solve kernel (body state in shared memory,
+    __syncthreads between levels); every world must still equal the same world stepped alone."""
+    d = product.dll
+    n_worlds = 72
+    s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
+    batch = d.CreatePhysicsWorldBatch(n_worlds, s, b, c)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(n_worlds)]
+    for i, v in enumerate(views):
+        d.BbxSceneBuild(v.ptr, bb.SCENE_RLWORLD, 0, 4000 + i)
+    log = []
+    views[5].set_sphere_callback(3, lambda s_, t, o, k: log.append((s_, t, o)))
+    assert d.PhysicsStepBatch(batch, DT, 40) == 0, d.BatchGetLastError(batch)
+    assert d.PhysicsStepBatch(batch, DT, 35) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    st = bb.BallboxStats(); d.BatchGetStats(batch, bb.C.byref(st))
+    assert st.overflow == 0 and st.levels > 3
+    for i in (0, 5, 17, 40, 71):
+        w = truth.build_scene(bb.SCENE_RLWORLD, 0, 4000 + i)
+        for _ in range(75):
+            w.step(DT)
+        mm = parity.compare_worlds(views[i], w)
+        assert not mm, f"world {i}: {mm[:3]}"
+    d.DestroyPhysicsWorldBatch(batch)

@@ -1,0 +1,33 @@
+"""Stage timing of the batched-worlds path (config 5). Usage: python tools/profile_batch.py [worlds] [settle] [steps]"""
+import ctypes as C, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ballbox_b200 as bbx
+from ballbox_b200 import binding as bb
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+settle = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+lib = bbx.load(); d = lib.dll
+s, b, c = lib.scene_capacity(bb.SCENE_RLWORLD, 0)
+batch = d.CreatePhysicsWorldBatch(W, s, b, c)
+for i in range(W):
+    d.BbxSceneBuild(d.BatchWorld(batch, i), bb.SCENE_RLWORLD, 0, 7000 + i)
+d.BatchUpload(batch)
+done = 0
+while done < settle:
+    k = min(50, settle - done); d.PhysicsStepBatch(batch, 1 / 60, k); d.BatchSynchronize(batch); done += k
+d.BatchSetStageTiming(batch, 1)
+out = (C.c_float * 6)(); n = C.c_int()
+d.BatchGetStageTiming(batch, out, C.byref(n))
+try:
+    import torch; torch.cuda.profiler.start()
+except Exception:
+    torch = None
+d.PhysicsStepBatch(batch, 1 / 60, steps); d.BatchSynchronize(batch)
+if torch: torch.cuda.profiler.stop()
+d.BatchGetStageTiming(batch, out, C.byref(n))
+st = bb.BallboxStats(); d.BatchGetStats(batch, C.byref(st))
+e = d.BatchGetLastError(batch)
+print("error:", e)
+names = bb.World.STAGES
+print({k: round(out[i] / max(n.value, 1), 4) for i, k in enumerate(names)}, "total", round(sum(out) / max(n.value, 1), 3), "ms/step over", n.value)
+print("contacts", st.contacts, "solver", st.solver_contacts, "levels", st.levels, "pairs", st.candidate_pairs, "ovf", st.overflow)
