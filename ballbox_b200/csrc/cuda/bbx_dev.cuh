@@ -61,12 +61,14 @@ struct StepCounters {
     int n_mslots;            // M slots handed out (level-major constraint order)
     int n_nodes;             // solver nodes (runs of contacts between the same two bodies)
     int n_hit_bb;            // box-box candidates that passed SAT
-    int pad[2];
+    int fq_tail;             // flow solver: entries pushed to the ready queue
+    int fq_head;             // flow solver: chunk tickets handed out in iteration 0
     unsigned int bounds[6];  // ordered-int encoded min xyz / max xyz of small bodies
     unsigned int cut_dyn;    // float bits: largest bounding radius among non-static bodies
     unsigned int cut_all;    // float bits: largest bounding radius among all bodies
     int n_big;
-    int pad2[5];
+    int fq_ticket;           // flow solver: chunk tickets handed out in iterations 1..I-1
+    int pad2[4];
 };
 
 struct BbxDev {
@@ -128,6 +130,17 @@ struct BbxDev {
     int4 *Nd_k[BBX_NCLS];                        // (first M slot, constraint count, dynamic gid A, dynamic gid B)
     int *slot_of;                                // cap_contacts: contact -> M slot
     int *level_count;                            // (cap_levels + 4) * BBX_NCLS
+    // ---- barrier-free flow solver (single large world, bbx_solver.cu k_solve_flow) ----
+    // one 64-byte record per body, every 8-byte word = (float data, int version):
+    //   [0] (vx,ver)(vy,ver) [1] (vz,ver)(wx,ver) [2] (wy,ver)(wz,ver) [3] (1/m | 1/I << 32)(dependency depth)
+    // stored whole by the thread that visited the body, polled by the thread of the body's next constraint
+    ulonglong2 *flow;                            // 4 per body
+    int  *fq;                                    // ready queue = visiting order of iteration 0 (cap_contacts, -1 = empty)
+    int4 *fnd;                                   // 2 per queue slot: (gid A, gid B, pos A, len A) (pos B, len B, contact, -)
+    ulonglong2 *fimp;                            // 2 per queue slot: (jn,tag)(jt0,tag) (jt1,tag)(mT1,tag), tag = iterations applied
+    int last_flow;                               // the last solve ran on the flow solver (impulses live in fimp)
+    int flow_blocks;                             // co-resident blocks of k_solve_flow
+    int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)
     unsigned long long *level_ns;                // optional trace: globaltimer at the end of each level of iteration 1 (first 4096)
     // level-major copies streamed by iterations >= 1
     float4 *M;                   // same four float4 fields, plane-major: field r of slot s is M[r*cap_contacts + s]; a node's

@@ -120,6 +120,9 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     d->cap_levels = C < (1 << 20) ? C : (1 << 20);
     DALLOC(d->slot_of, C); DALLOC(d->level_count, ((size_t)d->cap_levels + 4) * BBX_NCLS);
     DALLOC(d->M, 4 * (size_t)C);
+    DALLOC(d->flow, 4 * (size_t)N); DALLOC(d->fq, C); DALLOC(d->fnd, 2 * (size_t)C); DALLOC(d->fimp, 2 * (size_t)C);
+    BBX_CUDA(d, cudaMemsetAsync(d->fq, 0xff, sizeof(int) * (size_t)C, d->stream));
+    { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
     DALLOC(d->level_ns, 4096 + 8);
     DALLOC(d->ctr, 1);
     DALLOC(d->sort_keys, C);
@@ -142,7 +145,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
-        d->slot_of, d->level_count, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
+        d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }

@@ -110,12 +110,18 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         // not scheduled (or no sweep ran): the accumulated impulses are whatever the record held (0 in PhysicsStep)
         float jn = l3.x, jt0 = l3.y, jt1 = l3.z;
         int slot = solved ? dv.slot_of[c] : -1;
-        if (slot >= 0) { float4 m3 = dv.M[3 * (size_t)dv.cap_contacts + slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
+        if (slot >= 0 && dv.last_flow) {
+            // flow solver: (value, tag) words in queue order
+            ulonglong2 i0 = dv.fimp[2 * (size_t)slot], i1 = dv.fimp[2 * (size_t)slot + 1];
+            jn = __uint_as_float((unsigned int)i0.x); jt0 = __uint_as_float((unsigned int)i0.y); jt1 = __uint_as_float((unsigned int)i1.x);
+        }
+        else if (slot >= 0) { float4 m3 = dv.M[3 * (size_t)dv.cap_contacts + slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
         else if (solved && friction > 0.0f) {
             // a constraint between two non-dynamic bodies is never scheduled, but the reference still
             // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477).
             // (In the block-per-world path scheduled constraints keep their impulses in L: slot < 0 too.)
             int4 hd = dv.node[2 * (size_t)(c - RUN_K(id.z))];
+            if (dv.last_flow) hd.y = dv.node[2 * (size_t)(c - RUN_K(id.z)) + 1].x;      // flow solver layout: one half per body
             if (hd.x < 0 && hd.y < 0) { jt0 = -0.0f; jt1 = -0.0f; }
         }
         ContactConstraint r;
@@ -290,6 +296,8 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
         return bbx_fail(d, BBX_ERR_OVERFLOW, "contact or candidate buffer overflow: raise max_collisions", __FILE__, __LINE__);
     if (d->ctr_host->overflow & 16)
         return bbx_fail(d, BBX_ERR_OVERFLOW, "solver dependency graph deeper than the level table", __FILE__, __LINE__);
+    if (d->ctr_host->overflow & 64)
+        return bbx_fail(d, BBX_ERR_OVERFLOW, "flow solver gave up waiting for a predecessor (corrupt schedule)", __FILE__, __LINE__);
     int n = d->ctr_host->n_contacts;
     if (n > d->cap_contacts) n = d->cap_contacts;
     if (n == 0) return 0;
@@ -332,7 +340,7 @@ __global__ void k_import_reset(BbxDev dv, int n)
 {
     StepCounters* c = dv.ctr;
     c->n_contacts = n; c->n_cand_sb = 0; c->n_cand_bb = 0; c->n_hit_bb = 0; c->n_solver = 0; c->n_touched = 0;
-    c->n_levels = 0; c->n_frontier0 = 0; c->n_mslots = 0; c->n_nodes = 0;
+    c->n_levels = 0; c->n_frontier0 = 0; c->n_mslots = 0; c->n_nodes = 0; c->fq_tail = 0; c->fq_head = 0; c->fq_ticket = 0;
 }
 
 struct ImportRec { int ta, ia, tb, ib; };

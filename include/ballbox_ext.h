@@ -49,6 +49,11 @@ void UseSDFDevice(PhysicsWorld* world, int sdf_id, const float* params8);
 #define BBX_SOLVER_EXACT     0 /* level-scheduled Gauss-Seidel: bit-identical to the
                                   reference's sequential sweep (default)                    */
 #define BBX_SOLVER_COLOURED  1 /* graph-coloured Gauss-Seidel: reorders the sweep          */
+#define BBX_SOLVER_EXACT_FLOW 2 /* the same exact schedule, barrier-free: every constraint waits
+                                  only for its own two predecessors (versioned body records,
+                                  iterations overlap); bit-identical results, experimental:
+                                  measured slower than the level kernel at 1M bodies
+                                  (profiles/r01_notes.md)                                   */
 void BallboxSetSolverSchedule(PhysicsWorld* world, int schedule);
 
 /* ---- statistics of the most recent step (and totals since creation) -------- */

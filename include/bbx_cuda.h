@@ -56,7 +56,7 @@ typedef struct {
     PhysicsSettings settings;      /* by value, re-read at every step like the reference */
     int   sdf_id;                  /* BBX_SDF_* of ballbox_ext.h; 0 = no SDF              */
     float sdf_params[8];
-    int   solver_schedule;         /* BBX_SOLVER_EXACT / BBX_SOLVER_COLOURED               */
+    int   solver_schedule;         /* BBX_SOLVER_EXACT / _COLOURED / _EXACT_FLOW           */
     int   has_forces;              /* 0: force/torque arrays are known to be all zero      */
     int   want_callbacks;          /* collect callback events                              */
 } BbxStepParams;

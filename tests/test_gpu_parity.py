@@ -444,3 +444,47 @@ def test_world_block_solver_path(product, truth):
         mm = parity.compare_worlds(views[i], w)
         assert not mm, f"world {i}: {mm[:3]}"
     d.DestroyPhysicsWorldBatch(batch)
+
+
+@pytest.mark.parametrize("kind,n,steps", [(bb.SCENE_MIXED, 3000, 40), (bb.SCENE_SDF, 1500, 40), (bb.SCENE_BALLS, 5000, 30)])
+def test_flow_schedule_is_bit_exact(product, truth, kind, n, steps):
+    """BBX_SOLVER_EXACT_FLOW: the barrier-free solver (every constraint waits for its own two predecessors
+    through versioned body records, iterations overlap) keeps every body's constraints in the reference's
+    order, so state AND the full constraint arrays equal the reference's bit for bit, every step."""
+    g = product.build_scene(kind, n, 909)
+    product.dll.BallboxSetSolverSchedule(g.ptr, bb.SOLVER_EXACT_FLOW)
+    c = truth.build_scene(kind, n, 909)
+    for s in range(steps):
+        g.step(DT); c.step(DT, pruned=True)
+        mm = parity.compare_worlds(g, c)
+        assert not mm, f"step {s}: {mm[:3]}"
+    st = g.stats()
+    assert st.overflow == 0 and st.levels >= 3          # "levels" = dependency depth in constraints for this schedule
+
+
+def test_flow_schedule_batch_and_single_iteration(product, truth):
+    """The flow solver on a batch of worlds (chains never cross worlds) and with solver_iterations = 1
+    (the final visit of a body happens in iteration 0)."""
+    d = product.dll
+    s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
+    batch = d.CreatePhysicsWorldBatch(20, s, b, c)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(20)]
+    for i, v in enumerate(views):
+        d.BbxSceneBuild(v.ptr, bb.SCENE_RLWORLD, 0, 6000 + i)
+        d.BallboxSetSolverSchedule(v.ptr, bb.SOLVER_EXACT_FLOW)
+    assert d.PhysicsStepBatch(batch, DT, 50) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    for i in (0, 7, 19):
+        w = truth.build_scene(bb.SCENE_RLWORLD, 0, 6000 + i)
+        for _ in range(50):
+            w.step(DT)
+        mm = parity.compare_worlds(views[i], w)
+        assert not mm, f"world {i}: {mm[:3]}"
+    d.DestroyPhysicsWorldBatch(batch)
+    g = product.build_scene(bb.SCENE_MIXED, 800, 31); t = truth.build_scene(bb.SCENE_MIXED, 800, 31)
+    d.BallboxSetSolverSchedule(g.ptr, bb.SOLVER_EXACT_FLOW)
+    g.w.settings.solver_iterations = 1; t.w.settings.solver_iterations = 1
+    for s_ in range(25):
+        g.step(DT); t.step(DT)
+        mm = parity.compare_worlds(g, t)
+        assert not mm, f"step {s_}: {mm[:3]}"

@@ -41,6 +41,10 @@ L = st.levels if False else w.stats().levels
 cnt = (C.c_int * (8 * 4096))(); ns = (C.c_ulonglong * 4097)()
 lib.dll.BallboxDebugLevels.argtypes = [bb.WP, C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.c_int]
 lib.dll.BallboxDebugLevels(w.ptr, cnt, ns, 4096)
+fd = np.frombuffer(ns, dtype=np.uint64)[4088:4096].astype(np.float64)
+if fd[5] > 0:
+    print(f"flow solver (last step): chunk visits={fd[0]:.0f} processing passes={fd[1]:.0f} spin passes={fd[2]:.0f} failed lane polls={fd[3]:.0f} "
+          f"warp wait/busy cycles={fd[4]/max(fd[5],1):.3f} replay (after iteration 0) ms={(fd[7]-fd[6])/1e6:.3f}")
 cnt = np.frombuffer(cnt, dtype=np.int32).reshape(-1, 8)[:L]; ns = np.frombuffer(ns, dtype=np.uint64)[:L + 1].astype(np.int64)
 dt_us = np.diff(ns)[1:] / 1e3
 print("levels", L, "nodes/level (first 12):", cnt.sum(1)[:12].tolist())
