@@ -987,7 +987,26 @@ __device__ __forceinline__ void ww_sweep_node(const BbxDev& dv, float4* vel, int
     if (hasB) { ww_store_body(dv, vel, w, nd.y, B); if (wake) wake_body(dv, nd.y); }
 }
 
-// dynamic shared memory: per warp [ vel: 2*nb float4 | level_start: WW_LMAX+1 ints | next_count, bad ]
+// the same sweep with the node's first record already in registers (replay: it was requested one step ahead)
+__device__ __forceinline__ void ww_sweep_node_pre(const BbxDev& dv, float4* vel, int w, int c, int gA, int gB, int m, F8 lo, F8 hi,
+                                                  const SolveParams& sp)
+{
+    bool hasA = gA >= 0, hasB = gB >= 0;
+    BodyState A, B;
+    if (hasA) ww_load_body(dv, vel, w, gA, A);
+    if (hasB) ww_load_body(dv, vel, w, gB, B);
+    float4* L = dv.L + 4 * (size_t)c;
+    for (int j = 0; j < m; j++, L += 4) {
+        float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
+        if (j + 1 < m) { lo = ld256_cg(L + 4); hi = ld256_cg(L + 6); }       // next record in flight
+        solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+        __stcg(L + 3, c3);
+    }
+    if (hasA) ww_store_body(dv, vel, w, gA, A);
+    if (hasB) ww_store_body(dv, vel, w, gB, B);
+}
+
+// dynamic shared memory: per warp [ vel: 2*nb float4 | steps: WW_LMAX+1 ints | next_count, bad ]
 __global__ void __launch_bounds__(WW_WARPS * 32, 2) k_solve_worlds(BbxDev dv, SolveParams sp, int* wq, const int* wq_count, int warp_bytes)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -997,8 +1016,9 @@ __global__ void __launch_bounds__(WW_WARPS * 32, 2) k_solve_worlds(BbxDev dv, So
     const int nb = dv.cap_s + dv.cap_b;
     unsigned char* base = smem_raw + (size_t)wib * warp_bytes;
     float4* vel = reinterpret_cast<float4*>(base);
-    int* level_start = reinterpret_cast<int*>(base + (size_t)nb * 32);
-    int* next_count = level_start + WW_LMAX + 1;
+    // steps of one sweep: 32 consecutive queue slots of one level each, entry = first slot | (count - 1) << 24
+    int* steps = reinterpret_cast<int*>(base + (size_t)nb * 32);
+    int* next_count = steps + WW_LMAX + 1;
     int n0 = min(wq_count[w], dv.cap_contacts_world);
     if (n0 == 0) return;                                              // no dynamic contact in this world
     int* queue = wq + (size_t)w * dv.cap_contacts_world;              // this world's visiting order
@@ -1009,19 +1029,24 @@ __global__ void __launch_bounds__(WW_WARPS * 32, 2) k_solve_worlds(BbxDev dv, So
         F8 v = ld256_cg(&dv.vel[2 * g]);
         vel[2 * i] = v.a; vel[2 * i + 1] = v.b;
     }
-    if (lane == 0) { next_count[0] = 0; level_start[0] = 0; }
+    if (lane == 0) next_count[0] = 0;
     __syncwarp();
+    // node descriptors in visiting order (contact, dynamic gid A, dynamic gid B, run length): the replay streams them
+    int4* wd = dv.Nd_k[0] + (size_t)w * dv.cap_contacts_world;
     // ---- iteration 0: Kahn levels ----
-    int head = 0, tail = n0, lvl = 0;
+    int head = 0, tail = n0, lvl = 0, ns = 0;
     bool bad = false;
     while (head < tail) {
         for (int p0 = head; p0 < tail; p0 += 32) {
             int p = p0 + lane;
+            if (lane == 0 && ns < WW_LMAX) steps[ns] = p0 | ((min(32, tail - p0) - 1) << 24);
+            ns++;
             if (p < tail) {
                 int c = __ldcg(&queue[p]);
                 F8 rec = ld256_nc((const float4*)&dv.node[2 * (size_t)c]);
                 int4 nd = make_int4(__float_as_int(rec.a.x), __float_as_int(rec.a.y), __float_as_int(rec.a.z), 0);
                 int sa = __float_as_int(rec.b.x), sb = __float_as_int(rec.b.y);
+                __stcg(&wd[p], make_int4(c, nd.x, nd.y, nd.z));
                 ww_sweep_node(dv, vel, w, c, nd, sp, true);
                 if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) == 1) {
                     int q = tail + atomicAdd(next_count, 1);
@@ -1037,27 +1062,37 @@ __global__ void __launch_bounds__(WW_WARPS * 32, 2) k_solve_worlds(BbxDev dv, So
         int pushed = next_count[0];
         __syncwarp();
         head = tail; tail += pushed; lvl++;
-        if (tail > qcap || lvl > WW_LMAX) { bad = true; break; }
-        if (lane == 0) { next_count[0] = 0; level_start[lvl] = head; }
+        if (tail > qcap || ns > WW_LMAX) { bad = true; break; }
+        if (lane == 0) next_count[0] = 0;
         __syncwarp();
     }
     if (bad) { if (lane == 0) atomicOr(&dv.ctr->overflow, 32); return; }
     const int n_levels = lvl;
     if (lane == 0) atomicMax(&dv.ctr->n_levels, n_levels);
     // ---- iterations 1..I-1: replay the visiting order ----
-    for (int it = 1; it < sp.iterations; it++) {
-        for (int l = 0; l < n_levels; l++) {
-            int s0 = level_start[l], s1 = (l + 1 < n_levels) ? level_start[l + 1] : tail;
-            for (int p0 = s0; p0 < s1; p0 += 32) {
-                int p = p0 + lane;
-                if (p < s1) {
-                    int c = __ldcg(&queue[p]);
-                    int4 nd = dv.node[2 * (size_t)c];
-                    ww_sweep_node(dv, vel, w, c, nd, sp, false);
-                }
-            }
-            __syncwarp();
-        }
+    // One flattened sequence of steps; the warp is alone on its world, so what hides the latency of the record
+    // gather is software pipelining: the descriptor of step j+2 and the first record of step j+1 are in flight while
+    // step j is swept (a step never spans two levels; __syncwarp separates steps, which is all a level boundary needs).
+    const int K = ns, total = (sp.iterations - 1) * K;
+    auto desc_at = [&](int j) -> int4 {
+        if (j >= total) return make_int4(-1, -1, -1, 0);
+        int e = steps[j % K];
+        return lane <= (e >> 24) ? __ldcg(&wd[(e & 0xffffff) + lane]) : make_int4(-1, -1, -1, 0);
+    };
+    int4 d0 = desc_at(0), d1 = desc_at(1);
+    F8 lo0, hi0;
+    lo0.a = lo0.b = hi0.a = hi0.b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (d0.x >= 0) { const float4* L = dv.L + 4 * (size_t)d0.x; lo0 = ld256_cg(L); hi0 = ld256_cg(L + 2); }
+    // (with a single step per sweep the next step's record is the one this step is about to update: no early load)
+    const bool early = K >= 2;
+    for (int j = 0; j < total; j++) {
+        int4 d2 = desc_at(j + 2);
+        F8 lo1 = lo0, hi1 = hi0;
+        if (early && d1.x >= 0) { const float4* L = dv.L + 4 * (size_t)d1.x; lo1 = ld256_cg(L); hi1 = ld256_cg(L + 2); }
+        if (d0.x >= 0) ww_sweep_node_pre(dv, vel, w, d0.x, d0.y, d0.z, d0.w, lo0, hi0, sp);
+        __syncwarp();
+        if (!early && d1.x >= 0) { const float4* L = dv.L + 4 * (size_t)d1.x; lo1 = ld256_cg(L); hi1 = ld256_cg(L + 2); }
+        d0 = d1; d1 = d2; lo0 = lo1; hi0 = hi1;
     }
     // ---- write the velocities back ----
     for (int i = lane; i < nb; i += 32) {
@@ -1071,6 +1106,7 @@ static int world_warp_bytes(const BbxDev* d) { return (d->cap_s + d->cap_b) * 32
 static bool use_world_warps(const BbxDev* d, int imported)
 {
     return !imported && d->n_worlds >= 16 && d->cap_s + d->cap_b <= WW_BODY_MAX && d->cap_s > 0 && d->cap_b > 0 &&
+           d->cap_contacts_world < (1 << 24) &&
            WW_WARPS * world_warp_bytes(d) <= 220 * 1024;
 }
 
