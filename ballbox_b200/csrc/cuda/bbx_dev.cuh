@@ -138,8 +138,11 @@ struct BbxDev {
     int  *fq;                                    // ready queue = visiting order of iteration 0 (cap_contacts, -1 = empty)
     int4 *fnd;                                   // 2 per queue slot: (gid A, gid B, pos A, len A) (pos B, len B, contact, -)
     ulonglong2 *fimp;                            // 2 per queue slot: (jn,tag)(jt0,tag) (jt1,tag)(mT1,tag), tag = iterations applied
+    int last_per_contact;                        // the last solve used one node per constraint (layout of `node`)
     int last_flow;                               // the last solve ran on the flow solver (impulses live in fimp)
     int flow_blocks;                             // co-resident blocks of k_solve_flow
+    int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
+    int no_groups;                               // BBX_WORLD_GROUPS=0: batched worlds use the warp-per-world kernel (A/B measurements)
     int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)
     unsigned long long *level_ns;                // optional trace: globaltimer at the end of each level of iteration 1 (first 4096)
     // level-major copies streamed by iterations >= 1

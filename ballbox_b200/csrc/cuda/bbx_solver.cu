@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int order, int per_
 __device__ __forceinline__ void flow_init_body(const BbxDev& dv, int g);
 __device__ __forceinline__ void wake_body(const BbxDev& dv, int g);
 
-__global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact)
+__global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, int flow_records)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     bool has = false;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact)
                     int4* nd = &dv.node[2 * (size_t)cur];
                     if (nd[0].x == x) nd[0] = make_int4(x, i, d, nxt); else nd[1] = make_int4(x, i, d, nxt);
                 }
-                flow_init_body(dv, x);
+                if (flow_records) flow_init_body(dv, x);
                 wake_body(dv, x);          // :1373-1376, :1402-1405: every impulse application wakes the body, even a zero one
             } else
             for (int i = 1; i < d; i++) {
@@ -1110,6 +1110,135 @@ static bool use_world_warps(const BbxDev* d, int imported)
            WW_WARPS * world_warp_bytes(d) <= 220 * 1024;
 }
 
+// ---------------------------------------------------------------------------
+// Batched small worlds, second form: one BLOCK per GROUP of worlds, one thread per constraint.
+//
+// A 256-body world offers ~20 independent constraints per dependency level: a warp per world keeps a
+// third of its lanes busy (and sweeps a manifold of m contacts in m dependent rounds).  Here a block of
+// 256 threads owns a group of worlds (as many as it takes to run the whole batch in one wave) and sweeps
+// level l of all of them together: every constraint is its own node (chains per constraint, as in the flow
+// solver), so the lanes of a warp do equal work, levels are separated by __syncthreads() and body
+// velocities stay in the packed global array (L2), which a block-wide barrier keeps coherent.
+// Iteration 0 discovers the group's levels (Kahn) and writes descriptors and records in visiting order;
+// iterations 1..I-1 stream them.  Same per-body constraint order as everywhere else: bit-identical results.
+// ---------------------------------------------------------------------------
+#define GRP_THREADS 256
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+#define GRP_BLOCKS_PER_SM 3
+#define GRP_LMAX 2047                  // dependency levels of a group
+
+__global__ void __launch_bounds__(256) k_frontier0_groups(BbxDev dv, int* gq, int* gq_count, int wpb, int gcap)
+{
+    __shared__ int s_solver;
+    if (threadIdx.x == 0) s_solver = 0;
+    __syncthreads();
+    int n = min(dv.ctr->n_contacts, dv.cap_contacts);
+    int mine = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        int gA = dv.node[2 * (size_t)c].x, gB = dv.node[2 * (size_t)c + 1].x;
+        if (gA < 0 && gB < 0) continue;
+        mine++;
+        if (dv.indeg[c] == 0) {
+            int x = gA >= 0 ? gA : gB;
+            int w = x < dv.NS ? x / dv.cap_s : (x - dv.NS) / dv.cap_b;
+            int g = w / wpb;
+            int slot = atomicAdd(&gq_count[g], 1);
+            if (slot < gcap) gq[(size_t)g * gcap + slot] = c;
+        }
+    }
+    if (mine) atomicAdd(&s_solver, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_solver) { atomicAdd(&dv.ctr->n_solver, s_solver); atomicAdd(&dv.ctr->n_nodes, s_solver); }
+}
+
+__global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups(BbxDev dv, SolveParams sp, int* gq, const int* gq_count, int gcap)
+{
+    __shared__ int level_start[GRP_LMAX + 2];
+    __shared__ int s_next;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int n0 = min(gq_count[g], gcap);
+    if (n0 == 0) return;                                              // no dynamic contact in this group
+    int* queue = gq + (size_t)g * gcap;                               // visiting order of the group
+    const size_t base = (size_t)g * gcap;                             // the group's slice of M / Nd / slot numbers
+    int4* gd = dv.Nd_k[0] + base;                                     // descriptors in visiting order: (gid A, gid B, contact, -)
+    const size_t PL = (size_t)dv.cap_contacts;
+    if (tid == 0) { s_next = 0; level_start[0] = 0; }
+    __syncthreads();
+    // ---- iteration 0: Kahn levels ----
+    int head = 0, tail = n0, lvl = 0;
+    bool bad = false;
+    while (head < tail) {
+        for (int p = head + tid; p < tail; p += GRP_THREADS) {
+            const int c = __ldcg(&queue[p]);
+            F8 nd = ld256_nc((const float4*)&dv.node[2 * (size_t)c]);    // (gid A, pos, len, successor on A) (same for B)
+            const int gA = __float_as_int(nd.a.x), gB = __float_as_int(nd.b.x);
+            const int sa = __float_as_int(nd.a.w), sb = __float_as_int(nd.b.w);
+            const float4* L = dv.L + 4 * (size_t)c;
+            F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+            float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
+            const bool hasA = gA >= 0, hasB = gB >= 0;
+            BodyState A, B;
+            if (hasA) load_body(dv, gA, A);
+            if (hasB) load_body(dv, gB, B);
+            solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+            if (hasA) store_body(dv, gA, A);
+            if (hasB) store_body(dv, gB, B);
+            float4* M = dv.M + base + p;
+            __stcg(M, c0); __stcg(M + PL, c1); __stcg(M + 2 * PL, c2); __stcg(M + 3 * PL, c3);
+            __stcg(&gd[p], make_int4(gA, gB, c, 0));
+            dv.slot_of[c] = (int)(base + p);
+            if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < gcap) __stcg(&queue[q], sa); }
+            if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < gcap) __stcg(&queue[q], sb); }
+        }
+        __syncthreads();
+        const int pushed = s_next;
+        __syncthreads();
+        head = tail; tail += pushed; lvl++;
+        if (tail > gcap || lvl > GRP_LMAX) { bad = true; break; }
+        if (tid == 0) { s_next = 0; level_start[lvl] = head; }
+        __syncthreads();
+    }
+    if (bad) { if (tid == 0) atomicOr(&dv.ctr->overflow, 32); return; }
+    const int n_levels = lvl;
+    if (tid == 0) { atomicMax(&dv.ctr->n_levels, n_levels); level_start[n_levels] = tail; }
+    __syncthreads();
+    // ---- iterations 1..I-1: stream the visiting order ----
+    for (int it = 1; it < sp.iterations; it++) {
+        for (int l = 0; l < n_levels; l++) {
+            const int s0 = level_start[l], s1 = level_start[l + 1];
+            {
+                // the records of the NEXT level are static: pull them into L2 while this level is swept (no registers)
+                const int ln = (l + 1 < n_levels) ? l + 1 : 0;
+                const int pn = level_start[ln] + tid;
+                if (pn < level_start[ln + 1]) {
+                    const float4* Mn = dv.M + base + pn;
+                    prefetch_l2(&gd[pn]); prefetch_l2(Mn); prefetch_l2(Mn + PL); prefetch_l2(Mn + 2 * PL);
+                    if (n_levels > 1) prefetch_l2(Mn + 3 * PL);
+                }
+            }
+            for (int p = s0 + tid; p < s1; p += GRP_THREADS) {
+                const int4 d = __ldcg(&gd[p]);
+                float4* M = dv.M + base + p;
+                float4 c0 = __ldcg(M), c1 = __ldcg(M + PL), c2 = __ldcg(M + 2 * PL), c3 = __ldcg(M + 3 * PL);
+                const bool hasA = d.x >= 0, hasB = d.y >= 0;
+                BodyState A, B;
+                if (hasA) load_body(dv, d.x, A);
+                if (hasB) load_body(dv, d.y, B);
+                solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                if (hasA) store_body(dv, d.x, A);
+                if (hasB) store_body(dv, d.y, B);
+                __stcg(M + 3 * PL, c3);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static bool use_world_groups(const BbxDev* d, int imported, int schedule)
+{
+    return !imported && d->n_worlds >= 16 && schedule == BBX_SOLVER_EXACT && !d->no_groups;
+}
+
 // touched-body statistics and sanity for the host
 int bbx_stage_solve(BbxDev* d, const BbxStepParams* p) { return bbx_stage_solve_ex(d, p, 0, p->settings.solver_iterations, 0); }
 
@@ -1120,14 +1249,16 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     const int G = BBX_NUM_SMS * 8;
     // opt-in (BBX_SOLVER_EXACT_FLOW or BBX_SOLVER_FLOW=1): barrier-free flow solver, every constraint its own node
     const int flow = (p->solver_schedule == BBX_SOLVER_EXACT_FLOW || (d->force_flow && p->solver_schedule == BBX_SOLVER_EXACT)) ? 1 : 0;
+    const int groups = (!flow && use_world_groups(d, imported, p->solver_schedule)) ? 1 : 0;
+    const int per_contact = flow | groups;                 // every constraint is its own node
     BBX_CUDA(d, cudaMemsetAsync(d->deg, 0, sizeof(int) * ((size_t)d->N + 1), d->stream));
-    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, flow);
+    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, per_contact);
     if (iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);
     if (rc) return rc;
-    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0), flow);
-    BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, flow);
-    d->last_flow = flow;
+    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0), per_contact);
+    BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow);
+    d->last_flow = flow; d->last_per_contact = per_contact;
     if (flow) {
         BBX_LAUNCH(d, k_frontier_flow, G, 256, 0, *d);
         if (d->flow_blocks == 0) {
@@ -1151,6 +1282,33 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         // cooperative launch: every block must be resident (the waits rely on it) and iteration 0 ends with a grid barrier
         BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_flow, dim3(d->flow_blocks), dim3(FLOW_THREADS), fargs, 0, d->stream));
         d->launches++;
+        BBX_CUDA(d, cudaGetLastError());
+        return 0;
+    }
+    if (groups) {
+        // batched small worlds: a block per group of worlds, sized so that the batch runs in one wave
+        if (d->grp_blocks == 0) {
+            int per_sm = 0, sms = 0;
+            BBX_CUDA(d, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
+            BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_groups, GRP_THREADS, 0));
+            if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "group solver kernel does not fit on an SM", __FILE__, __LINE__);
+            d->grp_blocks = per_sm * sms;
+        }
+        int wpb = (d->n_worlds + d->grp_blocks - 1) / d->grp_blocks;
+        if (wpb < 1) wpb = 1;
+        const int n_groups = (d->n_worlds + wpb - 1) / wpb;
+        long long gcap_ll = (long long)wpb * d->cap_contacts_world;
+        if (gcap_ll > d->cap_contacts) gcap_ll = d->cap_contacts;
+        const int gcap = (int)gcap_ll;
+        int* gq = d->queue_k[0];                       // capacity cap_contacts
+        int* gq_count = d->adj_cursor;                 // free again after k_adj_link; N + 1 >= n_groups ints
+        BBX_CUDA(d, cudaMemsetAsync(gq_count, 0, sizeof(int) * (size_t)n_groups, d->stream));
+        BBX_LAUNCH(d, k_frontier0_groups, G, 256, 0, *d, gq, gq_count, wpb, gcap);
+        bbx_timing_mark(d, 4);
+        SolveParams spg;
+        spg.restitution = p->settings.restitution; spg.friction = p->settings.friction;
+        spg.vel_threshold = p->settings.velocity_threshold; spg.iterations = iterations; spg.gather = 0;
+        BBX_LAUNCH(d, k_solve_groups, n_groups, GRP_THREADS, 0, *d, spg, gq, gq_count, gcap);
         BBX_CUDA(d, cudaGetLastError());
         return 0;
     }

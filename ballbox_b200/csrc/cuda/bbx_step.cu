@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
             // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477).
             // (In the block-per-world path scheduled constraints keep their impulses in L: slot < 0 too.)
             int4 hd = dv.node[2 * (size_t)(c - RUN_K(id.z))];
-            if (dv.last_flow) hd.y = dv.node[2 * (size_t)(c - RUN_K(id.z)) + 1].x;      // flow solver layout: one half per body
+            if (dv.last_per_contact) hd.y = dv.node[2 * (size_t)(c - RUN_K(id.z)) + 1].x;   // per-constraint layout: one half per body
             if (hd.x < 0 && hd.y < 0) { jt0 = -0.0f; jt1 = -0.0f; }
         }
         ContactConstraint r;
