@@ -1122,9 +1122,9 @@ static bool use_world_warps(const BbxDev* d, int imported)
 // Iteration 0 discovers the group's levels (Kahn) and writes descriptors and records in visiting order;
 // iterations 1..I-1 stream them.  Same per-body constraint order as everywhere else: bit-identical results.
 // ---------------------------------------------------------------------------
-#define GRP_THREADS 256
+#define GRP_THREADS 128
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-#define GRP_BLOCKS_PER_SM 3
+#define GRP_BLOCKS_PER_SM 6
 #define GRP_LMAX 2047                  // dependency levels of a group
 
 __global__ void __launch_bounds__(256) k_frontier0_groups(BbxDev dv, int* gq, int* gq_count, int wpb, int gcap)
@@ -1203,21 +1203,29 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     if (tid == 0) { atomicMax(&dv.ctr->n_levels, n_levels); level_start[n_levels] = tail; }
     __syncthreads();
     // ---- iterations 1..I-1: stream the visiting order ----
+    // The descriptor of this thread's first constraint of the NEXT level is fetched while the current level is
+    // swept (descriptors are static), so that after the barrier the body loads can be issued at once; the next
+    // level's records are pulled into L2 at the same time (prefetch, no registers).
+    int2 dn = make_int2(-1, -1);
+    { const int pn = level_start[0] + tid; if (pn < level_start[1]) { int4 t4 = __ldcg(&gd[pn]); dn = make_int2(t4.x, t4.y); } }
     for (int it = 1; it < sp.iterations; it++) {
         for (int l = 0; l < n_levels; l++) {
             const int s0 = level_start[l], s1 = level_start[l + 1];
+            const int2 dc = dn;
             {
-                // the records of the NEXT level are static: pull them into L2 while this level is swept (no registers)
                 const int ln = (l + 1 < n_levels) ? l + 1 : 0;
                 const int pn = level_start[ln] + tid;
+                dn = make_int2(-1, -1);
                 if (pn < level_start[ln + 1]) {
+                    int4 t4 = __ldcg(&gd[pn]); dn = make_int2(t4.x, t4.y);
                     const float4* Mn = dv.M + base + pn;
-                    prefetch_l2(&gd[pn]); prefetch_l2(Mn); prefetch_l2(Mn + PL); prefetch_l2(Mn + 2 * PL);
+                    prefetch_l2(Mn); prefetch_l2(Mn + PL); prefetch_l2(Mn + 2 * PL);
                     if (n_levels > 1) prefetch_l2(Mn + 3 * PL);
                 }
             }
             for (int p = s0 + tid; p < s1; p += GRP_THREADS) {
-                const int4 d = __ldcg(&gd[p]);
+                int2 d = dc;
+                if (p != s0 + tid) { int4 t4 = __ldcg(&gd[p]); d = make_int2(t4.x, t4.y); }      // (levels wider than the block)
                 float4* M = dv.M + base + p;
                 float4 c0 = __ldcg(M), c1 = __ldcg(M + PL), c2 = __ldcg(M + 2 * PL), c3 = __ldcg(M + 3 * PL);
                 const bool hasA = d.x >= 0, hasB = d.y >= 0;

@@ -6,6 +6,7 @@ from ballbox_b200 import binding as bb
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 settle = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else None
 lib = bbx.load(); d = lib.dll
 s, b, c = lib.scene_capacity(bb.SCENE_RLWORLD, 0)
 batch = d.CreatePhysicsWorldBatch(W, s, b, c)
@@ -15,6 +16,8 @@ d.BatchUpload(batch)
 done = 0
 while done < settle:
     k = min(50, settle - done); d.PhysicsStepBatch(batch, 1 / 60, k); d.BatchSynchronize(batch); done += k
+if iters is not None:
+    d.SetSolverIterations(d.BatchWorld(batch, 0), iters)      # the batch steps with world 0's settings
 d.BatchSetStageTiming(batch, 1)
 out = (C.c_float * 6)(); n = C.c_int()
 d.BatchGetStageTiming(batch, out, C.byref(n))
