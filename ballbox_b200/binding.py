@@ -216,6 +216,10 @@ class BallboxLib:
             d.BallboxClearError.restype = None
             d.UseSDFDevice.argtypes = [WP, C.c_int, C.POINTER(C.c_float)]
             d.UseSDFDevice.restype = None
+            d.BallboxSetSDFBakeRegion.argtypes = [WP, Vec3, Vec3, C.c_int]
+            d.BallboxSetSDFBakeRegion.restype = None
+            d.BallboxBakeSDF.argtypes = [WP]; d.BallboxBakeSDF.restype = C.c_int
+            d.BallboxSdfInUse.argtypes = [WP]; d.BallboxSdfInUse.restype = C.c_int
             d.BallboxSetSolverSchedule.argtypes = [WP, C.c_int]
             d.BallboxSetSolverSchedule.restype = None
             d.BallboxGetStats.argtypes = [WP, C.POINTER(BallboxStats)]

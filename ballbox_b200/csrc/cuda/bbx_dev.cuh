@@ -162,6 +162,9 @@ struct BbxDev {
     int imported_list;           // the device contact list was imported from the host in array order
     int wb_attr_set;             // dynamic shared memory attribute of the per-world solve kernel was set
 
+    // baked SDF (host function sampled on a grid, bbx_dev_set_baked_sdf)
+    float *sdf_grid; int sdf_nx, sdf_ny, sdf_nz; float sdf_ox, sdf_oy, sdf_oz, sdf_inv_cell;
+
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy
     unsigned long long *sort_keys;   // export: 64-bit reference-order keys

@@ -377,9 +377,31 @@ __global__ void __launch_bounds__(128) k_bb_manifold(BbxDev dv, float tol, float
 // ---------------------------------------------------------------------------
 // SDF probing
 // ---------------------------------------------------------------------------
-struct SdfDesc { int id; float prm[8]; float eps; };
+struct SdfDesc { int id; float prm[8]; float eps; const float* grid; int nx, ny, nz; float ox, oy, oz, inv_cell; };
 
-__device__ __forceinline__ float sdf_at(const SdfDesc& s, float3 p) { return bbx_sdf_eval(s.id, s.prm, p.x, p.y, p.z); }
+// baked host SDF: trilinear interpolation of the grid samples, coordinates clamped to the baked region.
+// Plain f32 operations in a fixed order (compiled with -fmad=false like everything else): deterministic.
+__device__ __forceinline__ float sdf_baked(const SdfDesc& s, float3 p)
+{
+    float ux = (p.x - s.ox) * s.inv_cell, uy = (p.y - s.oy) * s.inv_cell, uz = (p.z - s.oz) * s.inv_cell;
+    ux = fminf(fmaxf(ux, 0.0f), (float)(s.nx - 1)); uy = fminf(fmaxf(uy, 0.0f), (float)(s.ny - 1)); uz = fminf(fmaxf(uz, 0.0f), (float)(s.nz - 1));
+    int ix = min((int)ux, s.nx - 2), iy = min((int)uy, s.ny - 2), iz = min((int)uz, s.nz - 2);
+    float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
+    const float* g = s.grid + ((size_t)iz * s.ny + iy) * s.nx + ix;
+    const size_t sy = (size_t)s.nx, sz = (size_t)s.nx * s.ny;
+    float v000 = __ldg(g), v100 = __ldg(g + 1), v010 = __ldg(g + sy), v110 = __ldg(g + sy + 1);
+    float v001 = __ldg(g + sz), v101 = __ldg(g + sz + 1), v011 = __ldg(g + sz + sy), v111 = __ldg(g + sz + sy + 1);
+    float a00 = v000 + (v100 - v000) * fx, a10 = v010 + (v110 - v010) * fx;
+    float a01 = v001 + (v101 - v001) * fx, a11 = v011 + (v111 - v011) * fx;
+    float b0 = a00 + (a10 - a00) * fy, b1 = a01 + (a11 - a01) * fy;
+    return b0 + (b1 - b0) * fz;
+}
+
+__device__ __forceinline__ float sdf_at(const SdfDesc& s, float3 p)
+{
+    if (s.id == BBX_SDF_ID_BAKED) return sdf_baked(s, p);
+    return bbx_sdf_eval(s.id, s.prm, p.x, p.y, p.z);
+}
 
 __device__ __forceinline__ float3 sdf_normal(const SdfDesc& s, float3 p)               // SDF_EstimateNormal :2318-2331
 {
@@ -463,6 +485,10 @@ int bbx_stage_narrowphase(BbxDev* d, const BbxStepParams* p)
     if (p->sdf_id != BBX_SDF_NONE) {
         SdfDesc s; s.id = p->sdf_id; s.eps = p->settings.sdf_normal_epsilon;
         for (int k = 0; k < 8; k++) s.prm[k] = p->sdf_params[k];
+        s.grid = d->sdf_grid; s.nx = d->sdf_nx; s.ny = d->sdf_ny; s.nz = d->sdf_nz;
+        s.ox = d->sdf_ox; s.oy = d->sdf_oy; s.oz = d->sdf_oz; s.inv_cell = d->sdf_inv_cell;
+        if (s.id == BBX_SDF_ID_BAKED && !s.grid)
+            return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "baked SDF selected but no grid was uploaded", __FILE__, __LINE__);
         if (d->NS > 0) BBX_LAUNCH(d, k_sdf_spheres, BBX_NUM_SMS * 8, 256, 0, *d, s);
         if (d->NB > 0) BBX_LAUNCH(d, k_sdf_boxes, BBX_NUM_SMS * 8, 128, 0, *d, s);
     }

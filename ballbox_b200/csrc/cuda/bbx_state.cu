@@ -146,7 +146,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
-        d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
+        d->sdf_grid, d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
@@ -155,6 +155,22 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
     cudaGetLastError();
     free(d->err);
     free(d);
+}
+
+extern "C" int bbx_dev_set_baked_sdf(BbxDev* d, const float* values, int nx, int ny, int nz, const float origin[3], float cell)
+{
+    if (!d || !values || !origin || nx < 2 || ny < 2 || nz < 2 || !(cell > 0.0f)) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));           // no step may still be reading the old grid
+    if (d->sdf_grid) { cudaFree(d->sdf_grid); d->sdf_grid = NULL; }
+    size_t n = (size_t)nx * ny * nz;
+    BBX_CUDA(d, cudaMalloc((void**)&d->sdf_grid, n * sizeof(float)));
+    BBX_CUDA(d, cudaMemcpyAsync(d->sdf_grid, values, n * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));           // `values` may be freed by the caller
+    d->sdf_nx = nx; d->sdf_ny = ny; d->sdf_nz = nz;
+    d->sdf_ox = origin[0]; d->sdf_oy = origin[1]; d->sdf_oz = origin[2]; d->sdf_inv_cell = 1.0f / cell;
+    return 0;
 }
 
 extern "C" void bbx_dev_set_stream(BbxDev* d, void* s) { if (d) d->stream = (cudaStream_t)s; }

@@ -40,6 +40,10 @@ struct PhysicsWorldBatch {
     void* stream;
     int sync_mode, schedule;
     int sdf_id; float sdf_params[8];
+    /* baked host SDF (ballbox_ext.h): region, resolution, and which function the device grid holds */
+    int bake_region_set, bake_res, bake_dirty;
+    float bake_lo[3], bake_hi[3];
+    SDFFunction baked_fn;
     int uploaded, forces_dirty, n_callbacks, cb_dirty, timing;
     CollisionContact* ev_contacts; int *ev_steps, *ev_worlds; int ev_cap;
     int has_err; char err[256];
@@ -293,6 +297,36 @@ void UseSDF(PhysicsWorld* world, SDFFunction fn)                      /* ballbox
     if (!world) return;
     world->SDFCollider = fn;
     world->usesSDF = (fn != NULL);
+}
+
+static int bake_sdf(struct PhysicsWorldBatch* b);
+
+void BallboxSetSDFBakeRegion(PhysicsWorld* world, Vec3 lo, Vec3 hi, int resolution)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return;
+    struct PhysicsWorldBatch* b = p->batch;
+    b->bake_region_set = 1; b->bake_res = resolution; b->bake_dirty = 1;
+    b->bake_lo[0] = lo.x; b->bake_lo[1] = lo.y; b->bake_lo[2] = lo.z;
+    b->bake_hi[0] = hi.x; b->bake_hi[1] = hi.y; b->bake_hi[2] = hi.z;
+}
+
+int BallboxBakeSDF(PhysicsWorld* world)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return BBX_ERR_BAD_ARGUMENT;
+    if (p->batch->has_err) return BBX_ERR_STICKY;
+    return bake_sdf(p->batch);
+}
+
+int BallboxSdfInUse(PhysicsWorld* world)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return BBX_SDF_NONE;
+    PhysicsWorld* w0 = &p->batch->worlds[0].pub;
+    if (!w0->usesSDF) return BBX_SDF_NONE;
+    if (p->batch->sdf_id != BBX_SDF_NONE) return p->batch->sdf_id;
+    return w0->SDFCollider ? BBX_SDF_BAKED : BBX_SDF_NONE;
 }
 
 void UseSDFDevice(PhysicsWorld* world, int sdf_id, const float* params8)
@@ -580,6 +614,73 @@ static int batch_upload(struct PhysicsWorldBatch* b)
     return rc;
 }
 
+/* Bake world 0's host SDF (reference UseSDF, ballbox.h:1688) into a regular grid on the device.  The GPU
+ * cannot call a host function pointer; this is the one-off sampling the step kernels interpolate. */
+static int bake_sdf(struct PhysicsWorldBatch* b)
+{
+    PhysicsWorld* w0 = &b->worlds[0].pub;
+    SDFFunction fn = w0->SDFCollider;
+    if (!fn) { batch_fail(b, "BallboxBakeSDF: no host SDF was set with UseSDF"); return BBX_ERR_BAD_ARGUMENT; }
+    int rc = batch_ensure_dev(b);
+    if (rc) return rc;
+    float lo[3], hi[3];
+    if (b->bake_region_set) {
+        for (int a = 0; a < 3; a++) { lo[a] = b->bake_lo[a]; hi[a] = b->bake_hi[a]; }
+    } else {
+        /* bounding box of every body of every world, grown by 25 % + 2 units on each side */
+        int any = 0;
+        for (int a = 0; a < 3; a++) { lo[a] = 0.0f; hi[a] = 0.0f; }
+        for (int w = 0; w < b->n_worlds; w++) {
+            SphereSystem* S = &b->worlds[w].spheres; BoxSystem* B = &b->worlds[w].boxes;
+            for (int i = 0; i < S->count + B->count; i++) {
+                Vec3 c; float r;
+                if (i < S->count) { c = S->positions[i]; r = S->radii[i]; }
+                else {
+                    int k = i - S->count; Quat q = B->rotations[k];
+                    float q2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+                    c = B->positions[k]; r = Vec3Length(B->sizes[k]) * (q2 > 1.0f ? q2 : 1.0f);
+                }
+                float pc[3] = { c.x, c.y, c.z };
+                for (int a = 0; a < 3; a++) {
+                    if (!(pc[a] == pc[a]) || !(r == r)) continue;                      /* NaN */
+                    if (!any || pc[a] - r < lo[a]) lo[a] = pc[a] - r;
+                    if (!any || pc[a] + r > hi[a]) hi[a] = pc[a] + r;
+                }
+                any = 1;
+            }
+        }
+        if (!any) for (int a = 0; a < 3; a++) { lo[a] = -10.0f; hi[a] = 10.0f; }
+        for (int a = 0; a < 3; a++) { float g = 0.25f * (hi[a] - lo[a]) + 2.0f; lo[a] -= g; hi[a] += g; }
+    }
+    int res = b->bake_res > 0 ? b->bake_res : 192;
+    if (res < 2) res = 2;
+    if (res > 1024) res = 1024;
+    float longest = 0.0f;
+    for (int a = 0; a < 3; a++) { if (!(hi[a] > lo[a])) hi[a] = lo[a] + 1.0f; if (hi[a] - lo[a] > longest) longest = hi[a] - lo[a]; }
+    int n[3]; float cell;
+    for (;;) {
+        cell = longest / (float)(res - 1);
+        long long total = 1;
+        for (int a = 0; a < 3; a++) { n[a] = (int)ceilf((hi[a] - lo[a]) / cell) + 1; if (n[a] < 2) n[a] = 2; total *= n[a]; }
+        if (total <= (1ll << 26) || res <= 2) break;
+        res = res * 3 / 4;                              /* keep the grid below 64 M samples (256 MB) */
+    }
+    size_t count = (size_t)n[0] * n[1] * n[2];
+    float* values = (float*)malloc(count * sizeof(float));
+    if (!values) { batch_fail(b, "BallboxBakeSDF: out of host memory"); return BBX_ERR_BAD_ARGUMENT; }
+    size_t at = 0;
+    for (int k = 0; k < n[2]; k++)
+        for (int j = 0; j < n[1]; j++)
+            for (int i = 0; i < n[0]; i++) {
+                Vec3 p = { lo[0] + (float)i * cell, lo[1] + (float)j * cell, lo[2] + (float)k * cell };
+                values[at++] = fn(p);
+            }
+    rc = batch_check_dev(b, bbx_dev_set_baked_sdf(b->dev, values, n[0], n[1], n[2], lo, cell));
+    free(values);
+    if (!rc) { b->baked_fn = fn; b->bake_dirty = 0; }
+    return rc;
+}
+
 static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, int want_callbacks, BbxStepParams* p)
 {
     PhysicsWorld* w0 = &b->worlds[0].pub;
@@ -589,11 +690,11 @@ static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, in
     p->sdf_id = BBX_SDF_NONE;
     if (w0->usesSDF) {
         if (b->sdf_id == BBX_SDF_NONE) {
-            /* reference condition is usesSDF && SDFCollider (ballbox.h:2075); a host pointer cannot run on the GPU */
+            /* reference condition is usesSDF && SDFCollider (ballbox.h:2075); a host pointer cannot run on the GPU:
+             * it is baked once into a grid (ballbox_ext.h) */
             if (w0->SDFCollider) {
-                batch_fail(b, "UseSDF(world, host_function): a host function pointer cannot be evaluated on the GPU; "
-                              "select a device SDF with UseSDFDevice (ballbox_ext.h)");
-                return BBX_ERR_HOST_SDF;
+                if (b->baked_fn != w0->SDFCollider || b->bake_dirty) { int rc = bake_sdf(b); if (rc) return rc; }
+                p->sdf_id = BBX_SDF_BAKED;
             }
         } else {
             p->sdf_id = b->sdf_id;

@@ -34,16 +34,31 @@ void BallboxSetStream(PhysicsWorld* world, void* stream);
 const char* BallboxGetLastError(PhysicsWorld* world);  /* NULL when healthy */
 void        BallboxClearError(PhysicsWorld* world);
 
-/* ---- device SDF colliders.  A host function pointer cannot run on the GPU;
- * UseSDF(world, fn) keeps the pointer (so user code still compiles) and the
- * next PhysicsStep fails loudly unless one of these was selected as well. ---- */
+/* ---- SDF colliders on the device.  A host function pointer cannot run on the GPU.
+ * UseSDF(world, fn) (reference ballbox.h:1688) keeps the pointer; at the next PhysicsStep the
+ * function is BAKED ONCE: sampled on a regular grid over the bake region and uploaded, and
+ * the kernels read it back with trilinear interpolation (f32, fixed operation order).  A
+ * baked SDF is an approximation: the error is the interpolation error of fn at the grid
+ * spacing (O(h^2 |f''|); exact for functions that are linear in x, y and z), and normals are the
+ * reference's central differences of the interpolant.  Outside the region the nearest grid
+ * value is used.  For bit-exact results select an SDF that exists as device code with
+ * UseSDFDevice instead (it takes precedence over a host pointer). ---------------------- */
 #define BBX_SDF_NONE        0
 #define BBX_SDF_PLANE_Y     1  /* f(p) = p.y - params[0]                                    */
 #define BBX_SDF_WAVY_DET    2  /* f(p) = p.y - S(p.x)*S(p.z), S = bbx_det_sin (bit-exact on
                                   CPU and GPU; see bbx_sdf_library.h)                       */
 #define BBX_SDF_WAVY_LIBM   3  /* f(p) = p.y - sinf(p.x)*sinf(p.z) with CUDA sinf (README)  */
 #define BBX_SDF_SPHERE_IN   4  /* inside of a sphere: f(p) = params[0] - |p|                */
+#define BBX_SDF_BAKED       5  /* reported by BallboxSdfInUse when a host function was baked */
 void UseSDFDevice(PhysicsWorld* world, int sdf_id, const float* params8);
+/* Region and resolution of the bake (cells along the longest axis, 2..1024; the other axes get the
+ * same spacing).  Default: the bounding box of all bodies at bake time, grown by 25 % + 2 units on
+ * every side, 192 cells along the longest axis.  Calling it (or UseSDF with another function)
+ * schedules a new bake. */
+void BallboxSetSDFBakeRegion(PhysicsWorld* world, Vec3 lo, Vec3 hi, int resolution);
+/* Bake now instead of at the next step; returns 0 or an error code (message: BallboxGetLastError). */
+int  BallboxBakeSDF(PhysicsWorld* world);
+int  BallboxSdfInUse(PhysicsWorld* world);      /* BBX_SDF_* the next step will use */
 
 /* ---- solver schedule ------------------------------------------------------- */
 #define BBX_SOLVER_EXACT     0 /* level-scheduled Gauss-Seidel: bit-identical to the

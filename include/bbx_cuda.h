@@ -61,6 +61,9 @@ typedef struct {
     int   want_callbacks;          /* collect callback events                              */
 } BbxStepParams;
 
+/* baked SDF: nx*ny*nz samples (x fastest) of a host function at origin + (i,j,k)*cell; replaces any earlier bake */
+int  bbx_dev_set_baked_sdf(BbxDev* dev, const float* values, int nx, int ny, int nz, const float origin[3], float cell);
+
 int  bbx_device_count(void);
 int  bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_spheres, int cap_boxes,
                     int cap_contacts_per_world);

@@ -28,6 +28,7 @@
 #define BBX_SDF_ID_WAVY_DET   2
 #define BBX_SDF_ID_WAVY_LIBM  3
 #define BBX_SDF_ID_SPHERE_IN  4
+#define BBX_SDF_ID_BAKED      5   /* a host function sampled once on a regular grid (device only; see ballbox_ext.h) */
 
 /* sine with one-step range reduction and an odd degree-11 polynomial; every
  * operation is a single IEEE binary32 op in a fixed order. */

@@ -191,12 +191,57 @@ def test_odd_geometry(product, truth):
         assert not mm, f"step {s}: {mm[:3]}"
 
 
-def test_host_sdf_pointer_fails_loudly(product):
-    w = product.build_scene(bb.SCENE_BALLS, 10, 1)
-    fn = bb.SDFFunction(lambda p: p.y)
-    product.dll.UseSDF(w.ptr, bb.C.cast(fn, bb.C.c_void_p))
-    with pytest.raises(bb.BallboxError, match="host function pointer"):
-        w.step(DT)
+def _sdf_scene(lib, fn_ptr):
+    """Spheres and rotated boxes dropped onto a host-function SDF (no UseSDFDevice)."""
+    w = lib.create_world(64, 32, 4096)
+    w.set_gravity((0.0, -9.8, 0.0))
+    for i in range(40):
+        w.add_sphere((-4.0 + 0.9 * (i % 10), 1.5 + 0.8 * (i // 10), -1.5 + 1.1 * (i % 4)), 0.3 + 0.02 * (i % 5))
+    for i in range(20):
+        w.add_box((-4.2 + 0.85 * (i % 10), 5.0 + 0.9 * (i // 10), 0.4 * (i % 3) - 0.4), (0.25, 0.2 + 0.02 * (i % 4), 0.3),
+                  w.quat_axis_angle((1, 2 + i, 3), 0.37 * i))
+    lib.dll.UseSDF(w.ptr, fn_ptr)
+    return w
+
+
+def test_host_sdf_is_baked_plane(product, truth):
+    """UseSDF(world, host_fn) without a device SDF: the function is sampled once on a grid and interpolated
+    on the GPU (ballbox_ext.h).  f(p) = p.y is linear, trilinear interpolation reproduces it up to rounding,
+    so the run stays within the north star's 1e-4 of the reference that calls the function itself."""
+    g = _sdf_scene(product, bb.C.cast(product.dll.BbxHostSdfPlane0, bb.C.c_void_p))
+    c = _sdf_scene(truth, bb.C.cast(truth.dll.BbxHostSdfPlane0, bb.C.c_void_p))
+    assert product.dll.BallboxSdfInUse(g.ptr) == 5            # BBX_SDF_BAKED
+    for s in range(45):
+        g.step(DT); c.step(DT)
+    assert len(g.constraints()) == len(c.constraints()) > 20
+    a, b = g.snapshot(), c.snapshot()
+    for f in ("s_pos", "b_pos", "s_vel", "b_vel"):
+        err = np.abs(a[f].astype(np.float64) - b[f]).max()
+        assert err < 1e-4 * max(1.0, np.abs(b[f]).max()), (f, err)
+
+
+def test_host_sdf_python_callback_is_baked_wavy(product, truth):
+    """An arbitrary user function (here a Python callback) on the README terrain: baked over an explicit region
+    at 0.1 spacing.  Accuracy is the interpolation error (h^2/8 |f''| ~ 1.3e-3 here), so the comparison with
+    the reference is a drift bound, not bit parity; nothing tunnels through the terrain."""
+    import math
+    f = lambda p: p.y - math.sin(p.x) * math.sin(p.z)
+    fn_g, fn_c = bb.SDFFunction(f), bb.SDFFunction(f)
+    g = _sdf_scene(product, bb.C.cast(fn_g, bb.C.c_void_p))
+    c = _sdf_scene(truth, bb.C.cast(fn_c, bb.C.c_void_p))
+    product.dll.BallboxSetSDFBakeRegion(g.ptr, bb.Vec3(-8, -2, -6), bb.Vec3(8, 10, 6), 161)
+    assert product.dll.BallboxBakeSDF(g.ptr) == 0, product.dll.BallboxGetLastError(g.ptr)
+    for s in range(40):
+        g.step(DT); c.step(DT)
+    a, b = g.snapshot(), c.snapshot()
+    assert np.abs(a["s_pos"].astype(np.float64) - b["s_pos"]).max() < 0.05
+    assert np.abs(a["b_pos"].astype(np.float64) - b["b_pos"]).max() < 0.08
+    n_s = g.n_spheres
+    sp = g.sphere_arrays()
+    for i in range(n_s):
+        x, y, z = (float(v) for v in sp["pos"][i])
+        assert y - math.sin(x) * math.sin(z) > -0.15, f"sphere {i} sank into the terrain"
+    assert len(g.constraints()) > 5 and abs(len(g.constraints()) - len(c.constraints())) <= 4
 
 
 def test_contact_overflow_is_reported(product):
