@@ -19,13 +19,13 @@ BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libballbox_b200.so")
 
 CUDA_SOURCES = ["bbx_state.cu", "bbx_integrate.cu", "bbx_broadphase.cu", "bbx_narrowphase.cu",
-                "bbx_solver.cu", "bbx_step.cu", "bbx_sort.cu"]
+                "bbx_solver.cu", "bbx_step.cu", "bbx_sort.cu", "bbx_queries.cu"]
 HOST_SOURCES = ["ballbox_host.c", "bbx_scenes.c"]
 
 # -fmad=false: no FMA contraction, results must match the reference bit for bit
 # (SURVEY.md F5).  IEEE sqrt/div are nvcc defaults; never --use_fast_math.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
-              "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xptxas", "-v"]
 GCC_FLAGS = ["-O2", "-std=gnu11", "-ffp-contract=off", "-fPIC", "-DBBX_PRODUCT", "-Wall", "-Wno-unused-function"]
 
 

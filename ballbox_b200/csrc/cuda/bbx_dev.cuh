@@ -213,6 +213,7 @@ int bbx_stage_collect_events(BbxDev* d, const BbxStepParams* p);
 int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out);
 
 #ifdef __CUDACC__
+#define BBX_HDI __host__ __device__ __forceinline__     // geometry shared by the kernels and the host queries
 // contact-run encoding in c_ids.z: low 8 bits = index k inside the run, bits 8.. = run length
 #define RUN_K(z)   ((z) & 0xff)
 #define RUN_LEN(z) ((z) >> 8)
@@ -228,33 +229,33 @@ __host__ __device__ __forceinline__ int bbx_node_class(int m, bool any_box)
 // ---------------------------------------------------------------------------
 // exact vector math (reference ballbox.h:501-535)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
-__device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
-__device__ __forceinline__ float3 v3add(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ float3 v3sub(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ float3 v3scale(float3 v, float s) { return f3(v.x * s, v.y * s, v.z * s); }
-__device__ __forceinline__ float  v3dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ float3 v3cross(float3 a, float3 b)
+BBX_HDI float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+BBX_HDI float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
+BBX_HDI float3 v3add(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+BBX_HDI float3 v3sub(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+BBX_HDI float3 v3scale(float3 v, float s) { return f3(v.x * s, v.y * s, v.z * s); }
+BBX_HDI float  v3dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+BBX_HDI float3 v3cross(float3 a, float3 b)
 {
     return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-__device__ __forceinline__ float  v3len(float3 v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
-__device__ __forceinline__ float3 v3norm(float3 v)
+BBX_HDI float  v3len(float3 v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
+BBX_HDI float3 v3norm(float3 v)
 {
     float l = v3len(v);
     if (l < 1e-6f) return f3(0.0f, 0.0f, 0.0f);
     return v3scale(v, 1.0f / l);
 }
-__device__ __forceinline__ float3 v3mul(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+BBX_HDI float3 v3mul(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 
 // glibc 2.39 fminf/fmaxf return the FIRST operand on ties (measured in this
 // image: fminf(+0,-0) = +0, fminf(-0,+0) = -0) and the non-NaN operand otherwise.
-__device__ __forceinline__ float bb_fminf(float x, float y) { return (x <= y || y != y) ? x : y; }
-__device__ __forceinline__ float bb_fmaxf(float x, float y) { return (x >= y || y != y) ? x : y; }
+BBX_HDI float bb_fminf(float x, float y) { return (x <= y || y != y) ? x : y; }
+BBX_HDI float bb_fmaxf(float x, float y) { return (x >= y || y != y) ? x : y; }
 
 // quaternion helpers (reference ballbox.h:543-562, :625-639)
-__device__ __forceinline__ float4 qconj(float4 q) { return make_float4(-q.x, -q.y, -q.z, q.w); }
-__device__ __forceinline__ float3 qrot(float4 q, float3 v)
+BBX_HDI float4 qconj(float4 q) { return make_float4(-q.x, -q.y, -q.z, q.w); }
+BBX_HDI float3 qrot(float4 q, float3 v)
 {
     float3 u = f3(q.x, q.y, q.z);
     float  s = q.w;
@@ -301,7 +302,7 @@ __device__ __forceinline__ float ord2f(unsigned int u)
 
 // bounding radius of a box whose rotation may be non-unit: QuatRotateVec3 scales
 // by |q|^2 (ballbox.h:630-639) and AddBox never normalises (ballbox.h:716).
-__device__ __forceinline__ float box_bound_radius(float3 half, float4 q)
+BBX_HDI float box_bound_radius(float3 half, float4 q)
 {
     float q2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
     if (!(q2 > 1.0f)) q2 = 1.0f;

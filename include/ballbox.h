@@ -254,6 +254,31 @@ void AddBoxTorque(PhysicsWorld* world, int index, Vec3 torque);
 void SetSphereCollisionCallback(PhysicsWorld* world, int sphereIndex, OnCollision callback);
 void SetBoxCollisionCallback(PhysicsWorld* world, int boxIndex, OnCollision callback);
 
+/* ---- standalone queries and helpers outside PhysicsStep (ref :231-239, :262-297).
+ * Host functions, as in the reference; their geometry is the __host__ __device__ code the
+ * narrowphase kernels run (ballbox_b200/csrc/cuda/bbx_geom.cuh), so a query returns the bits a
+ * step produces for that pair.  SDF helpers call the host function given to UseSDF. ------- */
+bool CheckSphereCollision(Vec3 pos1, float radius1, Vec3 pos2, float radius2);
+bool CheckSphereCollisionWithData(Vec3 pos1, float radius1, Vec3 pos2, float radius2, CollisionContact* contact);
+bool CheckSphereSystemCollisions(SphereSystem* system, int sphere_index);
+bool CheckBoxSystemCollisions(BoxSystem* system, int box_index);
+bool CheckSphereBoxCollision(Vec3 spherePos, float sphereRadius, Vec3 boxPos, Vec3 boxSize, Quat boxRot);
+bool CheckSphereBoxCollisionWithData(Vec3 spherePos, float sphereRadius, Vec3 boxPos, Vec3 boxSize, Quat boxRot, CollisionContact* contact);
+bool CheckBoxCollision(Vec3 pos1, Vec3 size1, Quat rot1, Vec3 pos2, Vec3 size2, Quat rot2);
+bool CheckBoxCollisionWithData(Vec3 pos1, Vec3 size1, Quat rot1, Vec3 pos2, Vec3 size2, Quat rot2, CollisionContact* contact);
+void GenerateBoxBoxManifold(PhysicsWorld* world, int boxIndexA, int boxIndexB, ContactManifold* manifold);
+void SelectOptimalContactPoints(Vec3* candidate_points, float* penetrations, int candidate_count,
+                                ContactManifold* manifold, Vec3 normal, int max_contacts);
+void AddManifoldToConstraints(PhysicsWorld* world, ContactManifold* manifold);
+Vec3 SDF_EstimateNormal(PhysicsWorld* world, Vec3 point);
+bool CheckBoxSDFCollision(PhysicsWorld* world, Vec3 boxPos, Vec3 boxSize, Quat boxRot, CollisionContact* contact);
+void GenerateBoxSDFContacts(PhysicsWorld* world, int boxIndex);
+/* the pre-constraint impulse path and the position pass: defined by the reference, never called by PhysicsStep */
+Vec3  GetBodyVelocityAtPoint(PhysicsWorld* world, int bodyType, int bodyIndex, Vec3 point);
+float CalculateEffectiveMass(PhysicsWorld* world, CollisionContact* contact);
+void  ApplyImpulse(PhysicsWorld* world, int bodyType, int bodyIndex, Vec3 impulse, Vec3 contactPoint);
+void  SolvePositionConstraints(PhysicsWorld* world);
+
 #ifdef __cplusplus
 }
 #endif
