@@ -117,7 +117,7 @@ assert CONSTRAINT_DTYPE.itemsize == 104 and CONTACT_DTYPE.itemsize == 44
 
 SCENE_README, SCENE_BALLS, SCENE_MIXED, SCENE_SDF, SCENE_RLWORLD = 1, 2, 3, 4, 5
 SDF_NONE, SDF_PLANE_Y, SDF_WAVY_DET, SDF_WAVY_LIBM, SDF_SPHERE_IN = 0, 1, 2, 3, 4
-SYNC_COMPAT, SYNC_RESIDENT = 0, 1
+SYNC_COMPAT, SYNC_RESIDENT, SYNC_COMPAT_BODIES = 0, 1, 2
 DL_BODIES, DL_CONSTRAINTS = 1, 2
 SOLVER_EXACT, SOLVER_COLOURED, SOLVER_EXACT_FLOW = 0, 1, 2
 

@@ -806,17 +806,25 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
     if (steps <= 0) return 0;
     int rc;
     for (int w = 0; w < b->n_worlds; w++) b->worlds[w].pub.dt = dt;
-    if (b->sync_mode == BBX_SYNC_COMPAT) {
-        /* drop-in semantics: whatever the user wrote into the host arrays is what the step sees */
+    if (b->sync_mode == BBX_SYNC_COMPAT || b->sync_mode == BBX_SYNC_COMPAT_BODIES) {
+        /* drop-in semantics: whatever the user wrote into the host arrays is what the step sees.
+         * COMPAT_BODIES leaves the constraint list on the device (it is 6x the size of the body state at
+         * 6 contacts per body): world->constraints->count is 0 until BallboxDownload(BBX_DL_CONSTRAINTS). */
+        const int full = b->sync_mode == BBX_SYNC_COMPAT;
         for (int s = 0; s < steps; s++) {
             BbxStepParams prm;
             if ((rc = batch_upload(b))) return rc;
-            if ((rc = fill_params(b, dt, 1, 0, &prm))) return rc;      /* compat replays from the downloaded list */
+            /* the full mode replays callbacks from the downloaded list, the other one from device-side events */
+            if ((rc = fill_params(b, dt, 1, (!full && b->n_callbacks > 0) ? 1 : 0, &prm))) return rc;
             if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, 1)))) return rc;
-            if ((rc = batch_download(b, BBX_DL_BODIES | BBX_DL_CONSTRAINTS))) return rc;
+            if ((rc = batch_download(b, full ? (BBX_DL_BODIES | BBX_DL_CONSTRAINTS) : BBX_DL_BODIES))) return rc;
             zero_host_forces(b);
             for (int w = 0; w < b->n_worlds; w++) b->worlds[w].collisions.count = 0;       /* ballbox.h:2310 */
-            if (b->n_callbacks > 0) for (int w = 0; w < b->n_worlds; w++) replay_callbacks(&b->worlds[w]);
+            if (!full) for (int w = 0; w < b->n_worlds; w++) b->worlds[w].constraints.count = 0;
+            if (b->n_callbacks > 0) {
+                if (full) for (int w = 0; w < b->n_worlds; w++) replay_callbacks(&b->worlds[w]);
+                else if ((rc = replay_events(b))) return rc;
+            }
         }
         return 0;
     }

@@ -226,9 +226,22 @@ def run_e2e(res, steps):
     el = time.perf_counter() - t0
     ns, nb, C = res["ns"], res["nb"], len(w.constraints())
     h2d = ns * (12 * 5 + 4 * 4 + 2) + nb * (12 * 7 + 16 + 4 * 2 + 2)
-    d2h = ns * (12 * 3 + 4 + 1) + nb * (12 * 3 + 16 + 4 + 1) + C * 104
-    return {"value": res["bodies"] * steps / el, "unit": "body-steps/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": el / steps * 1e3}
+    d2h_bodies = ns * (12 * 3 + 4 + 1) + nb * (12 * 3 + 16 + 4 + 1)
+    d2h = d2h_bodies + C * 104
+    out = {"value": res["bodies"] * steps / el, "unit": "body-steps/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": el / steps * 1e3,
+           "mode": "BBX_SYNC_COMPAT (default drop-in: bodies up, bodies + world->constraints down, every step)"}
+    # the same call when the user opts out of the per-step constraint-list download (ballbox_ext.h)
+    w.set_sync_mode(bb.SYNC_COMPAT_BODIES)
+    w.step(DT)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.step(DT)
+    el2 = time.perf_counter() - t0
+    out["bodies_only"] = {"value": res["bodies"] * steps / el2, "unit": "body-steps/s", "ms_per_step": el2 / steps * 1e3,
+                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_bodies),
+                          "mode": "BBX_SYNC_COMPAT_BODIES (constraint list stays on the device until asked for)"}
+    return out
 
 
 def run_c5(args, lib, torch, barrier, rank):

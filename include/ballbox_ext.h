@@ -15,6 +15,9 @@ extern "C" {
 /* ---- residency ------------------------------------------------------------ */
 #define BBX_SYNC_COMPAT    0   /* default: upload / step / download in every PhysicsStep   */
 #define BBX_SYNC_RESIDENT  1   /* state stays in HBM; host arrays move only on request     */
+#define BBX_SYNC_COMPAT_BODIES 2 /* like COMPAT, but world->constraints stays on the device
+                                  (count 0) until BallboxDownload(world, BBX_DL_CONSTRAINTS):
+                                  the list is ~6x the body state; callbacks still fire        */
 
 #define BBX_DL_BODIES       1  /* positions, rotations, velocities, sleep state            */
 #define BBX_DL_CONSTRAINTS  2  /* world->constraints in the reference's emission order     */

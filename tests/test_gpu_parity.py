@@ -533,3 +533,27 @@ def test_flow_schedule_batch_and_single_iteration(product, truth):
         g.step(DT); t.step(DT)
         mm = parity.compare_worlds(g, t)
         assert not mm, f"step {s_}: {mm[:3]}"
+
+
+def test_compat_bodies_mode_matches_full_compat(product, truth):
+    """BBX_SYNC_COMPAT_BODIES: the drop-in call without the per-step download of the constraint list.  Bodies,
+    callbacks and (on request) the constraint list are the ones of the full mode, i.e. of the reference."""
+    logs = []
+    worlds = []
+    for lib, mode in ((product, bb.SYNC_COMPAT_BODIES), (truth, None)):
+        w = lib.build_scene(bb.SCENE_MIXED, 500, 71)
+        if mode is not None:
+            w.set_sync_mode(mode)
+        log = []
+        for i in range(0, 40, 3):
+            w.set_sphere_callback(i, lambda s, t, o, c, log=log: log.append(("s", s, t, o, round(c.contents.penetration, 7))))
+            w.set_box_callback(i, lambda s, t, o, c, log=log: log.append(("b", s, t, o, round(c.contents.penetration, 7))))
+        logs.append(log); worlds.append(w)
+    g, c = worlds
+    for s in range(30):
+        g.step(DT); c.step(DT)
+        assert not parity.compare_worlds(g, c, constraints=False), f"step {s}"
+        assert g.w.constraints.contents.count == 0
+    assert logs[0] == logs[1] and len(logs[0]) > 10
+    g.download(bb.DL_CONSTRAINTS)
+    assert not parity.compare_worlds(g, c)
