@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_frontier0(BbxDev dv)
 // ---------------------------------------------------------------------------
 // K11 velocity solve
 // ---------------------------------------------------------------------------
-struct SolveParams { float restitution, friction, vel_threshold; int iterations; int gather; };
+struct SolveParams { float restitution, friction, vel_threshold; int iterations; int gather; int first_only; };
 
 struct BodyState {
     float3 v, w;
@@ -564,7 +564,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     __shared__ int lc_cache[LC_CACHE * BBX_NCLS];
     for (int i = threadIdx.x; i < min(n_levels, LC_CACHE) * BBX_NCLS; i += blockDim.x) lc_cache[i] = __ldcg(&lc[i]);
     __syncthreads();
-    for (int it = 1; it < sp.iterations; it++) {
+    // (with first_only the later iterations run in k_replay_pairs, two lanes per node)
+    for (int it = 1; it < (sp.first_only ? 1 : sp.iterations); it++) {
         for (int l = 0; l < n_levels; l++) {
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -897,6 +898,82 @@ __global__ void __launch_bounds__(FLOW_THREADS, FLOW_BLOCKS_PER_SM) k_solve_flow
         atomicMax(&dv.level_ns[FLOW_DBG + 7], ns);
     }
     atomicAdd(&dv.level_ns[FLOW_DBG + 3], dbg_fail);
+}
+
+// ---------------------------------------------------------------------------
+// Replay of the level-major order with TWO LANES PER NODE (iterations 1..I-1 of k_solve_levels)
+//
+// The even lane of a pair holds body A, the odd lane body B (solve_half): a node's sweep is half as
+// deep, a thread holds one body instead of two (64-72 registers instead of 115, twice the warps per
+// SM), and the per-level time, which is a chain of [gather, ~700 dependent instructions per
+// constraint, scatter] behind a grid barrier, shrinks accordingly.  Same level order, same per-body
+// constraint order, same operations per body: bit-identical to the one-lane sweep.
+// ---------------------------------------------------------------------------
+#define RP_THREADS 256
+#define RP_BLOCKS_PER_SM 4
+
+__global__ void __launch_bounds__(RP_THREADS, RP_BLOCKS_PER_SM) k_replay_pairs(BbxDev dv, SolveParams sp)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_head[BBX_NCLS], s_cnt[BBX_NCLS], s_pref[BBX_NCLS + 1];
+    __shared__ int lc_cache[LC_CACHE * BBX_NCLS];
+    const int n_levels = dv.ctr->n_levels;
+    const int* lc = dv.level_count;
+    for (int i = threadIdx.x; i < min(n_levels, LC_CACHE) * BBX_NCLS; i += blockDim.x) lc_cache[i] = lc[i];
+    const int lane = threadIdx.x & 31;
+    const bool side = lane & 1;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp0 = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;      // consecutive chunks go to different SMs
+    const int W = gridDim.x * warps_per_block;
+    const size_t PL = (size_t)dv.cap_contacts;
+    __syncthreads();
+    for (int it = 1; it < sp.iterations; it++) {
+        for (int l = 0; l < n_levels; l++) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int run = 0;
+                for (int k = 0; k < BBX_NCLS; k++) {
+                    if (l == 0) s_head[k] = 0; else s_head[k] += s_cnt[k];
+                    s_cnt[k] = (l < LC_CACHE) ? lc_cache[l * BBX_NCLS + k] : __ldcg(&lc[l * BBX_NCLS + k]);
+                    s_pref[k] = run;
+                    run += (s_cnt[k] + 15) >> 4;                      // 16 nodes per warp
+                }
+                s_pref[BBX_NCLS] = run;
+            }
+            __syncthreads();
+            const int total = s_pref[BBX_NCLS];
+            for (int ch = warp0; ch < total; ch += W) {
+                int k = 0;
+                #pragma unroll
+                for (int kk = 1; kk < BBX_NCLS; kk++) if (ch >= s_pref[kk]) k = kk;
+                const int idx = (ch - s_pref[k]) * 16 + (lane >> 1);
+                const bool live = idx < s_cnt[k];
+                int4 nd = make_int4(0, 0, -1, -1);
+                if (live) nd = __ldcg(&dv.Nd_k[k][s_head[k] + idx]);       // (first M slot, constraints, gid A, gid B)
+                const int m = live ? nd.y : 0;
+                const int g = side ? nd.w : nd.z;
+                const bool has = live && g >= 0;
+                BodyState S;
+                S.box = false;
+                if (has) load_body(dv, g, S);
+                int mmax = m;
+                for (int o = 16; o > 0; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+                float4* M = dv.M + (size_t)nd.x;
+                for (int j = 0; j < mmax; j++) {
+                    const bool on = j < m;
+                    const unsigned int msk = __ballot_sync(0xffffffffu, on);
+                    if (on) {
+                        float4 c0 = __ldcg(M + j), c1 = __ldcg(M + j + (side ? 2 * PL : PL)), c3 = __ldcg(M + j + 3 * PL);
+                        const float mN = __shfl_sync(msk, c1.w, lane & ~1), mT0 = __shfl_sync(msk, c1.w, lane | 1);
+                        solve_half(msk, side, has, c0, xyz(c1), mN, mT0, c3, S, sp);
+                        if (!side) __stcg(M + j + 3 * PL, c3);
+                    }
+                }
+                if (has) store_body(dv, g, S);
+            }
+            grid.sync();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1352,14 +1429,32 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         if (per_sm > SOLVE_BLOCKS_PER_SM) per_sm = SOLVE_BLOCKS_PER_SM;
         d->coop_blocks = per_sm * sms;
     }
+    if (d->rp_blocks == 0) {
+        int per_sm = 0, sms = 0;
+        BBX_CUDA(d, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
+        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_replay_pairs, RP_THREADS, 0));
+        if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "replay kernel does not fit on an SM", __FILE__, __LINE__);
+        if (per_sm > RP_BLOCKS_PER_SM) per_sm = RP_BLOCKS_PER_SM;
+        d->rp_blocks = per_sm * sms;
+        // measured neutral at 1M bodies (5.55 vs 5.48 ms: the fat levels are bound by their DRAM bursts, not by the
+        // depth of the sweep; profiles/r01_notes.md), so the one-lane replay stays the default
+        { const char* e = getenv("BBX_REPLAY_PAIRS"); d->no_pairs = (e && e[0] == '1') ? 0 : 1; }
+        { const char* e = getenv("BBX_REPLAY_BLOCKS"); if (e && atoi(e) > 0 && atoi(e) < d->rp_blocks) d->rp_blocks = atoi(e); }
+    }
     bbx_timing_mark(d, 4);
     SolveParams sp;
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;
-    sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = iterations;
+    sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = iterations; sp.gather = 0;
+    // iteration 0 (level discovery) on one lane per node; the later iterations with two lanes per node
+    sp.first_only = (iterations > 1 && !d->no_pairs) ? 1 : 0;
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
     BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
     d->launches++;
+    if (sp.first_only) {
+        BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_replay_pairs, dim3(d->rp_blocks), dim3(RP_THREADS), args, 0, d->stream));
+        d->launches++;
+    }
     BBX_CUDA(d, cudaGetLastError());
     return 0;
 }
