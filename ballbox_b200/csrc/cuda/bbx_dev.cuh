@@ -141,7 +141,7 @@ struct BbxDev {
     int last_per_contact;                        // the last solve used one node per constraint (layout of `node`)
     int last_flow;                               // the last solve ran on the flow solver (impulses live in fimp)
     int flow_blocks;                             // co-resident blocks of k_solve_flow
-    int rp_blocks, no_pairs;                     // co-resident blocks of k_replay_pairs; BBX_REPLAY_PAIRS=0 keeps one lane per node
+    int rp_blocks, replay_mode;                  // co-resident blocks of k_replay_pairs; BBX_REPLAY=2 selects it
     int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
     int no_groups;                               // BBX_WORLD_GROUPS=0: batched worlds use the warp-per-world kernel (A/B measurements)
     int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)

@@ -901,16 +901,17 @@ __global__ void __launch_bounds__(FLOW_THREADS, FLOW_BLOCKS_PER_SM) k_solve_flow
 }
 
 // ---------------------------------------------------------------------------
-// Replay of the level-major order with TWO LANES PER NODE (iterations 1..I-1 of k_solve_levels)
+// Replay of the level-major order with TWO LANES PER NODE (iterations 1..I-1 of k_solve_levels; opt-in,
+// BBX_REPLAY=2: measured equal to the one-lane replay, kept as the base for further work)
 //
 // The even lane of a pair holds body A, the odd lane body B (solve_half): a node's sweep is half as
-// deep, a thread holds one body instead of two (64-72 registers instead of 115, twice the warps per
-// SM), and the per-level time, which is a chain of [gather, ~700 dependent instructions per
-// constraint, scatter] behind a grid barrier, shrinks accordingly.  Same level order, same per-body
-// constraint order, same operations per body: bit-identical to the one-lane sweep.
+// deep and a thread holds one body instead of two, which leaves registers to software-pipeline the
+// warp's chunks of a level (next chunk's gather in flight during the current sweep).  Same level
+// order, same per-body constraint order, same operations per body: bit-identical to the one-lane sweep.
 // ---------------------------------------------------------------------------
 #define RP_THREADS 256
-#define RP_BLOCKS_PER_SM 4
+#define RP_BLOCKS_PER_SM 2
+struct PairRaw { F8 vw, qi; float4 c0, c1, c3; };
 
 __global__ void __launch_bounds__(RP_THREADS, RP_BLOCKS_PER_SM) k_replay_pairs(BbxDev dv, SolveParams sp)
 {
@@ -922,54 +923,104 @@ __global__ void __launch_bounds__(RP_THREADS, RP_BLOCKS_PER_SM) k_replay_pairs(B
     for (int i = threadIdx.x; i < min(n_levels, LC_CACHE) * BBX_NCLS; i += blockDim.x) lc_cache[i] = lc[i];
     const int lane = threadIdx.x & 31;
     const bool side = lane & 1;
-    const int warps_per_block = blockDim.x >> 5;
-    const int warp0 = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;      // consecutive chunks go to different SMs
-    const int W = gridDim.x * warps_per_block;
     const size_t PL = (size_t)dv.cap_contacts;
+    // WORK DISTRIBUTION.  Chunks of different classes cost 1..8 sweeps, so dealing them round-robin leaves most
+    // warps waiting at the barrier for the few that drew the long ones (ncu: half of all stall samples; a global
+    // ticket counter balances perfectly but its atomics cost more than they save: 6.2 vs 5.5 ms).  Static instead:
+    // the level's chunks are ordered from the longest class to the shortest and dealt in boustrophedon order
+    // (round 0: warp 0..W-1, round 1: warp W-1..0, ...), so the warp that drew the longest chunk of one round
+    // draws the shortest of the next.
+    const int warp0 = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;      // consecutive chunks go to different SMs
+    const int W = gridDim.x * (blockDim.x >> 5);
     __syncthreads();
     for (int it = 1; it < sp.iterations; it++) {
         for (int l = 0; l < n_levels; l++) {
             __syncthreads();
             if (threadIdx.x == 0) {
-                int run = 0;
+                // flattened chunk order of the level: classes from long to short runs (pref indexed by class)
                 for (int k = 0; k < BBX_NCLS; k++) {
                     if (l == 0) s_head[k] = 0; else s_head[k] += s_cnt[k];
                     s_cnt[k] = (l < LC_CACHE) ? lc_cache[l * BBX_NCLS + k] : __ldcg(&lc[l * BBX_NCLS + k]);
-                    s_pref[k] = run;
-                    run += (s_cnt[k] + 15) >> 4;                      // 16 nodes per warp
                 }
+                int run = 0;
+                for (int k = BBX_NCLS - 1; k >= 0; k--) { s_pref[k] = run; run += (s_cnt[k] + 15) >> 4; }     // 16 nodes per warp
                 s_pref[BBX_NCLS] = run;
             }
             __syncthreads();
             const int total = s_pref[BBX_NCLS];
-            for (int ch = warp0; ch < total; ch += W) {
-                int k = 0;
+            const bool trace = (it == 1 && l == sp.gather && sp.gather > 0);       // debug: per-warp time inside one level
+            unsigned long long t_in = 0; int my_chunks = 0;
+            if (trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_in));
+            // SOFTWARE PIPELINE over the warp's chunks of this level (they are independent of each other): while
+            // chunk r is swept, the body, box constants and first record of chunk r+1 and the descriptor of chunk
+            // r+2 are in flight, so only the first chunk of a level pays the gather latency.
+            const int rounds = (total + W - 1) / W;
+            auto desc_of = [&](int r) -> int4 {                  // (first M slot, constraints, gid A, gid B), m = 0 if none
+                if (r >= rounds) return make_int4(0, 0, -1, -1);
+                const int ch = r * W + ((r & 1) ? W - 1 - warp0 : warp0);
+                if (ch >= total) return make_int4(0, 0, -1, -1);
+                int k = BBX_NCLS - 1;
                 #pragma unroll
-                for (int kk = 1; kk < BBX_NCLS; kk++) if (ch >= s_pref[kk]) k = kk;
+                for (int kk = BBX_NCLS - 2; kk >= 0; kk--) if (ch >= s_pref[kk]) k = kk;
                 const int idx = (ch - s_pref[k]) * 16 + (lane >> 1);
-                const bool live = idx < s_cnt[k];
-                int4 nd = make_int4(0, 0, -1, -1);
-                if (live) nd = __ldcg(&dv.Nd_k[k][s_head[k] + idx]);       // (first M slot, constraints, gid A, gid B)
-                const int m = live ? nd.y : 0;
+                if (idx >= s_cnt[k]) return make_int4(0, 0, -1, -1);
+                return __ldcg(&dv.Nd_k[k][s_head[k] + idx]);
+            };
+            auto raw_of = [&](const int4& nd, PairRaw& o) {
+                if (nd.y <= 0) return;
                 const int g = side ? nd.w : nd.z;
-                const bool has = live && g >= 0;
+                const float4* M = dv.M + (size_t)nd.x;
+                o.c0 = __ldcg(M); o.c1 = __ldcg(M + (side ? 2 * PL : PL)); o.c3 = __ldcg(M + 3 * PL);
+                if (g >= 0) { o.vw = ld256_cg(&dv.vel[2 * g]); if (g >= dv.NS) o.qi = ld256_nc(&dv.boxq[2 * (g - dv.NS)]); }
+            };
+            int4 nd0 = desc_of(0), nd1 = desc_of(1);
+            PairRaw raw0;
+            raw_of(nd0, raw0);
+            for (int r = 0; r < rounds; r++) {
+                const int4 nd2 = desc_of(r + 2);
+                PairRaw raw1;
+                raw_of(nd1, raw1);
+                const int m = nd0.y;
+                const int g = side ? nd0.w : nd0.z;
+                const bool has = m > 0 && g >= 0;
+                if (m > 0) my_chunks++;
                 BodyState S;
                 S.box = false;
-                if (has) load_body(dv, g, S);
+                if (has) {
+                    S.v = xyz(raw0.vw.a); S.w = xyz(raw0.vw.b); S.im = raw0.vw.a.w; S.ii = raw0.vw.b.w;
+                    S.box = g >= dv.NS;
+                    if (S.box) {
+                        S.q = raw0.qi.a; S.iI = xyz(raw0.qi.b);
+                        float3 u = f3(S.q.x, S.q.y, S.q.z);
+                        S.k1 = S.q.w * S.q.w - v3dot(u, u); S.k2 = 2.0f * S.q.w;
+                    }
+                }
                 int mmax = m;
                 for (int o = 16; o > 0; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
-                float4* M = dv.M + (size_t)nd.x;
+                float4* M = dv.M + (size_t)nd0.x;
+                float4 n0 = raw0.c0, n1 = raw0.c1, n3 = raw0.c3;
                 for (int j = 0; j < mmax; j++) {
                     const bool on = j < m;
                     const unsigned int msk = __ballot_sync(0xffffffffu, on);
                     if (on) {
-                        float4 c0 = __ldcg(M + j), c1 = __ldcg(M + j + (side ? 2 * PL : PL)), c3 = __ldcg(M + j + 3 * PL);
+                        float4 c0 = n0, c1 = n1, c3 = n3;
+                        if (j + 1 < m) { n0 = __ldcg(M + j + 1); n1 = __ldcg(M + j + 1 + (side ? 2 * PL : PL)); n3 = __ldcg(M + j + 1 + 3 * PL); }
                         const float mN = __shfl_sync(msk, c1.w, lane & ~1), mT0 = __shfl_sync(msk, c1.w, lane | 1);
                         solve_half(msk, side, has, c0, xyz(c1), mN, mT0, c3, S, sp);
                         if (!side) __stcg(M + j + 3 * PL, c3);
                     }
                 }
                 if (has) store_body(dv, g, S);
+                nd0 = nd1; nd1 = nd2; raw0 = raw1;
+            }
+            if (trace && lane == 0) {
+                unsigned long long t_out; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_out));
+                unsigned long long d = t_out - t_in;
+                unsigned long long* o = dv.level_ns + FLOW_DBG;
+                atomicAdd(&o[0], d); atomicMax(&o[1], d); atomicAdd(&o[2], 1ull);
+                if (my_chunks == 1) { atomicAdd(&o[3], d); atomicAdd(&o[4], 1ull); }
+                else if (my_chunks == 2) { atomicAdd(&o[5], d); atomicAdd(&o[6], 1ull); }
+                else if (my_chunks >= 3) atomicAdd(&o[7], d);
             }
             grid.sync();
         }
@@ -1438,20 +1489,22 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         d->rp_blocks = per_sm * sms;
         // measured neutral at 1M bodies (5.55 vs 5.48 ms: the fat levels are bound by their DRAM bursts, not by the
         // depth of the sweep; profiles/r01_notes.md), so the one-lane replay stays the default
-        { const char* e = getenv("BBX_REPLAY_PAIRS"); d->no_pairs = (e && e[0] == '1') ? 0 : 1; }
+        // 0 (default): all iterations in k_solve_levels; 2: iterations 1..I-1 in k_replay_pairs (measured equal, 5.45 ms)
+        { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && atoi(e) == 2) ? 2 : 0; }
         { const char* e = getenv("BBX_REPLAY_BLOCKS"); if (e && atoi(e) > 0 && atoi(e) < d->rp_blocks) d->rp_blocks = atoi(e); }
     }
     bbx_timing_mark(d, 4);
     SolveParams sp;
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;
     sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = iterations; sp.gather = 0;
+    { const char* e = getenv("BBX_TRACE_LEVEL"); if (e) { sp.gather = atoi(e); cudaMemsetAsync(d->level_ns + FLOW_DBG, 0, 8 * sizeof(unsigned long long), d->stream); } }
     // iteration 0 (level discovery) on one lane per node; the later iterations with two lanes per node
-    sp.first_only = (iterations > 1 && !d->no_pairs) ? 1 : 0;
+    sp.first_only = (iterations > 1 && d->replay_mode != 0) ? 1 : 0;
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
     BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
     d->launches++;
-    if (sp.first_only) {
+    if (sp.first_only && d->replay_mode == 2) {
         BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_replay_pairs, dim3(d->rp_blocks), dim3(RP_THREADS), args, 0, d->stream));
         d->launches++;
     }
