@@ -244,6 +244,34 @@ def run_e2e(res, steps):
     return out
 
 
+def run_small_config(lib, torch, kind, n, settle, steps, label):
+    """Resident stepping of one of the other BASELINE configs (single world), CUDA events on the step stream."""
+    from ballbox_b200 import binding as bb
+    w = lib.build_scene(kind, n, 20261019)
+    w.set_sync_mode(bb.SYNC_RESIDENT)
+    lib.dll.BallboxSetDevice(w.ptr, torch.cuda.current_device())
+    stream = torch.cuda.current_stream()
+    w.set_stream(stream.cuda_stream)
+    w.upload()
+    done = 0
+    while done < settle:
+        k = min(50, settle - done); w.step_n(DT, k); w.synchronize(); done += k
+    w.set_stage_timing(True); w.stage_timing()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); w.step_n(DT, steps); e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    stages, covered = w.stage_timing()
+    st = w.stats()
+    bodies = st.spheres + st.boxes
+    out = {"workload": label, "value": bodies * steps / (ms * 1e-3), "unit": "body-steps/s", "ms_per_step": ms / steps,
+           "bodies": bodies, "contacts": st.contacts, "levels": st.levels, "settle_steps": settle,
+           "stages_ms_per_step": {k: round(v / max(covered, 1), 4) for k, v in stages.items()}}
+    w.destroy()
+    return out
+
+
 def run_c5(args, lib, torch, barrier, rank):
     """4096 independent 256-body worlds per GPU."""
     import ctypes as C
@@ -298,6 +326,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--skip-batched", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-others", action="store_true", help="do not time configs 2 and 4 (N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -377,6 +406,14 @@ def main():
                    "bodies_total": int(btot), "contacts_rank0": b["contacts"], "levels_rank0": b["levels"],
                    "launches": b["launches"], "scaling": "weak"}
 
+    others = None
+    if rank == 0 and world_size == 1 and not args.skip_others:
+        from ballbox_b200 import binding as bb
+        others = [run_small_config(lib, torch, bb.SCENE_BALLS, 100_000, 300, args.steps,
+                                   "c2_balls_in_a_box_100k_spheres_6_walls_restitution_0.3"),
+                  run_small_config(lib, torch, bb.SCENE_SDF, 200_000, 400, args.steps,
+                                   "c4_sdf_terrain_100k_spheres_100k_boxes_on_wavy_sdf_4_walls")]
+
     cpu = None
     if rank == 0 and world_size == 1 and not args.skip_cpu:
         cpu = cpu_sample(args.ref_bodies, args.cpu_steps)
@@ -393,6 +430,8 @@ def main():
                 "roofline": roofline, "e2e": e2e, "gpu_launches": r["launches"], "clocks": r["clocks"],
                 "stages_ms_per_step": r["stages_ms_per_step"], "batched_worlds": batched,
                 "setup": {"scene_build_s": r["build_s"], "settle_s": r["settle_s"]}}
+        if others:
+            line["other_configs"] = others
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
