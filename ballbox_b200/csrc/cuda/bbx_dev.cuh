@@ -142,6 +142,7 @@ struct BbxDev {
     int last_flow;                               // the last solve ran on the flow solver (impulses live in fimp)
     int flow_blocks;                             // co-resident blocks of k_solve_flow
     int rp_blocks, replay_mode;                  // co-resident blocks of k_replay_pairs; BBX_REPLAY=2 selects it
+    int tune_replay_blocks, tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_REPLAY_BLOCKS, BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL
     int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
     int no_groups;                               // BBX_WORLD_GROUPS=0: batched worlds use the warp-per-world kernel (A/B measurements)
     int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)

@@ -1406,13 +1406,13 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
             if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "flow solver kernel does not fit on an SM", __FILE__, __LINE__);
             if (per_sm > FLOW_BLOCKS_PER_SM) per_sm = FLOW_BLOCKS_PER_SM;
             d->flow_blocks = per_sm * sms;
-            { const char* e = getenv("BBX_FLOW_BLOCKS"); if (e && atoi(e) > 0 && atoi(e) < d->flow_blocks) d->flow_blocks = atoi(e); }
+            if (d->tune_flow_blocks > 0 && d->tune_flow_blocks < d->flow_blocks) d->flow_blocks = d->tune_flow_blocks;
         }
         bbx_timing_mark(d, 4);
         SolveParams spf;
         spf.restitution = p->settings.restitution; spf.friction = p->settings.friction;
         spf.vel_threshold = p->settings.velocity_threshold; spf.iterations = iterations;
-        { const char* e = getenv("BBX_FLOW_GATHER"); spf.gather = e ? atoi(e) : 0; }
+        spf.gather = d->tune_flow_gather;
         BbxDev dvf = *d;
         void* fargs[] = { (void*)&dvf, (void*)&spf };
         // cooperative launch: every block must be resident (the waits rely on it) and iteration 0 ends with a grid barrier
@@ -1490,14 +1490,13 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         // measured neutral at 1M bodies (5.55 vs 5.48 ms: the fat levels are bound by their DRAM bursts, not by the
         // depth of the sweep; profiles/r01_notes.md), so the one-lane replay stays the default
         // 0 (default): all iterations in k_solve_levels; 2: iterations 1..I-1 in k_replay_pairs (measured equal, 5.45 ms)
-        { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && atoi(e) == 2) ? 2 : 0; }
-        { const char* e = getenv("BBX_REPLAY_BLOCKS"); if (e && atoi(e) > 0 && atoi(e) < d->rp_blocks) d->rp_blocks = atoi(e); }
+        if (d->tune_replay_blocks > 0 && d->tune_replay_blocks < d->rp_blocks) d->rp_blocks = d->tune_replay_blocks;
     }
     bbx_timing_mark(d, 4);
     SolveParams sp;
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;
     sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = iterations; sp.gather = 0;
-    { const char* e = getenv("BBX_TRACE_LEVEL"); if (e) { sp.gather = atoi(e); cudaMemsetAsync(d->level_ns + FLOW_DBG, 0, 8 * sizeof(unsigned long long), d->stream); } }
+    if (d->trace_level > 0) { sp.gather = d->trace_level; BBX_CUDA(d, cudaMemsetAsync(d->level_ns + FLOW_DBG, 0, 8 * sizeof(unsigned long long), d->stream)); }
     // iteration 0 (level discovery) on one lane per node; the later iterations with two lanes per node
     sp.first_only = (iterations > 1 && d->replay_mode != 0) ? 1 : 0;
     BbxDev dv = *d;
