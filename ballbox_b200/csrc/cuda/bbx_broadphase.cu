@@ -298,12 +298,12 @@ __global__ void __launch_bounds__(128) k_find_pairs(BbxDev dv)
         int lc = c - w * g.cells_per_world;
         int cx = lc % g.nx, cy = (lc / g.nx) % g.ny, cz = lc / (g.nx * g.ny);
         int wbase = w * g.cells_per_world;
-        // own cell: partners later in the sorted order
-        {
-            int e = dv.cell_start[c + 1];
-            for (int q = p + 1; q < e; q++) fp_consider(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q], buf, nb);
-        }
-        // 13 forward neighbours: (dz,dy,dx) > (0,0,0) lexicographically
+        // Candidate runs of the sorted order: the rest of the own cell and the 13 forward neighbour cells
+        // ((dz,dy,dx) > (0,0,0) lexicographically; cells of one row are consecutive, so a row is one run).
+        // The runs are walked by ONE loop: the lanes of a warp then diverge only by their total candidate
+        // count, not by the length of every single run.
+        int rs[6], re[6], nr = 0;
+        rs[0] = p + 1; re[0] = dv.cell_start[c + 1]; nr = 1;
         for (int dz = 0; dz <= 1; dz++) {
             int z = cz + dz;
             if (z >= g.nz) continue;
@@ -316,8 +316,16 @@ __global__ void __launch_bounds__(128) k_find_pairs(BbxDev dv)
                 if (x1 >= g.nx) x1 = g.nx - 1;
                 if (x0 > x1) continue;
                 int row = wbase + (z * g.ny + y) * g.nx;
-                int s = dv.cell_start[row + x0], e = dv.cell_start[row + x1 + 1];   // consecutive cells: one run
-                for (int q = s; q < e; q++) fp_consider(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q], buf, nb);
+                rs[nr] = dv.cell_start[row + x0]; re[nr] = dv.cell_start[row + x1 + 1]; nr++;
+            }
+        }
+        {
+            int r = 0, q = rs[0], e = re[0];
+            while (true) {
+                while (q >= e) { if (++r >= nr) break; q = rs[r]; e = re[r]; }
+                if (r >= nr) break;
+                fp_consider(dv, i, pi, dv.sorted_id[q], dv.sorted_pos[q], buf, nb);
+                q++;
             }
         }
         // big bodies of this world
