@@ -60,7 +60,7 @@ struct StepCounters {
     int n_events;
     int n_mslots;            // M slots handed out (level-major constraint order)
     int n_nodes;             // solver nodes (runs of contacts between the same two bodies)
-    int n_hit_bb;            // box-box candidates that passed SAT
+    int n_hit_bb;            // box-box candidates that passed SAT with a FACE axis (stored from the front of hit_ids)
     int fq_tail;             // flow solver: entries pushed to the ready queue
     int fq_head;             // flow solver: chunk tickets handed out in iteration 0
     unsigned int bounds[6];  // ordered-int encoded min xyz / max xyz of small bodies
@@ -68,7 +68,8 @@ struct StepCounters {
     unsigned int cut_all;    // float bits: largest bounding radius among all bodies
     int n_big;
     int fq_ticket;           // flow solver: chunk tickets handed out in iterations 1..I-1
-    int pad2[4];
+    int n_hit_bb_edge;       // ... with an EDGE-EDGE axis (stored from the back of hit_ids)
+    int pad2[3];
 };
 
 struct BbxDev {

@@ -180,7 +180,8 @@ static __host__ __device__ __noinline__ float3 closest_point_between_edges(const
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
             float d = sq_dist_edges(v1[0], v3add(v1[0], e1[i]), v2[0], v3add(v2[0], e2[j]));
-            if (d < mind) { mind = d; cp = v3scale(v3add(o1.c, o2.c), 0.5f); }
+            // the first pair closer than 999999 fixes the result (later pairs can only assign the same midpoint)
+            if (d < mind) return v3scale(v3add(o1.c, o2.c), 0.5f);
         }
     return cp;
 }

@@ -59,8 +59,14 @@ __global__ void __launch_bounds__(256) k_bb_sat(BbxDev dv)
             Obb B = make_obb(xyz(dv.pos[pr.y]), xyz(dv.half[b]), dv.boxq[2 * b]);
             hit = sat_axes(A, B, minPd, ax, axisType);
         }
-        int slot = warp_reserve(&dv.ctr->n_hit_bb, hit ? 1 : 0);
+        // face-axis hits (contact point from 96 vertex/face tests) and edge-axis hits (contact point = midpoint of
+        // the centres) cost 5:1 in pass 2: they are kept apart, from the front and from the back of the hit list,
+        // so that the warps of pass 2 are homogeneous
+        const bool face = hit && axisType <= 5, edge = hit && axisType > 5;
+        int slot_f = warp_reserve(&dv.ctr->n_hit_bb, face ? 1 : 0);
+        int slot_e = warp_reserve(&dv.ctr->n_hit_bb_edge, edge ? 1 : 0);
         if (hit) {                                             // capacity: hits <= candidates <= cap_cand
+            int slot = face ? slot_f : dv.cap_cand - 1 - slot_e;
             dv.hit_ids[slot] = make_int4(pr.x, pr.y, axisType, 0);
             dv.hit_ax[slot] = make_float4(ax.x, ax.y, ax.z, fabsf(minPd));
         }
@@ -70,15 +76,16 @@ __global__ void __launch_bounds__(256) k_bb_sat(BbxDev dv)
 // Pass 2: contact point, manifold candidates and point selection for colliding pairs only.
 __global__ void __launch_bounds__(128) k_bb_manifold(BbxDev dv, float tol, float pen_tol, int max_contacts)
 {
-    int n = min(dv.ctr->n_hit_bb, dv.cap_cand);
-    int n_round = (n + 31) & ~31;
+    const int nf = dv.ctr->n_hit_bb, ne = dv.ctr->n_hit_bb_edge;          // nf + ne <= cap_cand by construction
+    const int nf_round = (nf + 31) & ~31, n_round = nf_round + ((ne + 31) & ~31);
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
         int np = 0;
         float3 pts[8]; float pens[8]; float3 normal = f3(0, 0, 0);
         int4 h = make_int4(0, 0, 0, 0);
-        if (t < n) {
-            h = dv.hit_ids[t];
-            float4 ax = dv.hit_ax[t];
+        const int src = t < nf_round ? (t < nf ? t : -1) : (t - nf_round < ne ? dv.cap_cand - 1 - (t - nf_round) : -1);
+        if (src >= 0) {
+            h = dv.hit_ids[src];
+            float4 ax = dv.hit_ax[src];
             normal = xyz(ax);
             int a = h.x - dv.NS, b = h.y - dv.NS;
             np = box_box_manifold(xyz(dv.pos[h.x]), xyz(dv.half[a]), dv.boxq[2 * a], xyz(dv.pos[h.y]), xyz(dv.half[b]),
