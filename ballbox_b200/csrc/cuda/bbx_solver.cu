@@ -168,12 +168,12 @@ __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int order, int per_
             if (l.x >= 0) {
                 int slot = atomicAdd(&dv.adj_cursor[l.x], 1);
                 unsigned int key = order == 2 ? (unsigned int)c : (body_order_key(dv, id, true, 0) | (unsigned int)k);
-                dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;
+                dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;                       // side A
             }
             if (l.y >= 0) {
                 int slot = atomicAdd(&dv.adj_cursor[l.y], 1);
                 unsigned int key = order == 2 ? (unsigned int)c : (body_order_key(dv, id, false, 0) | (unsigned int)k);
-                dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;
+                dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c | 0x80000000u;         // side B
             }
             continue;
         }
@@ -187,13 +187,47 @@ __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int order, int per_
         if (l.y >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.y], 1);
             unsigned int key = order == 1 ? coloured_key(id, l.w) : (order == 2 ? (((unsigned int)c << 3) | (unsigned int)l.w) : body_order_key(dv, id, false, l.w));
-            dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c;
+            dv.adj[slot] = ((unsigned long long)key << 32) | (unsigned int)c | 0x80000000u;             // side B
         }
     }
 }
 
 __device__ __forceinline__ void flow_init_body(const BbxDev& dv, int g);
 __device__ __forceinline__ void wake_body(const BbxDev& dv, int g);
+
+// One thread per body: sort the body's node list into chain order and write the successor links.  An entry is
+// (order key << 32) | side << 31 | node (side 0: the body is A of the node, 1: B), so that no node record has to be
+// read back.  Lists of up to ADJ_LOCAL entries are sorted in a thread-private array (all entries are requested at
+// once); longer ones (a big dynamic body) in place in global memory.
+#define ADJ_LOCAL 24
+#define ADJ_NODE(e) ((int)((unsigned int)(e) & 0x7fffffffu))
+#define ADJ_SIDE(e) ((int)(((unsigned int)(e)) >> 31))
+
+__device__ __forceinline__ bool adj_after(const BbxDev& dv, unsigned long long a, unsigned long long v)
+{
+    // a sorts after v?  Equal 32-bit keys can only happen in the coloured schedule (hash collision): fall back to the
+    // deterministic total order so that the result never depends on the contact numbering
+    return (a >> 32) > (v >> 32) || ((a >> 32) == (v >> 32) && node_before(dv, ADJ_NODE(v), ADJ_NODE(a)));
+}
+
+__device__ __forceinline__ void adj_write_links(const BbxDev& dv, int x, const unsigned long long* lst, int d, int per_contact)
+{
+    if (per_contact) {
+        // (position, length) and successor of every constraint in this body's chain
+        for (int i = 0; i < d; i++) {
+            const int cur = ADJ_NODE(lst[i]);
+            const int nxt = (i + 1 < d) ? ADJ_NODE(lst[i + 1]) : -1;
+            dv.node[2 * (size_t)cur + ADJ_SIDE(lst[i])] = make_int4(x, i, d, nxt);
+        }
+    } else {
+        for (int i = 1; i < d; i++) {
+            const unsigned long long e2 = lst[i];
+            const int link = ADJ_NODE(e2) | ((int)((e2 >> 32) & 7u) << 28);          // successor id | its class
+            int* nx = (int*)&dv.node[2 * (size_t)ADJ_NODE(lst[i - 1]) + 1];
+            nx[ADJ_SIDE(lst[i - 1])] = link;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, int flow_records)
 {
@@ -205,39 +239,30 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
         has = d > 0;
         if (has) {
             unsigned long long* lst = dv.adj + s;
-            // insertion sort: lists are short (a body touches a handful of neighbours)
-            for (int i = 1; i < d; i++) {
-                unsigned long long v = lst[i];
-                int j = i - 1;
-                // equal 32-bit keys can only happen in the coloured schedule (hash collision): fall back to
-                // the deterministic total order so that the result never depends on the contact numbering
-                while (j >= 0 && ((lst[j] >> 32) > (v >> 32) ||
-                                  ((lst[j] >> 32) == (v >> 32) && node_before(dv, (int)(unsigned int)v, (int)(unsigned int)lst[j])))) {
-                    lst[j + 1] = lst[j]; j--;
+            if (d <= ADJ_LOCAL) {
+                unsigned long long loc[ADJ_LOCAL];
+                for (int i = 0; i < d; i++) loc[i] = lst[i];
+                for (int i = 1; i < d; i++) {                      // insertion sort: lists are short
+                    unsigned long long v = loc[i];
+                    int j = i - 1;
+                    while (j >= 0 && adj_after(dv, loc[j], v)) { loc[j + 1] = loc[j]; j--; }
+                    loc[j + 1] = v;
                 }
-                lst[j + 1] = v;
+                atomicSub(&dv.indeg[ADJ_NODE(loc[0])], 1);         // first node of this body has no predecessor here
+                adj_write_links(dv, x, loc, d, per_contact);
+            } else {
+                for (int i = 1; i < d; i++) {
+                    unsigned long long v = lst[i];
+                    int j = i - 1;
+                    while (j >= 0 && adj_after(dv, lst[j], v)) { lst[j + 1] = lst[j]; j--; }
+                    lst[j + 1] = v;
+                }
+                atomicSub(&dv.indeg[ADJ_NODE(lst[0])], 1);
+                adj_write_links(dv, x, lst, d, per_contact);
             }
-            int prev = (int)(unsigned int)lst[0];
-            atomicSub(&dv.indeg[prev], 1);                 // first node of this body has no predecessor here
             if (per_contact) {
-                // successor links and (position, length) of every constraint in this body's chain; the body's
-                // versioned record starts at version 0
-                for (int i = 0; i < d; i++) {
-                    int cur = (int)(unsigned int)lst[i];
-                    int nxt = (i + 1 < d) ? (int)(unsigned int)lst[i + 1] : -1;
-                    int4* nd = &dv.node[2 * (size_t)cur];
-                    if (nd[0].x == x) nd[0] = make_int4(x, i, d, nxt); else nd[1] = make_int4(x, i, d, nxt);
-                }
-                if (flow_records) flow_init_body(dv, x);
+                if (flow_records) flow_init_body(dv, x);           // the body's versioned record starts at version 0
                 wake_body(dv, x);          // :1373-1376, :1402-1405: every impulse application wakes the body, even a zero one
-            } else
-            for (int i = 1; i < d; i++) {
-                unsigned long long e2 = lst[i];
-                int cur = (int)(unsigned int)e2;
-                int link = cur | ((int)((e2 >> 32) & 7u) << 28);          // successor id | its class
-                int* nx = (int*)&dv.node[2 * (size_t)prev + 1];
-                if (dv.node[2 * (size_t)prev].x == x) nx[0] = link; else nx[1] = link;
-                prev = cur;
             }
         }
     }
