@@ -260,10 +260,8 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                 atomicSub(&dv.indeg[ADJ_NODE(lst[0])], 1);
                 adj_write_links(dv, x, lst, d, per_contact);
             }
-            if (per_contact) {
-                if (flow_records) flow_init_body(dv, x);           // the body's versioned record starts at version 0
-                wake_body(dv, x);          // :1373-1376, :1402-1405: every impulse application wakes the body, even a zero one
-            }
+            if (per_contact && flow_records) flow_init_body(dv, x);    // the body's versioned record starts at version 0
+            wake_body(dv, x);              // :1373-1376, :1402-1405: every impulse application wakes the body, even a zero one
         }
     }
     unsigned int m = __ballot_sync(0xffffffffu, has);
@@ -303,7 +301,7 @@ __global__ void __launch_bounds__(256) k_frontier0(BbxDev dv)
 // ---------------------------------------------------------------------------
 // K11 velocity solve
 // ---------------------------------------------------------------------------
-struct SolveParams { float restitution, friction, vel_threshold; int iterations; int gather; int first_only; };
+struct SolveParams { float restitution, friction, vel_threshold; int iterations; int gather; int first_only; int levels_known; };
 
 struct BodyState {
     float3 v, w;
@@ -507,6 +505,73 @@ __device__ __forceinline__ void push_successor(const BbxDev& dv, int* lc_next, c
     dv.queue_k[cls][lm.head[cls] + lm.cnt[cls] + slot] = node;
 }
 
+// Level discovery WITHOUT the sweep (Kahn's algorithm on the successor links), at high occupancy: visits the
+// nodes level by level, hands out their level-major record slots, copies their records from contact order (L)
+// to the plane-major level order (M) and appends the successors that became ready.  The sweep of iteration 0
+// then is an ordinary replay.  Opt-in (BBX_FUSED_KAHN=0): measured equal at 1M bodies (this kernel 0.94 ms, the
+// solve kernel 0.91 ms shorter: a level of the discovery costs ~18 us with or without the sweep, it is the chain
+// queue -> node -> in-degree atomics -> class-queue append) and slower on the 100k-200k configs.
+#define KAHN_THREADS 256
+#define KAHN_BLOCKS_PER_SM 4
+
+__global__ void __launch_bounds__(KAHN_THREADS, KAHN_BLOCKS_PER_SM) k_kahn_levels(BbxDev dv)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ LevelMap lm;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    const int wtid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+    int* lc = dv.level_count;
+    const size_t PL = (size_t)dv.cap_contacts;
+    int lvl = 0;
+    if (threadIdx.x == 0) level_map_load(lm, lc, true);
+    __syncthreads();
+    while (lm.pref[BBX_NCLS] > 0) {
+        if (lvl + 2 >= dv.cap_levels) { if (tid == 0) atomicOr(&dv.ctr->overflow, 16); break; }
+        if (tid < BBX_NCLS) lc[(lvl + 2) * BBX_NCLS + tid] = 0;
+        int* lc_next = lc + (lvl + 1) * BBX_NCLS;
+        const int total = lm.pref[BBX_NCLS];
+        for (int t = wtid; t < total; t += stride) {
+            int k = 0;
+            #pragma unroll
+            for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
+            int idx = t - lm.pref[k];
+            bool live = idx < lm.cnt[k];
+            int p = lm.head[k] + idx;
+            int sa = -1, sb = -1, m = 0, c = 0;
+            int4 nd0 = make_int4(-1, -1, 0, 0);
+            if (live) {
+                c = __ldcg(&dv.queue_k[k][p]);
+                F8 rec = ld256_nc((const float4*)&dv.node[2 * (size_t)c]);       // ids, run length, successors: one sector
+                nd0 = make_int4(__float_as_int(rec.a.x), __float_as_int(rec.a.y), __float_as_int(rec.a.z), 0);
+                sa = __float_as_int(rec.b.x); sb = __float_as_int(rec.b.y);
+                m = nd0.z;
+                // the successors first: their readiness is what the next level waits for
+                if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) != 1) sa = -1;
+                if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) != 1) sb = -1;
+            }
+            push_successor(dv, lc_next, lm, sa);
+            push_successor(dv, lc_next, lm, sb);
+            int mbase = warp_reserve(&dv.ctr->n_mslots, m);
+            if (live) {
+                __stcg(&dv.Nd_k[k][p], make_int4(mbase, m, nd0.x, nd0.y));
+                const float4* L = dv.L + 4 * (size_t)c;
+                for (int j = 0; j < m; j++, L += 4) {
+                    F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+                    float4* M = dv.M + (size_t)(mbase + j);
+                    __stcg(M, lo.a); __stcg(M + PL, lo.b); __stcg(M + 2 * PL, hi.a); __stcg(M + 3 * PL, hi.b);
+                    dv.slot_of[c + j] = mbase + j;
+                }
+            }
+        }
+        grid.sync();
+        if (threadIdx.x == 0) level_map_load(lm, lc + (lvl + 1) * BBX_NCLS, false);
+        __syncthreads();
+        lvl++;
+    }
+    if (tid == 0) dv.ctr->n_levels = lvl;
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_levels(BbxDev dv, SolveParams sp)
 {
     cg::grid_group grid = cg::this_grid();
@@ -519,11 +584,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     int* lc = dv.level_count;                       // lc[level * BBX_NCLS + class]
     const size_t PL = (size_t)dv.cap_contacts;
 
-    // ---- iteration 0: discover levels (Kahn) while solving ----
+    // ---- iteration 0: discover levels (Kahn) while solving (only when k_kahn_levels has not run) ----
     int lvl = 0;
     if (threadIdx.x == 0) level_map_load(lm, lc, true);
     __syncthreads();
-    while (lm.pref[BBX_NCLS] > 0) {
+    while (!sp.levels_known && lm.pref[BBX_NCLS] > 0) {
         if (lvl + 2 >= dv.cap_levels) { if (tid == 0) atomicOr(&dv.ctr->overflow, 16); break; }
         if (tid < BBX_NCLS) lc[(lvl + 2) * BBX_NCLS + tid] = 0;
         int* lc_next = lc + (lvl + 1) * BBX_NCLS;
@@ -577,8 +642,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
         __syncthreads();
         lvl++;
     }
-    const int n_levels = lvl;
-    if (tid == 0) dv.ctr->n_levels = n_levels;
+    const int n_levels = sp.levels_known ? dv.ctr->n_levels : lvl;
+    if (tid == 0 && !sp.levels_known) dv.ctr->n_levels = n_levels;
     if (tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); dv.level_ns[4096 + 1] = ns; }
 
     // ---- iterations 1..I-1: stream the level-major records ----
@@ -590,7 +655,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     for (int i = threadIdx.x; i < min(n_levels, LC_CACHE) * BBX_NCLS; i += blockDim.x) lc_cache[i] = __ldcg(&lc[i]);
     __syncthreads();
     // (with first_only the later iterations run in k_replay_pairs, two lanes per node)
-    for (int it = 1; it < (sp.first_only ? 1 : sp.iterations); it++) {
+    for (int it = (sp.levels_known ? 0 : 1); it < (sp.first_only ? 1 : sp.iterations); it++) {
         for (int l = 0; l < n_levels; l++) {
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -958,7 +1023,7 @@ __global__ void __launch_bounds__(RP_THREADS, RP_BLOCKS_PER_SM) k_replay_pairs(B
     const int warp0 = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;      // consecutive chunks go to different SMs
     const int W = gridDim.x * (blockDim.x >> 5);
     __syncthreads();
-    for (int it = 1; it < sp.iterations; it++) {
+    for (int it = (sp.levels_known ? 0 : 1); it < sp.iterations; it++) {
         for (int l = 0; l < n_levels; l++) {
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -1517,18 +1582,35 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         // 0 (default): all iterations in k_solve_levels; 2: iterations 1..I-1 in k_replay_pairs (measured equal, 5.45 ms)
         if (d->tune_replay_blocks > 0 && d->tune_replay_blocks < d->rp_blocks) d->rp_blocks = d->tune_replay_blocks;
     }
-    bbx_timing_mark(d, 4);
+    if (d->kahn_blocks == 0) {
+        int per_sm = 0, sms = 0;
+        BBX_CUDA(d, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
+        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kahn_levels, KAHN_THREADS, 0));
+        if (per_sm > KAHN_BLOCKS_PER_SM) per_sm = KAHN_BLOCKS_PER_SM;
+        d->kahn_blocks = per_sm * sms;                 // 0: does not fit, the fused iteration 0 is used
+    }
     SolveParams sp;
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;
     sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = iterations; sp.gather = 0;
+    sp.levels_known = (d->kahn_blocks > 0 && !d->fused_kahn) ? 1 : 0;
+    if (sp.levels_known) {
+        BbxDev dvk = *d;
+        void* kargs[] = { (void*)&dvk };
+        BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_kahn_levels, dim3(d->kahn_blocks), dim3(KAHN_THREADS), kargs, 0, d->stream));
+        d->launches++;
+    }
+    bbx_timing_mark(d, 4);
     if (d->trace_level > 0) { sp.gather = d->trace_level; BBX_CUDA(d, cudaMemsetAsync(d->level_ns + FLOW_DBG, 0, 8 * sizeof(unsigned long long), d->stream)); }
     // iteration 0 (level discovery) on one lane per node; the later iterations with two lanes per node
-    sp.first_only = (iterations > 1 && d->replay_mode != 0) ? 1 : 0;
+    sp.first_only = (iterations > 1 && d->replay_mode != 0 && !sp.levels_known) ? 1 : 0;
+    const bool pairs_all = d->replay_mode == 2 && sp.levels_known;      // every sweep in k_replay_pairs
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
-    BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
-    d->launches++;
-    if (sp.first_only && d->replay_mode == 2) {
+    if (!pairs_all) {
+        BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
+        d->launches++;
+    }
+    if ((sp.first_only && d->replay_mode == 2) || pairs_all) {
         BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_replay_pairs, dim3(d->rp_blocks), dim3(RP_THREADS), args, 0, d->stream));
         d->launches++;
     }
