@@ -200,6 +200,7 @@ int  bbx_fail(BbxDev* d, int code, const char* what, const char* file, int line)
 static inline int bbx_blocks(long long n, int block) { long long b = (n + block - 1) / block; return (int)(b < 1 ? 1 : b); }
 
 void bbx_timing_mark(BbxDev* d, int mark);
+int  bbx_check_overflow(BbxDev* d);            // ctr_host must be current
 // stage entry points (one translation unit each)
 int bbx_stage_pack(BbxDev* d);
 int bbx_stage_unpack(BbxDev* d);

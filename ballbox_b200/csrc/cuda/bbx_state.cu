@@ -416,8 +416,9 @@ extern "C" int bbx_dev_download(BbxDev* d, const BbxHostBodies* hb)
     DN(hb->b_pos, d->r_b_pos, 12 * NB); DN(hb->b_vel, d->r_b_vel, 12 * NB); DN(hb->b_angvel, d->r_b_angvel, 12 * NB);
     DN(hb->b_rot, d->r_b_rot, 16 * NB); DN(hb->b_sleep, d->r_b_sleep, NB); DN(hb->b_timer, d->r_b_timer, 4 * NB);
 #undef DN
+    BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, s));
     BBX_CUDA(d, cudaStreamSynchronize(s));
-    return 0;
+    return bbx_check_overflow(d);                // state computed from a truncated contact list is not handed out silently
 }
 
 extern "C" int bbx_dev_stats(BbxDev* d, BallboxStats* out)

@@ -13,6 +13,18 @@ void bbx_timing_mark(BbxDev* d, int mark)
     cudaEventRecord(d->timing_ev[d->timing_steps * BBX_TIMING_MARKS + mark], d->stream);
 }
 
+// device-side failure flags of the steps so far (ctr_host must be current): a step that dropped contacts or could
+// not schedule its constraints has produced wrong state, which every download path reports instead of handing it out
+int bbx_check_overflow(BbxDev* d)
+{
+    const int f = d->ctr_host->overflow;
+    if (f & 3)  return bbx_fail(d, BBX_ERR_OVERFLOW, "contact or candidate buffer overflow: raise max_collisions", __FILE__, __LINE__);
+    if (f & 16) return bbx_fail(d, BBX_ERR_OVERFLOW, "solver dependency graph deeper than the level table", __FILE__, __LINE__);
+    if (f & 32) return bbx_fail(d, BBX_ERR_OVERFLOW, "batched worlds: a world's dependency graph or contact list exceeds the per-group tables", __FILE__, __LINE__);
+    if (f & 64) return bbx_fail(d, BBX_ERR_OVERFLOW, "flow solver gave up waiting for a predecessor (corrupt schedule)", __FILE__, __LINE__);
+    return 0;
+}
+
 extern "C" void bbx_dev_set_timing(BbxDev* d, int on)
 {
     if (!d) return;
@@ -292,12 +304,7 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
     BBX_CUDA(d, cudaGetLastError());
     BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
     BBX_CUDA(d, cudaStreamSynchronize(d->stream));
-    if (d->ctr_host->overflow & 3)
-        return bbx_fail(d, BBX_ERR_OVERFLOW, "contact or candidate buffer overflow: raise max_collisions", __FILE__, __LINE__);
-    if (d->ctr_host->overflow & 16)
-        return bbx_fail(d, BBX_ERR_OVERFLOW, "solver dependency graph deeper than the level table", __FILE__, __LINE__);
-    if (d->ctr_host->overflow & 64)
-        return bbx_fail(d, BBX_ERR_OVERFLOW, "flow solver gave up waiting for a predecessor (corrupt schedule)", __FILE__, __LINE__);
+    { int rco = bbx_check_overflow(d); if (rco) return rco; }
     int n = d->ctr_host->n_contacts;
     if (n > d->cap_contacts) n = d->cap_contacts;
     if (n == 0) return 0;
@@ -482,8 +489,7 @@ extern "C" int bbx_dev_download_contacts(BbxDev* d, CollisionContact* out, int c
     if (rc) return rc;
     BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
     BBX_CUDA(d, cudaStreamSynchronize(d->stream));
-    if (d->ctr_host->overflow & 3)
-        return bbx_fail(d, BBX_ERR_OVERFLOW, "contact or candidate buffer overflow: raise max_collisions", __FILE__, __LINE__);
+    { int rco = bbx_check_overflow(d); if (rco) return rco; }
     int n = d->ctr_host->n_contacts;
     if (n <= 0) return 0;
     KeyBits kb = key_bits_of(d);

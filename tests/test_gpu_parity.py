@@ -601,3 +601,13 @@ def test_full_size_batch_three_solvers_agree(product, monkeypatch):
         hashes.append((st.contacts, tuple(v.state_hash() for v in views)))
         d.DestroyPhysicsWorldBatch(batch)
     assert hashes[0] == hashes[1] == hashes[2] and hashes[0][0] > 1_000_000
+
+
+def test_overflow_is_reported_by_a_bodies_only_download(product):
+    """Resident stepping never looks at the host; a step that dropped contacts (max_collisions too small) must
+    still surface at the next download, also when only the bodies are fetched."""
+    w = product.build_scene(bb.SCENE_BALLS, 3000, 2, max_collisions=64)
+    w.set_sync_mode(bb.SYNC_RESIDENT)
+    w.step_n(DT, 5)
+    with pytest.raises(bb.BallboxError, match="overflow|max_collisions"):
+        w.download(bb.DL_BODIES)
