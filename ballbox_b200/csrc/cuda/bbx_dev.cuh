@@ -144,6 +144,7 @@ struct BbxDev {
     int flow_blocks;                             // co-resident blocks of k_solve_flow
     int kahn_blocks, fused_kahn;                 // co-resident blocks of k_kahn_levels; BBX_FUSED_KAHN=1: level discovery fused with sweep 0
     int rp_blocks, replay_mode;                  // co-resident blocks of k_replay_pairs; BBX_REPLAY=2 selects it
+    int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels
     int tune_replay_blocks, tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_REPLAY_BLOCKS, BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL
     int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
     int no_groups;                               // BBX_WORLD_GROUPS=0: batched worlds use the warp-per-world kernel (A/B measurements)

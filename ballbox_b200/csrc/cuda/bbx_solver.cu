@@ -1569,6 +1569,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "solver kernel does not fit on an SM", __FILE__, __LINE__);
         if (per_sm > SOLVE_BLOCKS_PER_SM) per_sm = SOLVE_BLOCKS_PER_SM;
         d->coop_blocks = per_sm * sms;
+        if (d->tune_solve_blocks > 0 && d->tune_solve_blocks < d->coop_blocks) d->coop_blocks = d->tune_solve_blocks;
     }
     if (d->rp_blocks == 0) {
         int per_sm = 0, sms = 0;

@@ -127,6 +127,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("BBX_FUSED_KAHN"); d->fused_kahn = (e && e[0] == '0') ? 0 : 1; }       // default: fused (measured, r01_notes.md)
     { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && atoi(e) == 2) ? 2 : 0; }
+    { const char* e = getenv("BBX_SOLVE_BLOCKS"); d->tune_solve_blocks = e ? atoi(e) : 0; }
     { const char* e = getenv("BBX_REPLAY_BLOCKS"); d->tune_replay_blocks = e ? atoi(e) : 0; }
     { const char* e = getenv("BBX_FLOW_BLOCKS"); d->tune_flow_blocks = e ? atoi(e) : 0; }
     { const char* e = getenv("BBX_FLOW_GATHER"); d->tune_flow_gather = e ? atoi(e) : 0; }
