@@ -611,3 +611,36 @@ def test_overflow_is_reported_by_a_bodies_only_download(product):
     w.step_n(DT, 5)
     with pytest.raises(bb.BallboxError, match="overflow|max_collisions"):
         w.download(bb.DL_BODIES)
+
+
+@pytest.mark.parametrize("schedule", [bb.SOLVER_EXACT, bb.SOLVER_EXACT_FLOW])
+def test_batch_edge_settings(product, truth, schedule):
+    """Batched worlds with unusual settings: sphere-only worlds (no box arrays in use), no friction (the tangent
+    sweep is skipped, :1462), a single solver iteration, zero iterations, restitution 1 and a manifold limit of 2."""
+    d = product.dll
+    cases = [dict(kind=bb.SCENE_BALLS, n=150, friction=0.0, iterations=3, restitution=0.3, mmax=8),
+             dict(kind=bb.SCENE_RLWORLD, n=0, friction=0.5, iterations=1, restitution=1.0, mmax=2),
+             dict(kind=bb.SCENE_RLWORLD, n=0, friction=0.2, iterations=0, restitution=0.0, mmax=8)]
+    for case in cases:
+        n_worlds = 18
+        s, b, c = product.scene_capacity(case["kind"], case["n"])
+        batch = d.CreatePhysicsWorldBatch(n_worlds, s, b, c)
+        views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(n_worlds)]
+        refs = []
+        for i, v in enumerate(views):
+            d.BbxSceneBuild(v.ptr, case["kind"], case["n"], 300 + i)
+            d.BallboxSetSolverSchedule(v.ptr, schedule)
+            r = truth.build_scene(case["kind"], case["n"], 300 + i)
+            for w in (v, r):
+                st = w.w.settings
+                st.friction = case["friction"]; st.solver_iterations = case["iterations"]
+                st.restitution = case["restitution"]; st.manifold_max_contacts = case["mmax"]
+            refs.append(r)
+        assert d.PhysicsStepBatch(batch, DT, 45) == 0, d.BatchGetLastError(batch)
+        assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+        for i in (0, 9, 17):
+            for _ in range(45):
+                refs[i].step(DT)
+            mm = parity.compare_worlds(views[i], refs[i])
+            assert not mm, f"{case}: world {i}: {mm[:3]}"
+        d.DestroyPhysicsWorldBatch(batch)
