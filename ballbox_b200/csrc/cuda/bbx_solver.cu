@@ -486,6 +486,7 @@ __device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level
 #define LC_CACHE 512
 #define SOLVE_THREADS 256
 #define SOLVE_BLOCKS_PER_SM 2
+#define PEND_ROUNDS 4                  // rounds of a level between two block-aggregated appends
 
 // Grid-wide barrier: cooperative-groups grid.sync() measured 1.2 us at 444 x 256 threads on B200,
 // a hand-written arrive/poll barrier 1.7 us (tools/micro/barrier_bench.cu), so we use the former.
@@ -576,6 +577,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ LevelMap lm;
+    __shared__ int s_pcnt[BBX_NCLS], s_pbase[BBX_NCLS];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
     // work index of this thread: consecutive 32-node chunks go round-robin over the BLOCKS, so a level
@@ -593,12 +595,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
         if (tid < BBX_NCLS) lc[(lvl + 2) * BBX_NCLS + tid] = 0;
         int* lc_next = lc + (lvl + 1) * BBX_NCLS;
         const int total = lm.pref[BBX_NCLS];
-        for (int t = wtid; t < total; t += stride) {
+        // Successors that became ready are collected per thread and appended once per BLOCK (and every PEND_ROUNDS
+        // rounds): the class counters of the next level are the busiest addresses of this kernel (a same-address
+        // atomic with a returned value costs 0.5-0.7 ns chip-wide, 1.7 us per dependent use: tools/micro/atomic_bench.cu),
+        // one atomic per block and class instead of one per warp and class takes them off the critical path.
+        int pend[2 * PEND_ROUNDS], np = 0;
+        const int rounds = (total + stride - 1) / stride;            // uniform over the grid: every thread takes part in the flushes
+        for (int r = 0; r < rounds; r++) {
+            const int t = wtid + r * stride;
             int k = 0;
             #pragma unroll
             for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
             int idx = t - lm.pref[k];
-            bool live = idx < lm.cnt[k];
+            bool live = t < total && idx < lm.cnt[k];
             int p = lm.head[k] + idx;
             int sa = -1, sb = -1, m = 0, c = 0;
             int4 nd0 = make_int4(-1, -1, 0, 0);
@@ -634,8 +643,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) != 1) sb = -1;
             }
             // successors that became ready join the next level of their own class
-            push_successor(dv, lc_next, lm, sa);
-            push_successor(dv, lc_next, lm, sb);
+            if (sa >= 0) pend[np++] = sa;
+            if (sb >= 0) pend[np++] = sb;
+            if ((r + 1) % PEND_ROUNDS == 0 || r + 1 == rounds) {
+                // block-aggregated append: slot inside the block through shared-memory counters, one global atomic per class
+                __syncthreads();
+                if (threadIdx.x < BBX_NCLS) s_pcnt[threadIdx.x] = 0;
+                __syncthreads();
+                int pslot[2 * PEND_ROUNDS];
+                for (int i = 0; i < np; i++) pslot[i] = atomicAdd(&s_pcnt[(pend[i] >> 28) & 7], 1);
+                __syncthreads();
+                if (threadIdx.x < BBX_NCLS && s_pcnt[threadIdx.x] > 0) s_pbase[threadIdx.x] = atomicAdd(&lc_next[threadIdx.x], s_pcnt[threadIdx.x]);
+                __syncthreads();
+                for (int i = 0; i < np; i++) {
+                    const int cls = (pend[i] >> 28) & 7;
+                    dv.queue_k[cls][lm.head[cls] + lm.cnt[cls] + s_pbase[cls] + pslot[i]] = pend[i] & 0x0fffffff;
+                }
+                np = 0;
+            }
         }
         grid.sync();
         if (threadIdx.x == 0) level_map_load(lm, lc + (lvl + 1) * BBX_NCLS, false);
