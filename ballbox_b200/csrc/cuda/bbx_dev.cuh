@@ -341,4 +341,27 @@ __device__ __forceinline__ int warp_reserve(int* counter, int n)
     return base + incl - n;
 }
 
+// block-wide reservation of n slots per thread (n may be 0) with ONE global atomic per block: every thread of the
+// block must call (uniform control flow); `s_warp` is a shared int[32].  The global append counters are the
+// busiest addresses of the detection kernels: a same-address atomic with a returned value costs 0.5-0.7 ns
+// chip-wide and ~1.7 us per dependent use under contention (tools/micro/atomic_bench.cu).
+__device__ __forceinline__ int block_reserve(int* counter, int n, int* s_warp)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int incl = n;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = lane < nw ? s_warp[lane] : 0, inc2 = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += y; }
+        int tot = __shfl_sync(0xffffffffu, inc2, 31), base = 0;
+        if (lane == 0 && tot > 0) base = atomicAdd(counter, tot);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < nw) s_warp[lane] = base + inc2 - v;
+    }
+    __syncthreads();
+    return s_warp[wid] + incl - n;
+}
+
 #endif // __CUDACC__

@@ -23,8 +23,9 @@ __device__ __forceinline__ void store_contact(const BbxDev& dv, int slot, int a,
 
 __global__ void __launch_bounds__(256) k_narrow_sb(BbxDev dv)
 {
+    __shared__ int s_warp[32];
     int n = min(dv.ctr->n_cand_sb, dv.cap_cand);
-    int n_round = (n + 31) & ~31;
+    int n_round = (n + blockDim.x - 1) / blockDim.x * blockDim.x;          // block-uniform trip count (block_reserve)
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
         bool hit = false;
         float3 pt, nrm; float pen = 0.0f; int2 pr = make_int2(0, 0);
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(256) k_narrow_sb(BbxDev dv)
             int b = pr.y - dv.NS;
             hit = sphere_box_contact(xyz(sp), sp.w, xyz(bp), xyz(dv.half[b]), dv.boxq[2 * b], pt, nrm, pen);
         }
-        int slot = warp_reserve(&dv.ctr->n_contacts, hit ? 1 : 0);
+        int slot = block_reserve(&dv.ctr->n_contacts, hit ? 1 : 0, s_warp);
         if (hit) {
             if (slot < dv.cap_contacts) store_contact(dv, slot, pr.x, pr.y, RUN_ENC(0, 1), PH_SB, pt, pen, nrm);
             else atomicOr(&dv.ctr->overflow, 2);
@@ -47,8 +48,9 @@ __global__ void __launch_bounds__(256) k_narrow_sb(BbxDev dv)
 // type, -), hit_ax = (SAT axis, |min overlap|).
 __global__ void __launch_bounds__(256) k_bb_sat(BbxDev dv)
 {
+    __shared__ int s_warp[32];
     int n = min(dv.ctr->n_cand_bb, dv.cap_cand);
-    int n_round = (n + 31) & ~31;
+    int n_round = (n + blockDim.x - 1) / blockDim.x * blockDim.x;          // block-uniform trip count (block_reserve)
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
         bool hit = false;
         int2 pr = make_int2(0, 0); float minPd = 0.0f; float3 ax = f3(0, 0, 0); int axisType = -1;
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(256) k_bb_sat(BbxDev dv)
         // the centres) cost 5:1 in pass 2: they are kept apart, from the front and from the back of the hit list,
         // so that the warps of pass 2 are homogeneous
         const bool face = hit && axisType <= 5, edge = hit && axisType > 5;
-        int slot_f = warp_reserve(&dv.ctr->n_hit_bb, face ? 1 : 0);
-        int slot_e = warp_reserve(&dv.ctr->n_hit_bb_edge, edge ? 1 : 0);
+        int slot_f = block_reserve(&dv.ctr->n_hit_bb, face ? 1 : 0, s_warp);
+        int slot_e = block_reserve(&dv.ctr->n_hit_bb_edge, edge ? 1 : 0, s_warp);
         if (hit) {                                             // capacity: hits <= candidates <= cap_cand
             int slot = face ? slot_f : dv.cap_cand - 1 - slot_e;
             dv.hit_ids[slot] = make_int4(pr.x, pr.y, axisType, 0);
@@ -77,7 +79,9 @@ __global__ void __launch_bounds__(256) k_bb_sat(BbxDev dv)
 __global__ void __launch_bounds__(128) k_bb_manifold(BbxDev dv, float tol, float pen_tol, int max_contacts)
 {
     const int nf = dv.ctr->n_hit_bb, ne = dv.ctr->n_hit_bb_edge;          // nf + ne <= cap_cand by construction
-    const int nf_round = (nf + 31) & ~31, n_round = nf_round + ((ne + 31) & ~31);
+    __shared__ int s_warp[32];
+    const int nf_round = (nf + 31) & ~31;
+    const int n_round = (nf_round + ((ne + 31) & ~31) + blockDim.x - 1) / blockDim.x * blockDim.x;      // block-uniform trip count
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
         int np = 0;
         float3 pts[8]; float pens[8]; float3 normal = f3(0, 0, 0);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(128) k_bb_manifold(BbxDev dv, float tol, float
             np = box_box_manifold(xyz(dv.pos[h.x]), xyz(dv.half[a]), dv.boxq[2 * a], xyz(dv.pos[h.y]), xyz(dv.half[b]),
                                   dv.boxq[2 * b], tol, pen_tol, max_contacts, ax.w, h.z, pts, pens, normal);
         }
-        int slot = warp_reserve(&dv.ctr->n_contacts, np);
+        int slot = block_reserve(&dv.ctr->n_contacts, np, s_warp);
         if (np > 0) {
             if (slot + np <= dv.cap_contacts) {
                 for (int k = 0; k < np; k++) store_contact(dv, slot + k, h.x, h.y, RUN_ENC(k, np), PH_BB, pts[k], pens[k], normal);
