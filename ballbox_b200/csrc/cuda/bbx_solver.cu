@@ -288,9 +288,16 @@ __global__ void __launch_bounds__(256) k_frontier0(BbxDev dv)
                 }
             }
         }
-        for (int k = 0; k < BBX_NCLS; k++) {                    // level 0 of every class queue
-            int slot = warp_append(&dv.level_count[k], cls == k);
-            if (cls == k) dv.queue_k[k][slot] = c;
+        // level 0 of the class queues: most warps have nothing to append; the others group their lanes by class
+        const bool push = cls >= 0;
+        const unsigned int active = __ballot_sync(0xffffffffu, push);
+        if (push) {
+            const unsigned int peers = __match_any_sync(active, cls);
+            const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&dv.level_count[cls], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            dv.queue_k[cls][base + __popc(peers & ((1u << lane) - 1u))] = c;
         }
     }
     if (my_nodes) { atomicAdd(&s_solver, my_solver); atomicAdd(&s_nodes, my_nodes); }
