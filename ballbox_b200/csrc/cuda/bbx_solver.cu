@@ -644,8 +644,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                     __stcg(M, c0); __stcg(M + PL, c1); __stcg(M + 2 * PL, c2); __stcg(M + 3 * PL, c3);
                     dv.slot_of[c + j] = mbase + j;
                 }
-                if (hasA) { store_body(dv, nd0.x, A); wake_body(dv, nd0.x); }
-                if (hasB) { store_body(dv, nd0.y, B); wake_body(dv, nd0.y); }
+                if (hasA) store_body(dv, nd0.x, A);            // (the bodies were woken by k_adj_link: one coalesced pass over the
+                if (hasB) store_body(dv, nd0.y, B);            //  touched bodies instead of a random flag access per node here)
                 if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) != 1) sa = -1;
                 if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) != 1) sb = -1;
             }
