@@ -684,31 +684,44 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     // the per-level class counts are static from here on: keep the first LC_CACHE levels in shared
     // memory so that a level does not start with a global round trip
     __shared__ int lc_cache[LC_CACHE * BBX_NCLS];
+    // ... and, when all levels fit, the queue position of every (level, class) as well: a level then starts without the
+    // two block barriers and the serial section that built its map
+    __shared__ int head_cache[LC_CACHE * BBX_NCLS];
+    const bool tables = n_levels <= LC_CACHE;
     for (int i = threadIdx.x; i < min(n_levels, LC_CACHE) * BBX_NCLS; i += blockDim.x) lc_cache[i] = __ldcg(&lc[i]);
+    __syncthreads();
+    if (tables && threadIdx.x < BBX_NCLS) {
+        int run = 0;
+        for (int l = 0; l < n_levels; l++) { head_cache[l * BBX_NCLS + threadIdx.x] = run; run += lc_cache[l * BBX_NCLS + threadIdx.x]; }
+    }
     __syncthreads();
     // (with first_only the later iterations run in k_replay_pairs, two lanes per node)
     for (int it = (sp.levels_known ? 0 : 1); it < (sp.first_only ? 1 : sp.iterations); it++) {
         for (int l = 0; l < n_levels; l++) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int run = 0;
-                for (int k = 0; k < BBX_NCLS; k++) {
-                    if (l == 0) lm.head[k] = 0; else lm.head[k] += lm.cnt[k];
-                    lm.cnt[k] = (l < LC_CACHE) ? lc_cache[l * BBX_NCLS + k] : __ldcg(&lc[l * BBX_NCLS + k]);
-                    lm.pref[k] = run;
-                    run += (lm.cnt[k] + 31) & ~31;
+            if (!tables) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    for (int k = 0; k < BBX_NCLS; k++) {
+                        if (l == 0) lm.head[k] = 0; else lm.head[k] += lm.cnt[k];
+                        lm.cnt[k] = (l < LC_CACHE) ? lc_cache[l * BBX_NCLS + k] : __ldcg(&lc[l * BBX_NCLS + k]);
+                    }
                 }
-                lm.pref[BBX_NCLS] = run;
+                __syncthreads();
             }
-            __syncthreads();
-            const int total = lm.pref[BBX_NCLS];
+            const int* cnt = tables ? &lc_cache[l * BBX_NCLS] : lm.cnt;
+            const int* head = tables ? &head_cache[l * BBX_NCLS] : lm.head;
+            int pref[BBX_NCLS + 1];
+            pref[0] = 0;
+            #pragma unroll
+            for (int k = 0; k < BBX_NCLS; k++) pref[k + 1] = pref[k] + ((cnt[k] + 31) & ~31);
+            const int total = pref[BBX_NCLS];
             for (int t = wtid; t < total; t += stride) {
-                int k = 0;
+                int k = 0, kbase = 0;
                 #pragma unroll
-                for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
-                int idx = t - lm.pref[k];
-                if (idx >= lm.cnt[k]) continue;
-                int4 nd = __ldcg(&dv.Nd_k[k][lm.head[k] + idx]);
+                for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= pref[kk]) { k = kk; kbase = pref[kk]; }
+                int idx = t - kbase;
+                if (idx >= cnt[k]) continue;
+                int4 nd = __ldcg(&dv.Nd_k[k][head[k] + idx]);
                 bool hasA = nd.z >= 0, hasB = nd.w >= 0;
                 BodyState A, B;
                 if (hasA) load_body(dv, nd.z, A);
