@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(256) k_frontier_flow(BbxDev dv)
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     int n_round = (n + 31) & ~31;
     int mine = 0;
-    if (blockIdx.x == 0 && threadIdx.x < 8) dv.level_ns[FLOW_DBG + threadIdx.x] = 0ull;     // debug trace of the last step
+    if (blockIdx.x == 0 && threadIdx.x < 16) dv.level_ns[FLOW_DBG - 8 + threadIdx.x] = 0ull;     // debug trace of the last step
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += gridDim.x * blockDim.x) {
         bool seed = false;
         if (c < n) {
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, FLOW_BLOCKS_PER_SM) k_solve_flow
     const bool side = lane & 1;                                         // 0: body A, 1: body B
     const size_t PL = (size_t)dv.cap_contacts;
     const int last_it = sp.iterations - 1;
-    int depth_max = 0;
+    int depth_max = 0, udepth_max = 0;
     bool dead = false;
     unsigned long long dbg_chunks = 0, dbg_proc = 0, dbg_spin = 0, dbg_fail = 0, dbg_wait = 0;
     const long long t_begin = clock64();
@@ -997,6 +997,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, FLOW_BLOCKS_PER_SM) k_solve_flow
                     const float mN = __shfl_sync(rdy, mS, lane & ~1), mT0 = __shfl_sync(rdy, mS, lane | 1);
                     solve_half(rdy, side, has, c0, r, mN, mT0, c3, S, sp);
                     const int depth = max(dp, __shfl_xor_sync(rdy, dp, 1)) + 1;
+                    udepth_max = max(udepth_max, depth);                       // depth of the unrolled (all-iterations) graph
                     if (!side) flow_store_imp(dv, s, c3, it + 1);
                     if (first) {
                         // keep the visiting order: record and descriptor in queue order for the replay and the export
@@ -1024,7 +1025,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, FLOW_BLOCKS_PER_SM) k_solve_flow
     }
     // statistics: dependency depth (reported as "levels"), trace
     for (int o = 16; o > 0; o >>= 1) depth_max = max(depth_max, __shfl_xor_sync(0xffffffffu, depth_max, o));
+    for (int o = 16; o > 0; o >>= 1) udepth_max = max(udepth_max, __shfl_xor_sync(0xffffffffu, udepth_max, o));
     if (lane == 0) {
+        if (udepth_max > 0) atomicMax(&dv.level_ns[FLOW_DBG - 8], (unsigned long long)udepth_max);   // debug trace (tools/profile_step.py)
         if (depth_max > 0) atomicMax(&dv.ctr->n_levels, depth_max);
         atomicAdd(&dv.level_ns[FLOW_DBG + 0], dbg_chunks); atomicAdd(&dv.level_ns[FLOW_DBG + 1], dbg_proc);
         atomicAdd(&dv.level_ns[FLOW_DBG + 2], dbg_spin); atomicAdd(&dv.level_ns[FLOW_DBG + 4], dbg_wait);

@@ -47,6 +47,9 @@ if os.environ.get("BBX_TRACE_LEVEL"):
     print(f"level trace (level {os.environ['BBX_TRACE_LEVEL']}, iteration 1): warps with work={fd[2]:.0f} mean busy us={fd[0]/max(fd[2],1)/1e3:.2f} max busy us={fd[1]/1e3:.2f} | "
           f"1 chunk: n={fd[4]:.0f} mean={fd[3]/max(fd[4],1)/1e3:.2f} us | 2 chunks: n={fd[6]:.0f} mean={fd[5]/max(fd[6],1)/1e3:.2f} us | 3+ chunks: n={n3:.0f} mean={fd[7]/max(n3,1)/1e3:.2f} us")
 elif fd[5] > 0:
+    ud = int(np.frombuffer(ns, dtype=np.uint64)[4080])
+    print(f"flow solver: dependency depth of ALL iterations together = {ud} constraints (iteration 0 alone: {w.stats().levels}; "
+          f"{w.w.settings.solver_iterations} iterations one after the other would be {w.stats().levels * w.w.settings.solver_iterations})")
     print(f"flow solver (last step): chunk visits={fd[0]:.0f} processing passes={fd[1]:.0f} spin passes={fd[2]:.0f} failed lane polls={fd[3]:.0f} "
           f"warp wait/busy cycles={fd[4]/max(fd[5],1):.3f} replay (after iteration 0) ms={(fd[7]-fd[6])/1e6:.3f}")
 cnt = np.frombuffer(cnt, dtype=np.int32).reshape(-1, 8)[:L]; ns = np.frombuffer(ns, dtype=np.uint64)[:L + 1].astype(np.int64)
