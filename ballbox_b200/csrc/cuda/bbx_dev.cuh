@@ -142,6 +142,7 @@ struct BbxDev {
     int last_per_contact;                        // the last solve used one node per constraint (layout of `node`)
     int last_flow;                               // the last solve ran on the flow solver (impulses live in fimp)
     int flow_blocks;                             // co-resident blocks of k_solve_flow
+    int packed_sweep;                            // BBX_PACKED=1: level replay with packed FP32x2 arithmetic (bit-exact, measured slower: register spills)
     int kahn_blocks, fused_kahn;                 // co-resident blocks of k_kahn_levels; BBX_FUSED_KAHN=1: level discovery fused with sweep 0
     int rp_blocks, replay_mode;                  // co-resident blocks of k_replay_pairs; BBX_REPLAY=2 selects it
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels

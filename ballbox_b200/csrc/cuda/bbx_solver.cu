@@ -308,7 +308,9 @@ __global__ void __launch_bounds__(256) k_frontier0(BbxDev dv)
 // ---------------------------------------------------------------------------
 // K11 velocity solve
 // ---------------------------------------------------------------------------
-struct SolveParams { float restitution, friction, vel_threshold; int iterations; int gather; int first_only; int levels_known; };
+typedef unsigned long long P2;                   // two packed floats (f32x2)
+struct PackConst { P2 neg0, one, mone, two, sgn; };   // (-0,-0) (1,1) (-1,-1) (2,2) (-1,1): opaque to ptxas on purpose
+struct SolveParams { float restitution, friction, vel_threshold; int iterations; int gather; int first_only; int levels_known; int packed; PackConst pc; };
 
 struct BodyState {
     float3 v, w;
@@ -471,6 +473,145 @@ __device__ __forceinline__ void solve_constraint(float4 c0, float4 c1, float4 c2
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same visit with PACKED FP32x2 arithmetic (sm_100a FFMA2): body A in the low half, body B in the high half of
+// every 64-bit operand.  The two bodies of a constraint go through structurally identical code, so velocity-at-point
+// and the three impulse applications (~80 % of the ~700 instructions) run once for both.
+// Bit-exactness: every operation is an fma whose result is the IEEE result of the scalar operation it stands for,
+//   a * b = fma(a, b, -0)     a + b = fma(a, 1, b)     a - b = fma(b, -1, a)
+// and the constants -0, 1, -1 come from the kernel parameters (SolveParams::pc).  With literal constants ptxas folds
+// these back into FMUL2 / FADD2 and then CONTRACTS neighbouring pairs into one FFMA2 (seen in the SASS, and in 2220
+// differing impulses on a 20k-sphere scene); it cannot do either with operands it does not know.
+// Mixed pairs (sphere + box) compute the box form and the sphere form and select per half.
+// (tools/micro/f32x2_bench.cu: one FFMA2 costs what one FFMA costs, in latency and in issue slots.)
+// ---------------------------------------------------------------------------
+struct P3 { P2 x, y, z; };
+__device__ __forceinline__ P2 pk(float a, float b) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float plo(P2 p) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); return a; }
+__device__ __forceinline__ float phi(P2 p) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); return b; }
+__device__ __forceinline__ P2 pfma(P2 a, P2 b, P2 c) { P2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+#define PMUL(a, b) pfma((a), (b), K.neg0)
+#define PADD(a, b) pfma((a), K.one, (b))
+#define PSUB(a, b) pfma((b), K.mone, (a))
+__device__ __forceinline__ P3 p3(float3 a, float3 b) { P3 r; r.x = pk(a.x, b.x); r.y = pk(a.y, b.y); r.z = pk(a.z, b.z); return r; }
+__device__ __forceinline__ P3 p3add(const PackConst& K, P3 a, P3 b) { P3 r; r.x = PADD(a.x, b.x); r.y = PADD(a.y, b.y); r.z = PADD(a.z, b.z); return r; }
+__device__ __forceinline__ P3 p3scale(const PackConst& K, P3 v, P2 s) { P3 r; r.x = PMUL(v.x, s); r.y = PMUL(v.y, s); r.z = PMUL(v.z, s); return r; }
+__device__ __forceinline__ P3 p3mul(const PackConst& K, P3 a, P3 b) { P3 r; r.x = PMUL(a.x, b.x); r.y = PMUL(a.y, b.y); r.z = PMUL(a.z, b.z); return r; }
+__device__ __forceinline__ P2 p3dot(const PackConst& K, P3 a, P3 b) { return PADD(PADD(PMUL(a.x, b.x), PMUL(a.y, b.y)), PMUL(a.z, b.z)); }
+__device__ __forceinline__ P3 p3cross(const PackConst& K, P3 a, P3 b)
+{
+    P3 r;
+    r.x = PSUB(PMUL(a.y, b.z), PMUL(a.z, b.y)); r.y = PSUB(PMUL(a.z, b.x), PMUL(a.x, b.z)); r.z = PSUB(PMUL(a.x, b.y), PMUL(a.y, b.x));
+    return r;
+}
+
+struct PairState {          // bodies A (low halves) and B (high halves)
+    P3 v, w;
+    P2 im, ii, k1, k2;
+    P3 iI, u, um;
+    bool boxA, boxB;
+};
+
+__device__ __forceinline__ void pair_from(const BodyState& A, const BodyState& B, bool hasA, bool hasB, PairState& s)
+{
+    const float3 z = f3(0.0f, 0.0f, 0.0f);
+    s.boxA = hasA && A.box; s.boxB = hasB && B.box;
+    s.v = p3(hasA ? A.v : z, hasB ? B.v : z); s.w = p3(hasA ? A.w : z, hasB ? B.w : z);
+    s.im = pk(hasA ? A.im : 0.0f, hasB ? B.im : 0.0f);
+    s.ii = pk(hasA && !A.box ? A.ii : 0.0f, hasB && !B.box ? B.ii : 0.0f);
+    if (s.boxA || s.boxB) {
+        const float3 ua = s.boxA ? f3(A.q.x, A.q.y, A.q.z) : z, ub = s.boxB ? f3(B.q.x, B.q.y, B.q.z) : z;
+        s.u = p3(ua, ub); s.um = p3(f3(-ua.x, -ua.y, -ua.z), f3(-ub.x, -ub.y, -ub.z));
+        s.iI = p3(s.boxA ? A.iI : z, s.boxB ? B.iI : z);
+        s.k1 = pk(s.boxA ? A.k1 : 0.0f, s.boxB ? B.k1 : 0.0f); s.k2 = pk(s.boxA ? A.k2 : 0.0f, s.boxB ? B.k2 : 0.0f);
+    }
+}
+
+__device__ __forceinline__ P3 pqrot_pre(const PackConst& K, P3 u, P2 k1, P2 k2, P3 v)      // qrot_pre on both halves
+{
+    P3 a = p3scale(K, v, k1);
+    P3 b = p3scale(K, u, PMUL(K.two, p3dot(K, u, v)));
+    P3 c = p3scale(K, p3cross(K, u, v), k2);
+    return p3add(K, p3add(K, a, b), c);
+}
+
+__device__ __forceinline__ P2 psel(bool lo_first, bool hi_first, P2 first, P2 second)
+{
+    return pk(lo_first ? plo(first) : plo(second), hi_first ? phi(first) : phi(second));
+}
+
+// ApplyConstraintImpulse on both bodies: A receives -X, B receives +X (X = n * jn or a tangent impulse)
+__device__ __forceinline__ void pair_apply(const PackConst& K, PairState& s, P3 r, float3 X)
+{
+    // (-1) * X for A (v3scale(X, -1.0f)); X itself for B (1 * X is exact)
+    P3 J; J.x = PMUL(pk(X.x, X.x), K.sgn); J.y = PMUL(pk(X.y, X.y), K.sgn); J.z = PMUL(pk(X.z, X.z), K.sgn);
+    P3 L = p3cross(K, r, J);
+    s.v = p3add(K, s.v, p3scale(K, J, s.im));
+    P3 dw = p3scale(K, L, s.ii);                                                      // spheres
+    if (s.boxA || s.boxB) {
+        P3 loc = pqrot_pre(K, s.um, s.k1, s.k2, L);
+        P3 dl = p3mul(K, loc, s.iI);
+        P3 db = pqrot_pre(K, s.u, s.k1, s.k2, dl);
+        dw.x = psel(s.boxA, s.boxB, db.x, dw.x); dw.y = psel(s.boxA, s.boxB, db.y, dw.y); dw.z = psel(s.boxA, s.boxB, db.z, dw.z);
+    }
+    s.w = p3add(K, s.w, dw);
+}
+
+__device__ __forceinline__ float3 pair_rel(const PackConst& K, const PairState& s, P3 r, bool hasA, bool hasB)   // vB - vA at the contact
+{
+    P3 vel = p3add(K, s.v, p3cross(K, s.w, r));
+    const float3 z = f3(0.0f, 0.0f, 0.0f);
+    float3 vA = hasA ? f3(plo(vel.x), plo(vel.y), plo(vel.z)) : z;
+    float3 vB = hasB ? f3(phi(vel.x), phi(vel.y), phi(vel.z)) : z;
+    return v3sub(vB, vA);
+}
+
+__device__ __forceinline__ void solve_constraint_packed(float4 c0, float4 c1, float4 c2, float4& c3, bool hasA, bool hasB,
+                                                        PairState& s, const SolveParams& sp)
+{
+    const PackConst& K = sp.pc;
+    float3 n = xyz(c0);
+    float bias = c0.w, mN = c1.w, mT0 = c2.w, mT1 = c3.w;
+    const P3 r = p3(xyz(c1), xyz(c2));
+    float3 rel = pair_rel(K, s, r, hasA, hasB);
+    float vn = v3dot(rel, n);
+    float vbias = 0.0f;
+    if (vn < -sp.vel_threshold) vbias = -sp.restitution * vn;                // :1443-1445
+    float jn = mN * (-(vn + vbias) + bias);                                  // :1447
+    float old = c3.x;
+    c3.x = bb_fmaxf(0.0f, c3.x + jn);                                        // :1451
+    jn = c3.x - old;
+    pair_apply(K, s, r, v3scale(n, jn));                                     // :1456-1459
+    if (sp.friction > 0.0f) {                                                // :1462-1487
+        rel = pair_rel(K, s, r, hasA, hasB);
+        float3 t1, t2;
+        tangents_of(n, t1, t2);
+        float maxF = sp.friction * c3.x;
+        {
+            float vt = v3dot(rel, t1);
+            float jt = mT0 * (-vt);
+            float o = c3.y;
+            c3.y = bb_fmaxf(-maxF, bb_fminf(maxF, c3.y + jt));
+            jt = c3.y - o;
+            pair_apply(K, s, r, v3scale(t1, jt));
+        }
+        {
+            float vt = v3dot(rel, t2);                                       // same pre-loop rel (:1466 is outside the j loop)
+            float jt = mT1 * (-vt);
+            float o = c3.z;
+            c3.z = bb_fmaxf(-maxF, bb_fminf(maxF, c3.z + jt));
+            jt = c3.z - o;
+            pair_apply(K, s, r, v3scale(t2, jt));
+        }
+    }
+}
+
+__device__ __forceinline__ void pair_to(const PairState& s, bool hasA, bool hasB, BodyState& A, BodyState& B)
+{
+    if (hasA) { A.v = f3(plo(s.v.x), plo(s.v.y), plo(s.v.z)); A.w = f3(plo(s.w.x), plo(s.w.y), plo(s.w.z)); }
+    if (hasB) { B.v = f3(phi(s.v.x), phi(s.v.y), phi(s.v.z)); B.w = f3(phi(s.w.x), phi(s.w.y), phi(s.w.z)); }
+}
+
 // Per level, the nodes of class k sit in queue_k[k][head_k .. head_k + cnt_k).  The flattened
 // index space pads every class to a multiple of 32 so that a warp never mixes classes.
 struct LevelMap { int head[BBX_NCLS]; int cnt[BBX_NCLS]; int pref[BBX_NCLS + 1]; };
@@ -580,11 +721,13 @@ __global__ void __launch_bounds__(KAHN_THREADS, KAHN_BLOCKS_PER_SM) k_kahn_level
     if (tid == 0) dv.ctr->n_levels = lvl;
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_levels(BbxDev dv, SolveParams sp)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ LevelMap lm;
     __shared__ int s_pcnt[BBX_NCLS], s_pbase[BBX_NCLS];
+    constexpr bool PACKED0 = false;                 // iteration 0 keeps the scalar sweep (register budget of the discovery pass)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
     // work index of this thread: consecutive 32-node chunks go round-robin over the BLOCKS, so a level
@@ -636,14 +779,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 // the current constraint is swept), then written plane-major
                 const float4* L = dv.L + 4 * (size_t)c;
                 F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+                PairState ps;
+                if (PACKED0) pair_from(A, B, hasA, hasB, ps);
                 for (int j = 0; j < m; j++, L += 4) {
                     float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
                     if (j + 1 < m) { lo = ld256_nc(L + 4); hi = ld256_nc(L + 6); }
-                    solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    if (PACKED0) solve_constraint_packed(c0, c1, c2, c3, hasA, hasB, ps, sp);
+                    else         solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     float4* M = dv.M + (size_t)(mbase + j);
                     __stcg(M, c0); __stcg(M + PL, c1); __stcg(M + 2 * PL, c2); __stcg(M + 3 * PL, c3);
                     dv.slot_of[c + j] = mbase + j;
                 }
+                if (PACKED0) pair_to(ps, hasA, hasB, A, B);
                 if (hasA) store_body(dv, nd0.x, A);            // (the bodies were woken by k_adj_link: one coalesced pass over the
                 if (hasB) store_body(dv, nd0.y, B);            //  touched bodies instead of a random flag access per node here)
                 if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) != 1) sa = -1;
@@ -729,12 +876,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 float4* M = dv.M + (size_t)nd.x;
                 // software pipeline: the record of constraint j+1 is in flight while constraint j is swept
                 float4 n0 = __ldcg(M), n1 = __ldcg(M + PL), n2 = __ldcg(M + 2 * PL), n3 = __ldcg(M + 3 * PL);
+                PairState ps;
+                if (PACKED) pair_from(A, B, hasA, hasB, ps);
                 for (int j = 0; j < nd.y; j++, M++) {
+                    if (PACKED && j > 0) { n0 = __ldcg(M); n1 = __ldcg(M + PL); n2 = __ldcg(M + 2 * PL); n3 = __ldcg(M + 3 * PL); }
                     float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
-                    if (j + 1 < nd.y) { n0 = __ldcg(M + 1); n1 = __ldcg(M + 1 + PL); n2 = __ldcg(M + 1 + 2 * PL); n3 = __ldcg(M + 1 + 3 * PL); }
-                    solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    if (!PACKED && j + 1 < nd.y) { n0 = __ldcg(M + 1); n1 = __ldcg(M + 1 + PL); n2 = __ldcg(M + 1 + 2 * PL); n3 = __ldcg(M + 1 + 3 * PL); }
+                    if (PACKED) solve_constraint_packed(c0, c1, c2, c3, hasA, hasB, ps, sp);
+                    else        solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     __stcg(M + 3 * PL, c3);
                 }
+                if (PACKED) pair_to(ps, hasA, hasB, A, B);
                 if (hasA) store_body(dv, nd.z, A);
                 if (hasB) store_body(dv, nd.w, B);
             }
@@ -1613,7 +1765,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         BBX_CUDA(d, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d->device));
         if (!coop) return bbx_fail(d, BBX_ERR_NO_DEVICE, "device lacks cooperative launch", __FILE__, __LINE__);
         BBX_CUDA(d, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
-        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_levels, SOLVE_THREADS, 0));
+        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, d->packed_sweep ? k_solve_levels<true> : k_solve_levels<false>, SOLVE_THREADS, 0));
         if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "solver kernel does not fit on an SM", __FILE__, __LINE__);
         if (per_sm > SOLVE_BLOCKS_PER_SM) per_sm = SOLVE_BLOCKS_PER_SM;
         d->coop_blocks = per_sm * sms;
@@ -1642,6 +1794,12 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;
     sp.vel_threshold = p->settings.velocity_threshold; sp.iterations = iterations; sp.gather = 0;
     sp.levels_known = (d->kahn_blocks > 0 && !d->fused_kahn) ? 1 : 0;
+    sp.packed = d->packed_sweep;
+    {   // f32x2 constants of the packed sweep, low half first
+        const unsigned long long n0 = 0x80000000ull, one = 0x3f800000ull, mone = 0xbf800000ull, two = 0x40000000ull;
+        sp.pc.neg0 = n0 | (n0 << 32); sp.pc.one = one | (one << 32); sp.pc.mone = mone | (mone << 32);
+        sp.pc.two = two | (two << 32); sp.pc.sgn = mone | (one << 32);
+    }
     if (sp.levels_known) {
         BbxDev dvk = *d;
         void* kargs[] = { (void*)&dvk };
@@ -1656,7 +1814,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
     if (!pairs_all) {
-        BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
+        BBX_CUDA(d, cudaLaunchCooperativeKernel(d->packed_sweep ? (void*)k_solve_levels<true> : (void*)k_solve_levels<false>, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
         d->launches++;
     }
     if ((sp.first_only && d->replay_mode == 2) || pairs_all) {

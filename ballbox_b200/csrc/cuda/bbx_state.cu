@@ -125,6 +125,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     // measurement switches (A/B runs of tools/ and profiles/r01_notes.md), read once per device state
     { const char* e = getenv("BBX_WORLD_GROUPS"); d->no_groups = (e && e[0] == '0') ? 1 : 0; }
     { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
+    { const char* e = getenv("BBX_PACKED"); d->packed_sweep = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("BBX_FUSED_KAHN"); d->fused_kahn = (e && e[0] == '0') ? 0 : 1; }       // default: fused (measured, r01_notes.md)
     { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && atoi(e) == 2) ? 2 : 0; }
     { const char* e = getenv("BBX_SOLVE_BLOCKS"); d->tune_solve_blocks = e ? atoi(e) : 0; }

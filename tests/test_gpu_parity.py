@@ -603,6 +603,14 @@ def test_full_size_batch_three_solvers_agree(product, monkeypatch):
     assert hashes[0] == hashes[1] == hashes[2] and hashes[0][0] > 1_000_000
 
 
+@pytest.mark.parametrize("kind,n,steps", [(bb.SCENE_MIXED, 2500, 40), (bb.SCENE_SDF, 1200, 30)])
+def test_packed_fp32x2_sweep_is_bit_exact(product, truth, monkeypatch, kind, n, steps):
+    """BBX_PACKED=1 replays the levels with fma.rn.f32x2 (both bodies of a constraint in one instruction); every
+    packed operation must round like the scalar one it replaces (sphere-sphere, box-box and mixed pairs)."""
+    monkeypatch.setenv("BBX_PACKED", "1")
+    lockstep(product, truth, kind, n, 31, steps, every=3)
+
+
 def test_overflow_is_reported_by_a_bodies_only_download(product):
     """Resident stepping never looks at the host; a step that dropped contacts (max_collisions too small) must
     still surface at the next download, also when only the bodies are fetched."""
