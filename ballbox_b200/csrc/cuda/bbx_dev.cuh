@@ -186,6 +186,9 @@ struct BbxDev {
     // optional per-stage timing (CUDA events on the step stream)
     int timing_on, timing_steps, timing_cap;
     cudaEvent_t *timing_ev;      // timing_cap * BBX_TIMING_MARKS events
+    // drop-in (host array) path: device->host copies run on their own stream so that they overlap the export kernels
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_upload, ev_chain;
     char *err;                   // 256-byte host buffer (kept out of the by-value kernel argument)
     int has_err;
 };

@@ -161,6 +161,9 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
     if (d->ctr_host) cudaFreeHost(d->ctr_host);
     if (d->timing_ev) { for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventDestroy(d->timing_ev[i]); free(d->timing_ev); }
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    if (d->ev_upload) cudaEventDestroy(d->ev_upload);
+    if (d->ev_chain) cudaEventDestroy(d->ev_chain);
     cudaGetLastError();
     free(d->err);
     free(d);
@@ -323,6 +326,8 @@ extern "C" int bbx_dev_upload(BbxDev* d, const BbxHostBodies* hb)
     UP(d->r_b_timer, hb->b_timer, 4 * NB); UP(d->r_b_static, hb->b_static, NB); UP(d->r_b_sleep, hb->b_sleep, NB);
     if (hb->b_hascb) UP(d->r_b_hascb, hb->b_hascb, NB); else BBX_CUDA(d, cudaMemsetAsync(d->r_b_hascb, 0, NB ? NB : 1, s));
 #undef UP
+    if (!d->ev_upload) BBX_CUDA(d, cudaEventCreateWithFlags(&d->ev_upload, cudaEventDisableTiming));
+    BBX_CUDA(d, cudaEventRecord(d->ev_upload, s));
     long long vs = 0, vb = 0;
     for (int w = 0; w < d->n_worlds; w++) { vs += hb->s_count[w]; vb += hb->b_count[w]; }
     d->n_valid_spheres = (int)vs; d->n_valid_boxes = (int)vb;
@@ -403,6 +408,34 @@ int bbx_stage_unpack(BbxDev* d)
     return 0;
 }
 
+int bbx_copy_stream(BbxDev* d)
+{
+    if (!d->copy_stream) BBX_CUDA(d, cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    if (!d->ev_chain) BBX_CUDA(d, cudaEventCreateWithFlags(&d->ev_chain, cudaEventDisableTiming));
+    return 0;
+}
+
+extern "C" int bbx_dev_wait_upload(BbxDev* d)
+{
+    if (!d) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (d->ev_upload) BBX_CUDA(d, cudaEventSynchronize(d->ev_upload));
+    return 0;
+}
+
+// body arrays -> host on stream `s` (after the unpack kernel on the step stream)
+static int download_bodies_on(BbxDev* d, const BbxHostBodies* hb, cudaStream_t s)
+{
+    size_t NS = d->NS, NB = d->NB;
+#define DN(dst, src, bytes) do { if ((bytes) > 0 && (dst)) BBX_CUDA(d, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s)); } while (0)
+    DN(hb->s_pos, d->r_s_pos, 12 * NS); DN(hb->s_vel, d->r_s_vel, 12 * NS); DN(hb->s_angvel, d->r_s_angvel, 12 * NS);
+    DN(hb->s_sleep, d->r_s_sleep, NS); DN(hb->s_timer, d->r_s_timer, 4 * NS);
+    DN(hb->b_pos, d->r_b_pos, 12 * NB); DN(hb->b_vel, d->r_b_vel, 12 * NB); DN(hb->b_angvel, d->r_b_angvel, 12 * NB);
+    DN(hb->b_rot, d->r_b_rot, 16 * NB); DN(hb->b_sleep, d->r_b_sleep, NB); DN(hb->b_timer, d->r_b_timer, 4 * NB);
+#undef DN
+    return 0;
+}
+
 extern "C" int bbx_dev_download(BbxDev* d, const BbxHostBodies* hb)
 {
     if (!d || !hb) return BBX_ERR_BAD_ARGUMENT;
@@ -410,17 +443,35 @@ extern "C" int bbx_dev_download(BbxDev* d, const BbxHostBodies* hb)
     BBX_CUDA(d, cudaSetDevice(d->device));
     int rc = bbx_stage_unpack(d);
     if (rc) return rc;
-    size_t NS = d->NS, NB = d->NB;
     cudaStream_t s = d->stream;
-#define DN(dst, src, bytes) do { if ((bytes) > 0 && (dst)) BBX_CUDA(d, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s)); } while (0)
-    DN(hb->s_pos, d->r_s_pos, 12 * NS); DN(hb->s_vel, d->r_s_vel, 12 * NS); DN(hb->s_angvel, d->r_s_angvel, 12 * NS);
-    DN(hb->s_sleep, d->r_s_sleep, NS); DN(hb->s_timer, d->r_s_timer, 4 * NS);
-    DN(hb->b_pos, d->r_b_pos, 12 * NB); DN(hb->b_vel, d->r_b_vel, 12 * NB); DN(hb->b_angvel, d->r_b_angvel, 12 * NB);
-    DN(hb->b_rot, d->r_b_rot, 16 * NB); DN(hb->b_sleep, d->r_b_sleep, NB); DN(hb->b_timer, d->r_b_timer, 4 * NB);
-#undef DN
+    if ((rc = download_bodies_on(d, hb, s))) return rc;
     BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, s));
     BBX_CUDA(d, cudaStreamSynchronize(s));
     return bbx_check_overflow(d);                // state computed from a truncated contact list is not handed out silently
+}
+
+extern "C" int bbx_dev_download_begin(BbxDev* d, const BbxHostBodies* hb)
+{
+    if (!d || !hb) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    int rc = bbx_stage_unpack(d);
+    if (rc) return rc;
+    if ((rc = bbx_copy_stream(d))) return rc;
+    BBX_CUDA(d, cudaEventRecord(d->ev_chain, d->stream));
+    BBX_CUDA(d, cudaStreamWaitEvent(d->copy_stream, d->ev_chain, 0));
+    return download_bodies_on(d, hb, d->copy_stream);
+}
+
+extern "C" int bbx_dev_download_end(BbxDev* d)
+{
+    if (!d) return BBX_ERR_BAD_ARGUMENT;
+    cudaSetDevice(d->device);
+    if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);     // also after a failure: the host arrays must be quiet
+    if (d->has_err) return BBX_ERR_STICKY;
+    BBX_CUDA(d, cudaMemcpyAsync(d->ctr_host, d->ctr, sizeof(StepCounters), cudaMemcpyDeviceToHost, d->stream));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    return bbx_check_overflow(d);
 }
 
 extern "C" int bbx_dev_stats(BbxDev* d, BallboxStats* out)

@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(256) k_gather_records(const float* src, float*
 }
 
 static int ensure_export_buffers(BbxDev* d);
+int bbx_copy_stream(BbxDev* d);
 int bbx_radix_sort(BbxDev* d, unsigned long long* keys_a, unsigned int* vals_a, unsigned long long* keys_b,
                    unsigned int* vals_b, int n, int bits, int* hist, int* hist_scan,
                    unsigned long long** keys_sorted, unsigned int** vals_sorted);
@@ -312,16 +313,30 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
     int rc = bbx_radix_sort(d, d->sort_keys, d->sort_vals_a, d->sort_keys_b, d->sort_vals_b, n, total_bits,
                             d->sort_hist, d->sort_hist_scan, &ks, &order);
     if (rc) return rc;
-    BBX_LAUNCH(d, k_gather_records, BBX_NUM_SMS * 16, 256, 0, (const float*)d->export_buf, (float*)d->export_sorted, order, n);
-    BBX_CUDA(d, cudaGetLastError());
     if (d->n_worlds == 1) {
         if (n > cap_per_world)
             return bbx_fail(d, BBX_ERR_OVERFLOW, "the step produced more contacts than max_collisions", __FILE__, __LINE__);
-        BBX_CUDA(d, cudaMemcpyAsync(out, d->export_sorted, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
-        BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+        // gather and copy in chunks: chunk i crosses PCIe (copy stream) while chunk i+1 is gathered (step stream)
+        { int rcs = bbx_copy_stream(d); if (rcs) return rcs; }
+        const int CH = 1 << 19;                                    // 512k records = 54.5 MB, ~1 ms on the link
+        for (int off = 0; off < n; off += CH) {
+            const int m = n - off < CH ? n - off : CH;
+            BBX_LAUNCH(d, k_gather_records, BBX_NUM_SMS * 16, 256, 0, (const float*)d->export_buf,
+                       (float*)(d->export_sorted + off), order + off, m);
+            BBX_CUDA(d, cudaEventRecord(d->ev_chain, d->stream));
+            BBX_CUDA(d, cudaStreamWaitEvent(d->copy_stream, d->ev_chain, 0));
+            BBX_CUDA(d, cudaMemcpyAsync(out + off, d->export_sorted + off, sizeof(ContactConstraint) * (size_t)m,
+                                        cudaMemcpyDeviceToHost, d->copy_stream));
+        }
+        BBX_CUDA(d, cudaGetLastError());
+        BBX_CUDA(d, cudaStreamSynchronize(d->copy_stream));
+        // the next step (or export) on the step stream must not overwrite export_sorted early: it is ordered after the
+        // host-side wait above
         counts[0] = n;
         return 0;
     }
+    BBX_LAUNCH(d, k_gather_records, BBX_NUM_SMS * 16, 256, 0, (const float*)d->export_buf, (float*)d->export_sorted, order, n);
+    BBX_CUDA(d, cudaGetLastError());
     // batch: sorted by world first; cut the list at world boundaries on the host
     std::vector<unsigned long long> keys((size_t)n);
     std::vector<ContactConstraint> recs((size_t)n);

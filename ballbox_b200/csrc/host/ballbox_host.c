@@ -817,8 +817,16 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
             /* the full mode replays callbacks from the downloaded list, the other one from device-side events */
             if ((rc = fill_params(b, dt, 1, (!full && b->n_callbacks > 0) ? 1 : 0, &prm))) return rc;
             if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, 1)))) return rc;
-            if ((rc = batch_download(b, full ? (BBX_DL_BODIES | BBX_DL_CONSTRAINTS) : BBX_DL_BODIES))) return rc;
+            /* the step is queued, not finished: clear the force arrays (:1836) as soon as the upload has read them */
+            if ((rc = batch_check_dev(b, bbx_dev_wait_upload(b->dev)))) return rc;
             zero_host_forces(b);
+            if (full) {
+                /* body arrays cross the link while the constraint records are exported and sorted */
+                if ((rc = batch_check_dev(b, bbx_dev_download_begin(b->dev, &b->hb)))) return rc;
+                rc = batch_download(b, BBX_DL_CONSTRAINTS);
+                int rc2 = batch_check_dev(b, bbx_dev_download_end(b->dev));
+                if (rc || rc2) return rc ? rc : rc2;
+            } else if ((rc = batch_download(b, BBX_DL_BODIES))) return rc;
             for (int w = 0; w < b->n_worlds; w++) b->worlds[w].collisions.count = 0;       /* ballbox.h:2310 */
             if (!full) for (int w = 0; w < b->n_worlds; w++) b->worlds[w].constraints.count = 0;
             if (b->n_callbacks > 0) {

@@ -74,6 +74,16 @@ int  bbx_dev_upload(BbxDev* dev, const BbxHostBodies* hb);
 int  bbx_dev_upload_forces(BbxDev* dev, const BbxHostBodies* hb);
 int  bbx_dev_step(BbxDev* dev, const BbxStepParams* params, int steps);
 int  bbx_dev_download(BbxDev* dev, const BbxHostBodies* hb);
+/* Overlap helpers of the drop-in PhysicsStep (host arrays in, host arrays out):
+ *   bbx_dev_wait_upload     returns when the last bbx_dev_upload has finished READING the host arrays (the step
+ *                           itself may still be running): the caller may then overwrite them (force clearing :1836)
+ *   bbx_dev_download_begin  like bbx_dev_download, but the copies are only queued (on a second stream)
+ *   bbx_dev_download_end    waits for them and reports a contact overflow like bbx_dev_download
+ * bbx_dev_download_constraints between begin and end shares the copy stream: body arrays travel while the
+ * constraint records are still being exported and sorted. */
+int  bbx_dev_wait_upload(BbxDev* dev);
+int  bbx_dev_download_begin(BbxDev* dev, const BbxHostBodies* hb);
+int  bbx_dev_download_end(BbxDev* dev);
 
 /* ---- the reference's public stage functions (ballbox.h:217-229), single world only -----------
  * bbx_dev_run_stage runs ONE stage on the state uploaded before it:
