@@ -219,6 +219,7 @@ class BallboxLib:
             d.BallboxSetSDFBakeRegion.argtypes = [WP, Vec3, Vec3, C.c_int]
             d.BallboxSetSDFBakeRegion.restype = None
             d.BallboxBakeSDF.argtypes = [WP]; d.BallboxBakeSDF.restype = C.c_int
+            d.BallboxSetSDFBakeGradient.argtypes = [WP, C.c_int]; d.BallboxSetSDFBakeGradient.restype = None
             d.BallboxSdfInUse.argtypes = [WP]; d.BallboxSdfInUse.restype = C.c_int
             d.BallboxSetSolverSchedule.argtypes = [WP, C.c_int]
             d.BallboxSetSolverSchedule.restype = None

@@ -169,7 +169,7 @@ struct BbxDev {
     int wb_attr_set;             // dynamic shared memory attribute of the per-world solve kernel was set
 
     // baked SDF (host function sampled on a grid, bbx_dev_set_baked_sdf)
-    float *sdf_grid; int sdf_nx, sdf_ny, sdf_nz; float sdf_ox, sdf_oy, sdf_oz, sdf_inv_cell;
+    float *sdf_grid; int sdf_ch; int sdf_nx, sdf_ny, sdf_nz; float sdf_ox, sdf_oy, sdf_oz, sdf_inv_cell;
 
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy

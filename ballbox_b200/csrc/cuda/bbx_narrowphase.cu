@@ -107,24 +107,47 @@ __global__ void __launch_bounds__(128) k_bb_manifold(BbxDev dv, float tol, float
 // ---------------------------------------------------------------------------
 // SDF probing
 // ---------------------------------------------------------------------------
-struct SdfDesc { int id; float prm[8]; float eps; const float* grid; int nx, ny, nz; float ox, oy, oz, inv_cell; };
+struct SdfDesc { int id; float prm[8]; float eps; const float* grid; int ch; int nx, ny, nz; float ox, oy, oz, inv_cell; };
 
 // baked host SDF: trilinear interpolation of the grid samples, coordinates clamped to the baked region.
 // Plain f32 operations in a fixed order (compiled with -fmad=false like everything else): deterministic.
-__device__ __forceinline__ float sdf_baked(const SdfDesc& s, float3 p)
+struct BakedCell { size_t base, sy, sz; float fx, fy, fz; };
+__device__ __forceinline__ BakedCell baked_cell(const SdfDesc& s, float3 p)
 {
     float ux = (p.x - s.ox) * s.inv_cell, uy = (p.y - s.oy) * s.inv_cell, uz = (p.z - s.oz) * s.inv_cell;
     ux = fminf(fmaxf(ux, 0.0f), (float)(s.nx - 1)); uy = fminf(fmaxf(uy, 0.0f), (float)(s.ny - 1)); uz = fminf(fmaxf(uz, 0.0f), (float)(s.nz - 1));
     int ix = min((int)ux, s.nx - 2), iy = min((int)uy, s.ny - 2), iz = min((int)uz, s.nz - 2);
-    float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
-    const float* g = s.grid + ((size_t)iz * s.ny + iy) * s.nx + ix;
-    const size_t sy = (size_t)s.nx, sz = (size_t)s.nx * s.ny;
-    float v000 = __ldg(g), v100 = __ldg(g + 1), v010 = __ldg(g + sy), v110 = __ldg(g + sy + 1);
-    float v001 = __ldg(g + sz), v101 = __ldg(g + sz + 1), v011 = __ldg(g + sz + sy), v111 = __ldg(g + sz + sy + 1);
-    float a00 = v000 + (v100 - v000) * fx, a10 = v010 + (v110 - v010) * fx;
-    float a01 = v001 + (v101 - v001) * fx, a11 = v011 + (v111 - v011) * fx;
-    float b0 = a00 + (a10 - a00) * fy, b1 = a01 + (a11 - a01) * fy;
-    return b0 + (b1 - b0) * fz;
+    BakedCell c;
+    c.fx = ux - (float)ix; c.fy = uy - (float)iy; c.fz = uz - (float)iz;
+    c.base = ((size_t)iz * s.ny + iy) * s.nx + ix; c.sy = (size_t)s.nx; c.sz = (size_t)s.nx * s.ny;
+    return c;
+}
+__device__ __forceinline__ float trilerp(const BakedCell& c, float v000, float v100, float v010, float v110,
+                                         float v001, float v101, float v011, float v111)
+{
+    float a00 = v000 + (v100 - v000) * c.fx, a10 = v010 + (v110 - v010) * c.fx;
+    float a01 = v001 + (v101 - v001) * c.fx, a11 = v011 + (v111 - v011) * c.fx;
+    float b0 = a00 + (a10 - a00) * c.fy, b1 = a01 + (a11 - a01) * c.fy;
+    return b0 + (b1 - b0) * c.fz;
+}
+__device__ __forceinline__ float sdf_baked(const SdfDesc& s, float3 p)
+{
+    const BakedCell c = baked_cell(s, p);
+    const size_t k = (size_t)s.ch;                      // 1: distance only; 4: distance + gradient, distance first
+    const float* g = s.grid + c.base * k;
+    return trilerp(c, __ldg(g), __ldg(g + k), __ldg(g + c.sy * k), __ldg(g + (c.sy + 1) * k),
+                   __ldg(g + c.sz * k), __ldg(g + (c.sz + 1) * k), __ldg(g + (c.sz + c.sy) * k), __ldg(g + (c.sz + c.sy + 1) * k));
+}
+// gradient channels (the reference's central differences of the host function, sampled at the grid nodes)
+__device__ __forceinline__ float3 sdf_baked_gradient(const SdfDesc& s, float3 p)
+{
+    const BakedCell c = baked_cell(s, p);
+    const float4* g = reinterpret_cast<const float4*>(s.grid) + c.base;
+    float4 v000 = __ldg(g), v100 = __ldg(g + 1), v010 = __ldg(g + c.sy), v110 = __ldg(g + c.sy + 1);
+    float4 v001 = __ldg(g + c.sz), v101 = __ldg(g + c.sz + 1), v011 = __ldg(g + c.sz + c.sy), v111 = __ldg(g + c.sz + c.sy + 1);
+    return f3(trilerp(c, v000.y, v100.y, v010.y, v110.y, v001.y, v101.y, v011.y, v111.y),
+              trilerp(c, v000.z, v100.z, v010.z, v110.z, v001.z, v101.z, v011.z, v111.z),
+              trilerp(c, v000.w, v100.w, v010.w, v110.w, v001.w, v101.w, v011.w, v111.w));
 }
 
 __device__ __forceinline__ float sdf_at(const SdfDesc& s, float3 p)
@@ -135,6 +158,7 @@ __device__ __forceinline__ float sdf_at(const SdfDesc& s, float3 p)
 
 __device__ __forceinline__ float3 sdf_normal(const SdfDesc& s, float3 p)               // SDF_EstimateNormal :2318-2331
 {
+    if (s.id == BBX_SDF_ID_BAKED && s.ch == 4) return v3norm(sdf_baked_gradient(s, p));
     float e = s.eps;
     float3 ex = f3(e, 0.0f, 0.0f), ey = f3(0.0f, e, 0.0f), ez = f3(0.0f, 0.0f, e);
     float nx = (sdf_at(s, v3add(p, ex)) - sdf_at(s, v3sub(p, ex))) / (2.0f * e);
@@ -215,7 +239,7 @@ int bbx_stage_narrowphase(BbxDev* d, const BbxStepParams* p)
     if (p->sdf_id != BBX_SDF_NONE) {
         SdfDesc s; s.id = p->sdf_id; s.eps = p->settings.sdf_normal_epsilon;
         for (int k = 0; k < 8; k++) s.prm[k] = p->sdf_params[k];
-        s.grid = d->sdf_grid; s.nx = d->sdf_nx; s.ny = d->sdf_ny; s.nz = d->sdf_nz;
+        s.grid = d->sdf_grid; s.ch = d->sdf_ch; s.nx = d->sdf_nx; s.ny = d->sdf_ny; s.nz = d->sdf_nz;
         s.ox = d->sdf_ox; s.oy = d->sdf_oy; s.oz = d->sdf_oz; s.inv_cell = d->sdf_inv_cell;
         if (s.id == BBX_SDF_ID_BAKED && !s.grid)
             return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "baked SDF selected but no grid was uploaded", __FILE__, __LINE__);

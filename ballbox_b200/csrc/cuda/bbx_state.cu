@@ -169,18 +169,18 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
     free(d);
 }
 
-extern "C" int bbx_dev_set_baked_sdf(BbxDev* d, const float* values, int nx, int ny, int nz, const float origin[3], float cell)
+extern "C" int bbx_dev_set_baked_sdf(BbxDev* d, const float* values, int channels, int nx, int ny, int nz, const float origin[3], float cell)
 {
-    if (!d || !values || !origin || nx < 2 || ny < 2 || nz < 2 || !(cell > 0.0f)) return BBX_ERR_BAD_ARGUMENT;
+    if (!d || !values || !origin || nx < 2 || ny < 2 || nz < 2 || !(cell > 0.0f) || (channels != 1 && channels != 4)) return BBX_ERR_BAD_ARGUMENT;
     if (d->has_err) return BBX_ERR_STICKY;
     BBX_CUDA(d, cudaSetDevice(d->device));
     BBX_CUDA(d, cudaStreamSynchronize(d->stream));           // no step may still be reading the old grid
     if (d->sdf_grid) { cudaFree(d->sdf_grid); d->sdf_grid = NULL; }
-    size_t n = (size_t)nx * ny * nz;
+    size_t n = (size_t)nx * ny * nz * (size_t)channels;
     BBX_CUDA(d, cudaMalloc((void**)&d->sdf_grid, n * sizeof(float)));
     BBX_CUDA(d, cudaMemcpyAsync(d->sdf_grid, values, n * sizeof(float), cudaMemcpyHostToDevice, d->stream));
     BBX_CUDA(d, cudaStreamSynchronize(d->stream));           // `values` may be freed by the caller
-    d->sdf_nx = nx; d->sdf_ny = ny; d->sdf_nz = nz;
+    d->sdf_nx = nx; d->sdf_ny = ny; d->sdf_nz = nz; d->sdf_ch = channels;
     d->sdf_ox = origin[0]; d->sdf_oy = origin[1]; d->sdf_oz = origin[2]; d->sdf_inv_cell = 1.0f / cell;
     return 0;
 }

@@ -42,6 +42,7 @@ struct PhysicsWorldBatch {
     int sdf_id; float sdf_params[8];
     /* baked host SDF (ballbox_ext.h): region, resolution, and which function the device grid holds */
     int bake_region_set, bake_res, bake_dirty;
+    int bake_no_gradient; float baked_eps;      /* gradient channels are sampled with the sdf_normal_epsilon of bake time */
     float bake_lo[3], bake_hi[3];
     SDFFunction baked_fn;
     int uploaded, forces_dirty, n_callbacks, cb_dirty, timing;
@@ -309,6 +310,13 @@ void BallboxSetSDFBakeRegion(PhysicsWorld* world, Vec3 lo, Vec3 hi, int resoluti
     b->bake_region_set = 1; b->bake_res = resolution; b->bake_dirty = 1;
     b->bake_lo[0] = lo.x; b->bake_lo[1] = lo.y; b->bake_lo[2] = lo.z;
     b->bake_hi[0] = hi.x; b->bake_hi[1] = hi.y; b->bake_hi[2] = hi.z;
+}
+
+void BallboxSetSDFBakeGradient(PhysicsWorld* world, int on)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return;
+    p->batch->bake_no_gradient = on ? 0 : 1; p->batch->bake_dirty = 1;
 }
 
 int BallboxBakeSDF(PhysicsWorld* world)
@@ -663,21 +671,30 @@ static int bake_sdf(struct PhysicsWorldBatch* b)
         long long total = 1;
         for (int a = 0; a < 3; a++) { n[a] = (int)ceilf((hi[a] - lo[a]) / cell) + 1; if (n[a] < 2) n[a] = 2; total *= n[a]; }
         if (total <= (1ll << 26) || res <= 2) break;
-        res = res * 3 / 4;                              /* keep the grid below 64 M samples (256 MB) */
+        res = res * 3 / 4;                              /* keep the grid below 64 M nodes (256 MB, 1 GB with gradients) */
     }
     size_t count = (size_t)n[0] * n[1] * n[2];
-    float* values = (float*)malloc(count * sizeof(float));
+    const int ch = b->bake_no_gradient ? 1 : 4;
+    float* values = (float*)malloc(count * sizeof(float) * (size_t)ch);
     if (!values) { batch_fail(b, "BallboxBakeSDF: out of host memory"); return BBX_ERR_BAD_ARGUMENT; }
+    const float eps = w0->settings.sdf_normal_epsilon;
     size_t at = 0;
     for (int k = 0; k < n[2]; k++)
         for (int j = 0; j < n[1]; j++)
             for (int i = 0; i < n[0]; i++) {
                 Vec3 p = { lo[0] + (float)i * cell, lo[1] + (float)j * cell, lo[2] + (float)k * cell };
                 values[at++] = fn(p);
+                if (ch == 4) {
+                    /* the three components of SDF_EstimateNormal before normalisation (ballbox.h:2325-2327) */
+                    Vec3 ex = { eps, 0.0f, 0.0f }, ey = { 0.0f, eps, 0.0f }, ez = { 0.0f, 0.0f, eps };
+                    values[at++] = (fn(Vec3Add(p, ex)) - fn(Vec3Sub(p, ex))) / (2.0f * eps);
+                    values[at++] = (fn(Vec3Add(p, ey)) - fn(Vec3Sub(p, ey))) / (2.0f * eps);
+                    values[at++] = (fn(Vec3Add(p, ez)) - fn(Vec3Sub(p, ez))) / (2.0f * eps);
+                }
             }
-    rc = batch_check_dev(b, bbx_dev_set_baked_sdf(b->dev, values, n[0], n[1], n[2], lo, cell));
+    rc = batch_check_dev(b, bbx_dev_set_baked_sdf(b->dev, values, ch, n[0], n[1], n[2], lo, cell));
     free(values);
-    if (!rc) { b->baked_fn = fn; b->bake_dirty = 0; }
+    if (!rc) { b->baked_fn = fn; b->bake_dirty = 0; b->baked_eps = eps; }
     return rc;
 }
 
@@ -693,7 +710,8 @@ static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, in
             /* reference condition is usesSDF && SDFCollider (ballbox.h:2075); a host pointer cannot run on the GPU:
              * it is baked once into a grid (ballbox_ext.h) */
             if (w0->SDFCollider) {
-                if (b->baked_fn != w0->SDFCollider || b->bake_dirty) { int rc = bake_sdf(b); if (rc) return rc; }
+                if (b->baked_fn != w0->SDFCollider || b->bake_dirty ||
+                    (!b->bake_no_gradient && b->baked_eps != w0->settings.sdf_normal_epsilon)) { int rc = bake_sdf(b); if (rc) return rc; }
                 p->sdf_id = BBX_SDF_BAKED;
             }
         } else {

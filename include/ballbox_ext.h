@@ -42,8 +42,9 @@ void        BallboxClearError(PhysicsWorld* world);
  * function is BAKED ONCE: sampled on a regular grid over the bake region and uploaded, and
  * the kernels read it back with trilinear interpolation (f32, fixed operation order).  A
  * baked SDF is an approximation: the error is the interpolation error of fn at the grid
- * spacing (O(h^2 |f''|); exact for functions that are linear in x, y and z), and normals are the
- * reference's central differences of the interpolant.  Outside the region the nearest grid
+ * spacing (O(h^2 |f''|); exact for functions that are linear in x, y and z); normals interpolate the
+ * reference's central differences sampled at the grid nodes (BallboxSetSDFBakeGradient; accuracy table:
+ * profiles/r01_sdf_bake.md).  Outside the region the nearest grid
  * value is used.  For bit-exact results select an SDF that exists as device code with
  * UseSDFDevice instead (it takes precedence over a host pointer). ---------------------- */
 #define BBX_SDF_NONE        0
@@ -59,6 +60,11 @@ void UseSDFDevice(PhysicsWorld* world, int sdf_id, const float* params8);
  * every side, 192 cells along the longest axis.  Calling it (or UseSDF with another function)
  * schedules a new bake. */
 void BallboxSetSDFBakeRegion(PhysicsWorld* world, Vec3 lo, Vec3 hi, int resolution);
+/* Gradient channels (default on): the bake also samples the three central differences of SDF_EstimateNormal
+ * (ballbox.h:2318-2331, epsilon = settings.sdf_normal_epsilon at bake time; a later change of that setting re-bakes)
+ * and contact normals interpolate THEM, error O(h^2), instead of differencing the interpolated distance, error O(h).
+ * Costs 4x the grid memory and 7 calls of fn per node.  0 turns them off. */
+void BallboxSetSDFBakeGradient(PhysicsWorld* world, int on);
 /* Bake now instead of at the next step; returns 0 or an error code (message: BallboxGetLastError). */
 int  BallboxBakeSDF(PhysicsWorld* world);
 int  BallboxSdfInUse(PhysicsWorld* world);      /* BBX_SDF_* the next step will use */

@@ -61,8 +61,11 @@ typedef struct {
     int   want_callbacks;          /* collect callback events                              */
 } BbxStepParams;
 
-/* baked SDF: nx*ny*nz samples (x fastest) of a host function at origin + (i,j,k)*cell; replaces any earlier bake */
-int  bbx_dev_set_baked_sdf(BbxDev* dev, const float* values, int nx, int ny, int nz, const float origin[3], float cell);
+/* baked SDF: nx*ny*nz samples (x fastest) of a host function at origin + (i,j,k)*cell; replaces any earlier bake.
+ * channels = 1: the distance; channels = 4: distance followed by the three central differences of
+ * SDF_EstimateNormal (ballbox.h:2325-2327) at the node, which the kernels interpolate instead of differencing the
+ * interpolated distance */
+int  bbx_dev_set_baked_sdf(BbxDev* dev, const float* values, int channels, int nx, int ny, int nz, const float origin[3], float cell);
 
 int  bbx_device_count(void);
 int  bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_spheres, int cap_boxes,

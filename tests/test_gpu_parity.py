@@ -244,6 +244,49 @@ def test_host_sdf_python_callback_is_baked_wavy(product, truth):
     assert len(g.constraints()) > 5 and abs(len(g.constraints()) - len(c.constraints())) <= 4
 
 
+def test_baked_sdf_gradient_channels_sharpen_normals(product):
+    """Three worlds reach the same state with the exact device SDF; two of them then switch to a bake of the same
+    function (host pointer only) and take one more step.  Penetrations agree with the exact ones within the
+    interpolation bound; with gradient channels (default) the contact normals are an order of magnitude closer than
+    with differences of the interpolated distance (tools/sdf_bake_report.py, profiles/r01_sdf_bake.md)."""
+    worlds = [product.build_scene(bb.SCENE_SDF, 600, 77) for _ in range(3)]
+    for w in worlds:
+        for _ in range(90):
+            w.step(DT)
+    sa, ba = worlds[0].sphere_arrays(), worlds[0].box_arrays()
+    ext = np.concatenate([sa["radius"], np.linalg.norm(ba["size"], axis=1)])[:, None]
+    pos = np.concatenate([sa["pos"], ba["pos"]])
+    lo, hi = (pos - ext).min(0) - 1.0, (pos + ext).max(0) + 1.0
+    h = float((hi - lo).max()) / 192
+    for w, grad in ((worlds[1], 0), (worlds[2], 1)):
+        product.dll.UseSDFDevice(w.ptr, 0, None)
+        product.dll.BallboxSetSDFBakeGradient(w.ptr, grad)
+        product.dll.BallboxSetSDFBakeRegion(w.ptr, bb.Vec3(*map(float, lo)), bb.Vec3(*map(float, hi)), 193)
+    lists = []
+    for w in worlds:
+        w.step(DT)
+        k = w.constraints().copy()
+        lists.append(k[k["b_type"] == 2])
+    assert product.dll.BallboxSdfInUse(worlds[0].ptr) == bb.SDF_WAVY_DET and product.dll.BallboxSdfInUse(worlds[2].ptr) == 5
+    exact = {}
+    for r in lists[0]:
+        exact.setdefault((int(r["a_type"]), int(r["a_index"])), []).append(r)
+    worst = []
+    for baked in lists[1:]:
+        ang, dpen = [], []
+        for r in baked:
+            cands = exact.get((int(r["a_type"]), int(r["a_index"])), [])
+            d = [float(np.abs(c["point"].astype(np.float64) - r["point"]).max()) for c in cands]
+            if not d or min(d) > 0.05:
+                continue
+            c = cands[int(np.argmin(d))]
+            dpen.append(abs(float(c["penetration"]) - float(r["penetration"])))
+            ang.append(np.degrees(np.arccos(np.clip(np.dot(c["normal"].astype(np.float64), r["normal"]), -1, 1))))
+        assert len(ang) > 100 and max(dpen) <= 2.5 * h * h / 8, (len(ang), max(dpen), h)
+        worst.append(max(ang))
+    assert worst[1] < 0.2 * worst[0] and worst[1] < 1.0, worst
+
+
 def test_contact_overflow_is_reported(product):
     w = product.build_scene(bb.SCENE_BALLS, 3000, 2, max_collisions=64)
     with pytest.raises(bb.BallboxError, match="overflow|max_collisions"):
