@@ -152,6 +152,8 @@ class BallboxLib:
         d = self.dll
         d.CreatePhysicsWorld.restype = WP
         d.CreatePhysicsWorld.argtypes = [C.c_int, C.c_int, C.c_int]
+        if hasattr(d, "OracleSetWarmStarting"):          # the C restatement's definition of the warm-start extension
+            d.OracleSetWarmStarting.argtypes = [WP, C.c_float]; d.OracleSetWarmStarting.restype = None
         d.DestroyPhysicsWorld.argtypes = [WP]
         d.DestroyPhysicsWorld.restype = None
         d.PhysicsStep.argtypes = [WP, C.c_float]
@@ -220,6 +222,7 @@ class BallboxLib:
             d.BallboxSetSDFBakeRegion.restype = None
             d.BallboxBakeSDF.argtypes = [WP]; d.BallboxBakeSDF.restype = C.c_int
             d.BallboxSetSDFBakeGradient.argtypes = [WP, C.c_int]; d.BallboxSetSDFBakeGradient.restype = None
+            d.BallboxSetWarmStarting.argtypes = [WP, C.c_float]; d.BallboxSetWarmStarting.restype = None
             d.BallboxSdfInUse.argtypes = [WP]; d.BallboxSdfInUse.restype = C.c_int
             d.BallboxSetSolverSchedule.argtypes = [WP, C.c_int]
             d.BallboxSetSolverSchedule.restype = None
@@ -323,6 +326,10 @@ class World:
         thunk = OnCollision(fn)
         self._keep.append(thunk)
         self.lib.dll.SetBoxCollisionCallback(self.ptr, index, thunk)
+
+    def set_warm_starting(self, factor):
+        d = self.lib.dll
+        (d.BallboxSetWarmStarting if self.lib.product else d.OracleSetWarmStarting)(self.ptr, factor)
 
     def use_sdf(self, sdf_id):
         self.lib.dll.BbxSceneUseSdf(self.ptr, sdf_id)

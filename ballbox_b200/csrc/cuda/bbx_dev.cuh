@@ -130,6 +130,9 @@ struct BbxDev {
     int  *queue_k[BBX_NCLS];                     // node ids (first contact of the run)
     int4 *Nd_k[BBX_NCLS];                        // (first M slot, constraint count, dynamic gid A, dynamic gid B)
     int *slot_of;                                // cap_contacts: contact -> M slot
+    // warm starting (extension): open-addressing table (body A, body B, k) -> final impulses of the previous step
+    unsigned long long *warm_key; float4 *warm_val; unsigned int warm_mask;
+    int *warm_epoch;                             // per world: bumped by a world reset, stored with every entry (stale entries miss)
     int *level_count;                            // (cap_levels + 4) * BBX_NCLS
     // ---- barrier-free flow solver (single large world, bbx_solver.cu k_solve_flow) ----
     // one 64-byte record per body, every 8-byte word = (float data, int version):
@@ -194,6 +197,22 @@ struct BbxDev {
 };
 
 // ---------------------------------------------------------------------------
+// warm-start table: key = (gid A, gid B + 2, index k of the contact inside its pair's run)
+// ---------------------------------------------------------------------------
+#define BBX_WARM_EMPTY 0xffffffffffffffffull
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long warm_key_of(int a, int b, int k)
+{
+    return ((unsigned long long)(unsigned int)a << 36) | ((unsigned long long)(unsigned int)(b + 2) << 8) | (unsigned long long)(k & 255);
+}
+__device__ __forceinline__ unsigned int warm_hash(unsigned long long x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (unsigned int)x;
+}
+#endif
+
+// ---------------------------------------------------------------------------
 // error handling / launch accounting
 // ---------------------------------------------------------------------------
 int  bbx_fail(BbxDev* d, int code, const char* what, const char* file, int line);
@@ -220,6 +239,8 @@ int bbx_stage_positions_only(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_sleep_only(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_integrate_positions(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_collect_events(BbxDev* d, const BbxStepParams* p);
+int bbx_warm_ensure(BbxDev* d);
+int bbx_stage_warm_save(BbxDev* d, const BbxStepParams* p);
 int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out);
 
 #ifdef __CUDACC__

@@ -57,7 +57,9 @@ __device__ __forceinline__ float inv_mass_sum(float imA, float imB, float3 rA, f
 //         masses, bias and accumulated impulses are the ones found in the host records
 // per_contact: every contact is its own scheduling node (flow solver), one half per body:
 // node[2c] = (dynamic gid A or -1, position in A's chain, length of A's chain, successor on A), node[2c+1] = same for B
-__global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, float allowed, float dt, int mode, int per_contact)
+// warm > 0 (extension, mode 0 only): a contact found in the previous step's table starts from warm x its final impulses
+// and is flagged (c_nrm.w = 1) for k_warm_apply
+__global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, float allowed, float dt, int mode, int per_contact, float warm)
 {
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -99,8 +101,26 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         L[0] = make_float4(nrm.x, nrm.y, nrm.z, bias);
         L[1] = make_float4(rA.x, rA.y, rA.z, mN);
         L[2] = make_float4(rB.x, rB.y, rB.z, mT0);
-        if (mode == 0) L[3] = make_float4(0.0f, 0.0f, 0.0f, mT1);                       // impulses start at 0 (:1203-1206)
-        else           L[3] = make_float4(keep.x, keep.y, keep.z, mT1);
+        if (mode == 0 && warm > 0.0f) {
+            const unsigned long long key = warm_key_of(a, b, RUN_K(id.z));
+            unsigned int h = warm_hash(key) & dv.warm_mask;
+            float4 prev = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            bool hit = false;
+            for (unsigned int probe = 0; probe <= dv.warm_mask; probe++, h = (h + 1) & dv.warm_mask) {
+                const unsigned long long kk = dv.warm_key[h];
+                if (kk == BBX_WARM_EMPTY) break;
+                if (kk == key) {
+                    prev = dv.warm_val[h];
+                    const int wa = a < dv.NS ? a / dv.cap_s : (a - dv.NS) / dv.cap_b;
+                    hit = __float_as_int(prev.w) == dv.warm_epoch[wa];              // entries of a world that was reset since are stale
+                    break;
+                }
+            }
+            L[3] = hit ? make_float4(warm * prev.x, warm * prev.y, warm * prev.z, mT1) : make_float4(0.0f, 0.0f, 0.0f, mT1);
+            reinterpret_cast<float*>(&dv.c_nrm[c])[3] = hit ? 1.0f : 0.0f;
+        }
+        else if (mode == 0) L[3] = make_float4(0.0f, 0.0f, 0.0f, mT1);                  // impulses start at 0 (:1203-1206)
+        else                L[3] = make_float4(keep.x, keep.y, keep.z, mT1);
         dv.slot_of[c] = -1;
         if (per_contact) {
             dv.node[2 * (size_t)c] = make_int4(dynA ? a : -1, 0, 0, -1);
@@ -229,7 +249,8 @@ __device__ __forceinline__ void adj_write_links(const BbxDev& dv, int x, const u
     }
 }
 
-__global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, int flow_records)
+// keep_sorted: the sorted list is written back (k_warm_apply walks it)
+__global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, int flow_records, int keep_sorted)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     bool has = false;
@@ -250,6 +271,7 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                 }
                 atomicSub(&dv.indeg[ADJ_NODE(loc[0])], 1);         // first node of this body has no predecessor here
                 adj_write_links(dv, x, loc, d, per_contact);
+                if (keep_sorted) for (int i = 0; i < d; i++) lst[i] = loc[i];
             } else {
                 for (int i = 1; i < d; i++) {
                     unsigned long long v = lst[i];
@@ -260,7 +282,7 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                 atomicSub(&dv.indeg[ADJ_NODE(lst[0])], 1);
                 adj_write_links(dv, x, lst, d, per_contact);
             }
-            if (per_contact && flow_records) flow_init_body(dv, x);    // the body's versioned record starts at version 0
+            if (per_contact && flow_records && !keep_sorted) flow_init_body(dv, x);    // the body's versioned record starts at version 0
             wake_body(dv, x);              // :1373-1376, :1402-1405: every impulse application wakes the body, even a zero one
         }
     }
@@ -420,6 +442,49 @@ __device__ __forceinline__ void apply_impulse(BodyState& s, float3 J, float3 L)
         float3 dl = v3mul(loc, s.iI);
         s.w = v3add(s.w, qrot_pre(u, s.k1, s.k2, dl));
     }
+}
+
+// Warm starting (extension, ballbox_ext.h): before the first sweep every contact that was matched with the previous
+// step applies its starting impulses, A receiving -X and B +X for X = n*jn, then t1*jt0 and t2*jt1 when friction > 0,
+// constraint after constraint in emission order.  An application only touches the body it is applied to, so walking
+// every body's own chain (sorted by k_adj_link) performs, per body, exactly the operations of that sequential pass.
+__global__ void __launch_bounds__(128) k_warm_apply(BbxDev dv, int per_contact, int flow_records, float friction)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= dv.N) return;
+    const int s0 = dv.adj_start[x], d = dv.adj_start[x + 1] - s0;
+    if (d <= 0) return;
+    BodyState S;
+    load_body(dv, x, S);
+    for (int i = 0; i < d; i++) {
+        const unsigned long long e = dv.adj[s0 + i];
+        const int c0 = ADJ_NODE(e), side = ADJ_SIDE(e);
+        const int m = per_contact ? 1 : RUN_LEN(dv.c_ids[c0].z);
+        for (int j = 0; j < m; j++) {
+            const int c = c0 + j;
+            if (dv.c_nrm[c].w == 0.0f) continue;                       // not matched: starts from zero, nothing applied
+            const float4* L = dv.L + 4 * (size_t)c;
+            const float4 l0 = L[0], lr = L[side ? 2 : 1], l3 = L[3];
+            const float3 n = xyz(l0), r = xyz(lr);
+            float3 t1, t2;
+            tangents_of(n, t1, t2);
+            {
+                float3 P = v3scale(n, l3.x);
+                if (!side) P = v3scale(P, -1.0f);
+                apply_impulse(S, P, v3cross(r, P));
+            }
+            if (friction > 0.0f) {
+                float3 T = v3scale(t1, l3.y);
+                if (!side) T = v3scale(T, -1.0f);
+                apply_impulse(S, T, v3cross(r, T));
+                T = v3scale(t2, l3.z);
+                if (!side) T = v3scale(T, -1.0f);
+                apply_impulse(S, T, v3cross(r, T));
+            }
+        }
+    }
+    store_body(dv, x, S);
+    if (per_contact && flow_records) flow_init_body(dv, x);
 }
 
 // one constraint, one Gauss-Seidel visit (:1414-1488) on bodies held in registers
@@ -1665,6 +1730,22 @@ static bool use_world_groups(const BbxDev* d, int imported, int schedule)
     return !imported && d->n_worlds >= 16 && schedule == BBX_SOLVER_EXACT && !d->no_groups;
 }
 
+// warm-start table, allocated at first use: at most half full
+int bbx_warm_ensure(BbxDev* d)
+{
+    if (d->warm_key) return 0;
+    unsigned long long cap = 1024;
+    while (cap < 2ull * (unsigned long long)d->cap_contacts) cap <<= 1;
+    if (cap > (1ull << 31)) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "warm starting: contact capacity too large", __FILE__, __LINE__);
+    BBX_CUDA(d, cudaMalloc((void**)&d->warm_key, sizeof(unsigned long long) * cap));
+    BBX_CUDA(d, cudaMalloc((void**)&d->warm_val, sizeof(float4) * cap));
+    BBX_CUDA(d, cudaMalloc((void**)&d->warm_epoch, sizeof(int) * (size_t)d->n_worlds));
+    d->warm_mask = (unsigned int)(cap - 1);
+    BBX_CUDA(d, cudaMemsetAsync(d->warm_key, 0xff, sizeof(unsigned long long) * cap, d->stream));
+    BBX_CUDA(d, cudaMemsetAsync(d->warm_epoch, 0, sizeof(int) * (size_t)d->n_worlds, d->stream));
+    return 0;
+}
+
 // touched-body statistics and sanity for the host
 int bbx_stage_solve(BbxDev* d, const BbxStepParams* p) { return bbx_stage_solve_ex(d, p, 0, p->settings.solver_iterations, 0); }
 
@@ -1678,12 +1759,15 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     const int groups = (!flow && use_world_groups(d, imported, p->solver_schedule)) ? 1 : 0;
     const int per_contact = flow | groups;                 // every constraint is its own node
     BBX_CUDA(d, cudaMemsetAsync(d->deg, 0, sizeof(int) * ((size_t)d->N + 1), d->stream));
-    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, per_contact);
+    const float warm = (presolve_mode == 0 && !imported && p->warm_start > 0.0f) ? p->warm_start : 0.0f;
+    if (warm > 0.0f) { int rcw = bbx_warm_ensure(d); if (rcw) return rcw; }
+    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, per_contact, warm);
     if (iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);
     if (rc) return rc;
     BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0), per_contact);
-    BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow);
+    BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, warm > 0.0f ? 1 : 0);
+    if (warm > 0.0f) BBX_LAUNCH(d, k_warm_apply, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, p->settings.friction);
     d->last_flow = flow; d->last_per_contact = per_contact;
     if (flow) {
         BBX_LAUNCH(d, k_frontier_flow, G, 256, 0, *d);

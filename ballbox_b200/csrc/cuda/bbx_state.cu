@@ -156,7 +156,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
         d->sdf_grid, d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
-        d->sort_hist, d->sort_hist_scan };
+        d->sort_hist, d->sort_hist_scan, d->warm_key, d->warm_val, d->warm_epoch };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
     if (d->ctr_host) cudaFreeHost(d->ctr_host);
@@ -564,6 +564,7 @@ __global__ void __launch_bounds__(256) k_restore_worlds(BbxDev dv, int n)
 {
     int w = dv.reset_ids[blockIdx.x];
     if (blockIdx.x >= n || w < 0 || w >= dv.n_worlds) return;
+    if (threadIdx.x == 0 && dv.warm_epoch) dv.warm_epoch[w]++;          // the world's remembered impulses are stale now
     for (int i = threadIdx.x; i < dv.cap_s + dv.cap_b; i += blockDim.x) {
         bool box = i >= dv.cap_s;
         int g = box ? dv.NS + w * dv.cap_b + (i - dv.cap_s) : w * dv.cap_s + i;

@@ -78,6 +78,7 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
         if (q.want_callbacks && (rc = bbx_stage_collect_events(d, &q))) return rc;
         bbx_timing_mark(d, 3);
         if ((rc = bbx_stage_solve(d, &q))) return rc;                  // stage 4 (marks 4 inside, before the solve kernel)
+        if (q.warm_start > 0.0f && (rc = bbx_stage_warm_save(d, &q))) return rc;
         bbx_timing_mark(d, 5);
         if ((rc = bbx_stage_integrate_positions(d, &q))) return rc;    // stages 5-6
         bbx_timing_mark(d, 6);
@@ -104,6 +105,29 @@ __device__ __forceinline__ void split_gid(const BbxDev& dv, int g, int& type, in
 struct KeyBits { int wb, ib, jb; };
 static int bits_for(int n) { int b = 1; while ((1ll << b) < n) b++; return b; }
 
+// accumulated impulses of contact c as the step left them
+__device__ __forceinline__ void final_impulses(const BbxDev& dv, int c, int4 id, float4 l3, int solved, float friction,
+                                               float& jn, float& jt0, float& jt1)
+{
+    // not scheduled (or no sweep ran): the accumulated impulses are whatever the record held (0 in PhysicsStep)
+    jn = l3.x; jt0 = l3.y; jt1 = l3.z;
+    int slot = solved ? dv.slot_of[c] : -1;
+    if (slot >= 0 && dv.last_flow) {
+        // flow solver: (value, tag) words in queue order
+        ulonglong2 i0 = dv.fimp[2 * (size_t)slot], i1 = dv.fimp[2 * (size_t)slot + 1];
+        jn = __uint_as_float((unsigned int)i0.x); jt0 = __uint_as_float((unsigned int)i0.y); jt1 = __uint_as_float((unsigned int)i1.x);
+    }
+    else if (slot >= 0) { float4 m3 = dv.M[3 * (size_t)dv.cap_contacts + slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
+    else if (solved && friction > 0.0f) {
+        // a constraint between two non-dynamic bodies is never scheduled, but the reference still
+        // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477).
+        // (In the block-per-world path scheduled constraints keep their impulses in L: slot < 0 too.)
+        int4 hd = dv.node[2 * (size_t)(c - RUN_K(id.z))];
+        if (dv.last_per_contact) hd.y = dv.node[2 * (size_t)(c - RUN_K(id.z)) + 1].x;   // per-constraint layout: one half per body
+        if (hd.x < 0 && hd.y < 0) { jt0 = -0.0f; jt1 = -0.0f; }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactConstraint* out, unsigned long long* keys,
                                                             float restitution, float friction, int solved, KeyBits kb)
 {
@@ -119,23 +143,8 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         if (fabsf(n3.x) >= 0.57735f) t1 = f3(n3.y, -n3.x, 0.0f); else t1 = f3(0.0f, n3.z, -n3.y);
         t1 = v3norm(t1);
         t2 = v3cross(n3, t1);
-        // not scheduled (or no sweep ran): the accumulated impulses are whatever the record held (0 in PhysicsStep)
-        float jn = l3.x, jt0 = l3.y, jt1 = l3.z;
-        int slot = solved ? dv.slot_of[c] : -1;
-        if (slot >= 0 && dv.last_flow) {
-            // flow solver: (value, tag) words in queue order
-            ulonglong2 i0 = dv.fimp[2 * (size_t)slot], i1 = dv.fimp[2 * (size_t)slot + 1];
-            jn = __uint_as_float((unsigned int)i0.x); jt0 = __uint_as_float((unsigned int)i0.y); jt1 = __uint_as_float((unsigned int)i1.x);
-        }
-        else if (slot >= 0) { float4 m3 = dv.M[3 * (size_t)dv.cap_contacts + slot]; jn = m3.x; jt0 = m3.y; jt1 = m3.z; }
-        else if (solved && friction > 0.0f) {
-            // a constraint between two non-dynamic bodies is never scheduled, but the reference still
-            // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477).
-            // (In the block-per-world path scheduled constraints keep their impulses in L: slot < 0 too.)
-            int4 hd = dv.node[2 * (size_t)(c - RUN_K(id.z))];
-            if (dv.last_per_contact) hd.y = dv.node[2 * (size_t)(c - RUN_K(id.z)) + 1].x;   // per-constraint layout: one half per body
-            if (hd.x < 0 && hd.y < 0) { jt0 = -0.0f; jt1 = -0.0f; }
-        }
+        float jn, jt0, jt1;
+        final_impulses(dv, c, id, l3, solved, friction, jn, jt0, jt1);
         ContactConstraint r;
         r.bodyA_type = ta; r.bodyA_index = la; r.bodyB_type = tb; r.bodyB_index = lb;
         r.contact_point.x = pt.x; r.contact_point.y = pt.y; r.contact_point.z = pt.z;
@@ -155,6 +164,39 @@ __global__ void __launch_bounds__(256) k_export_constraints(BbxDev dv, ContactCo
         key = (key << 5) | (unsigned long long)RUN_K(id.z);
         keys[c] = key;
     }
+}
+
+// ---------------------------------------------------------------------------
+// warm starting: remember this step's final impulses by contact identity
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_warm_save(BbxDev dv, int solved, float friction)
+{
+    int n = min(dv.ctr->n_contacts, dv.cap_contacts);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        int4 id = dv.c_ids[c];
+        float jn, jt0, jt1;
+        final_impulses(dv, c, id, dv.L[4 * (size_t)c + 3], solved, friction, jn, jt0, jt1);
+        const int wa = id.x < dv.NS ? id.x / dv.cap_s : (id.x - dv.NS) / dv.cap_b;
+        const unsigned long long key = warm_key_of(id.x, id.y, RUN_K(id.z));
+        unsigned int h = warm_hash(key) & dv.warm_mask;
+        for (unsigned int probe = 0; probe <= dv.warm_mask; probe++, h = (h + 1) & dv.warm_mask) {
+            unsigned long long old = atomicCAS(&dv.warm_key[h], BBX_WARM_EMPTY, key);
+            if (old == BBX_WARM_EMPTY || old == key) {
+                dv.warm_val[h] = make_float4(jn, jt0, jt1, __int_as_float(dv.warm_epoch[wa]));
+                break;
+            }
+        }
+    }
+}
+
+int bbx_stage_warm_save(BbxDev* d, const BbxStepParams* p)
+{
+    int rc = bbx_warm_ensure(d);
+    if (rc) return rc;
+    BBX_CUDA(d, cudaMemsetAsync(d->warm_key, 0xff, sizeof(unsigned long long) * ((size_t)d->warm_mask + 1), d->stream));
+    BBX_LAUNCH(d, k_warm_save, BBX_NUM_SMS * 8, 256, 0, *d, p->settings.solver_iterations > 0 ? 1 : 0, p->settings.friction);
+    BBX_CUDA(d, cudaGetLastError());
+    return 0;
 }
 
 // ---------------------------------------------------------------------------

@@ -42,6 +42,7 @@ struct PhysicsWorldBatch {
     int sdf_id; float sdf_params[8];
     /* baked host SDF (ballbox_ext.h): region, resolution, and which function the device grid holds */
     int bake_region_set, bake_res, bake_dirty;
+    float warm_start;                           /* BallboxSetWarmStarting */
     int bake_no_gradient; float baked_eps;      /* gradient channels are sampled with the sdf_normal_epsilon of bake time */
     float bake_lo[3], bake_hi[3];
     SDFFunction baked_fn;
@@ -720,6 +721,7 @@ static int fill_params(struct PhysicsWorldBatch* b, float dt, int has_forces, in
         }
     }
     p->solver_schedule = b->schedule;
+    p->warm_start = b->warm_start;
     p->has_forces = has_forces;
     p->want_callbacks = want_callbacks;
     return 0;
@@ -1075,6 +1077,7 @@ void BallboxClearError(PhysicsWorld* w)
     p->batch->has_err = 0; p->batch->err[0] = 0;
     if (p->batch->dev) bbx_dev_clear_error(p->batch->dev);
 }
+void BallboxSetWarmStarting(PhysicsWorld* w, float factor) { BbxWorldPriv* p = priv_of(w); if (p) p->batch->warm_start = factor > 0.0f ? factor : 0.0f; }
 void BallboxSetSolverSchedule(PhysicsWorld* w, int schedule) { BbxWorldPriv* p = priv_of(w); if (p) p->batch->schedule = schedule; }
 int  BallboxGetStats(PhysicsWorld* w, BallboxStats* out)
 {

@@ -80,6 +80,18 @@ int  BallboxSdfInUse(PhysicsWorld* world);      /* BBX_SDF_* the next step will 
                                   (profiles/r01_notes.md)                                   */
 void BallboxSetSolverSchedule(PhysicsWorld* world, int schedule);
 
+/* ---- warm starting (NOT in the reference: its ContactConstraint reserves the accumulated impulses "for warm
+ * starting" but GenerateContactConstraints zeroes them, ballbox.h:134-136, :1203-1206).  factor = 0 (default) keeps
+ * the reference's behaviour.  With factor > 0 a contact that also existed in the previous step -- same body A, same
+ * body B, same index k among the contacts of that pair in emission order -- starts from factor x the impulses it
+ * ended the previous step with, and, when solver_iterations > 0, a pass before the first sweep applies them:
+ * for every matched constraint in array order, A receives -n*jn and B +n*jn, then (friction > 0) the same for
+ * t1*jt0 and t2*jt1, through ApplyConstraintImpulse.  Unmatched contacts start from zero and apply nothing.
+ * The sequential definition is restated in oracle/bbx_oracle.c (OracleSetWarmStarting) and the GPU path is
+ * bit-identical to it with the exact schedules.  PhysicsStep / PhysicsStepN / PhysicsStepBatch only; the public
+ * stage functions ignore it.  A world reset (BatchResetWorlds) forgets that world's impulses. */
+void BallboxSetWarmStarting(PhysicsWorld* world, float factor);
+
 /* ---- statistics of the most recent step (and totals since creation) -------- */
 typedef struct {
     long long steps;               /* device steps executed                                 */

@@ -59,6 +59,8 @@ typedef struct {
     int   solver_schedule;         /* BBX_SOLVER_EXACT / _COLOURED / _EXACT_FLOW           */
     int   has_forces;              /* 0: force/torque arrays are known to be all zero      */
     int   want_callbacks;          /* collect callback events                              */
+    float warm_start;              /* 0: impulses start at zero like the reference (:1203-1206); f > 0: a contact that
+                                      existed in the previous step starts from f x its final impulses (ballbox_ext.h) */
 } BbxStepParams;
 
 /* baked SDF: nx*ny*nz samples (x fastest) of a host function at origin + (i,j,k)*cell; replaces any earlier bake.

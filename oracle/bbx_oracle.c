@@ -109,9 +109,11 @@ PhysicsWorld* CreatePhysicsWorld(int ms, int mb, int mc)
     ResetPhysicsSettingsToDefaults(w);
     return w;
 }
+static void warm_forget(PhysicsWorld* w);
 void DestroyPhysicsWorld(PhysicsWorld* w)
 {
     if (!w) return;
+    warm_forget(w);
     SphereSystem* s = w->spheres; BoxSystem* b = w->boxes;
     free(s->positions); free(s->radii); free(s->velocities); free(s->forces); free(s->masses); free(s->angular_velocities);
     free(s->torques); free(s->inertias); free(s->is_static); free(s->is_sleeping); free(s->sleep_timers); free(s->collision_callbacks); free(s);
@@ -582,9 +584,46 @@ static void push(PhysicsWorld* w, const BodyRef* b, Vec3 J, Vec3 L)             
         if (x->is_sleeping[i]) { x->is_sleeping[i] = false; x->sleep_timers[i] = 0.0f; }
     }
 }
+/* ---- warm starting: an EXTENSION of this repo (include/ballbox_ext.h, BallboxSetWarmStarting), not reference
+ * behaviour; the reference zeroes the accumulated impulses (:1203-1206).  This is the sequential definition the CUDA
+ * path is checked against; nothing pins it but itself. */
+#define ORACLE_WARM_WORLDS 64
+static struct { PhysicsWorld* w; float factor; ContactConstraint* prev; int n, cap; } g_warm[ORACLE_WARM_WORLDS];
+static int warm_slot(PhysicsWorld* w, int create)
+{
+    for (int i = 0; i < ORACLE_WARM_WORLDS; i++) if (g_warm[i].w == w) return i;
+    if (create) for (int i = 0; i < ORACLE_WARM_WORLDS; i++) if (!g_warm[i].w) { g_warm[i].w = w; return i; }
+    return -1;
+}
+void OracleSetWarmStarting(PhysicsWorld* w, float factor)
+{
+    int i = warm_slot(w, 1);
+    if (i >= 0) g_warm[i].factor = factor > 0.0f ? factor : 0.0f;
+}
+static void warm_forget(PhysicsWorld* w)
+{
+    int i = warm_slot(w, 0);
+    if (i >= 0) { free(g_warm[i].prev); memset(&g_warm[i], 0, sizeof(g_warm[i])); }
+}
+static bool same_pair_ids(const ContactConstraint* a, const ContactConstraint* b)
+{
+    return a->bodyA_type == b->bodyA_type && a->bodyA_index == b->bodyA_index && a->bodyB_type == b->bodyB_type && a->bodyB_index == b->bodyB_index;
+}
+/* index k of constraint i among the consecutive records of its body pair */
+static int run_index(const ContactConstraint* K, int i) { int k = 0; while (i - k - 1 >= 0 && same_pair_ids(&K[i], &K[i - k - 1])) k++; return k; }
+
 static void stage_solve(PhysicsWorld* w)
 {
     ConstraintCollection* K = w->constraints; CollisionCollection* C = w->collisions;
+    const int ws = warm_slot(w, 0);
+    const float warm = ws >= 0 ? g_warm[ws].factor : 0.0f;
+    bool* matched = NULL;
+    if (warm > 0.0f) {                                   /* keep the previous list: K is about to be overwritten */
+        if (g_warm[ws].cap < K->capacity) { g_warm[ws].prev = (ContactConstraint*)realloc(g_warm[ws].prev, sizeof(ContactConstraint) * (size_t)K->capacity); g_warm[ws].cap = K->capacity; }
+        memcpy(g_warm[ws].prev, K->constraints, sizeof(ContactConstraint) * (size_t)K->count);
+        g_warm[ws].n = K->count;
+        matched = (bool*)calloc((size_t)(C->count > 0 ? C->count : 1), sizeof(bool));
+    }
     K->count = 0;
     for (int i = 0; i < C->count && K->count < K->capacity; i++) {                           /* :1184-1210 */
         CollisionContact* s = &C->contacts[i]; ContactConstraint* c = &K->constraints[K->count++];
@@ -592,6 +631,26 @@ static void stage_solve(PhysicsWorld* w)
         c->contact_point = s->contact_point; c->contact_normal = s->contact_normal; c->penetration = s->penetration;
         c->restitution = w->settings.restitution; c->friction = w->settings.friction;
         c->normal_impulse = 0.0f; c->tangent_impulse[0] = 0.0f; c->tangent_impulse[1] = 0.0f;
+    }
+    if (warm > 0.0f) {
+        /* match by (body A, body B, k); both lists are in emission order but a plain search per pair start is enough here */
+        const ContactConstraint* P = g_warm[ws].prev; const int np = g_warm[ws].n;
+        int from = 0;
+        for (int i = 0; i < K->count; i++) {
+            ContactConstraint* c = &K->constraints[i];
+            const int k = run_index(K->constraints, i);
+            int j = -1;
+            for (int t = 0; t < np; t++) {                                   /* resume where the last match was: O(n) in practice */
+                int q = from + t; if (q >= np) q -= np;
+                if (same_pair_ids(c, &P[q]) && run_index(P, q) == k) { j = q; break; }
+            }
+            if (j < 0) continue;
+            from = j;
+            c->normal_impulse = warm * P[j].normal_impulse;
+            c->tangent_impulse[0] = warm * P[j].tangent_impulse[0];
+            c->tangent_impulse[1] = warm * P[j].tangent_impulse[1];
+            matched[i] = true;
+        }
     }
     for (int i = 0; i < K->count; i++) {                                                     /* presolve :1300-1355 */
         ContactConstraint* c = &K->constraints[i];
@@ -604,6 +663,24 @@ static void stage_solve(PhysicsWorld* w)
         for (int j = 0; j < 2; j++) c->tangent_mass[j] = eff_mass(&a, &b, rA, rB, c->tangent[j]);
         c->position_bias = (w->settings.baumgarte_bias / w->dt) * fmaxf(0.0f, c->penetration - w->settings.allowed_penetration);
     }
+    if (warm > 0.0f && w->settings.solver_iterations > 0) {
+        for (int i = 0; i < K->count; i++) {
+            if (!matched[i]) continue;
+            ContactConstraint* c = &K->constraints[i];
+            BodyRef a = body_ref(w, c->bodyA_type, c->bodyA_index, c->contact_point), b = body_ref(w, c->bodyB_type, c->bodyB_index, c->contact_point);
+            Vec3 rA = Vec3Sub(c->contact_point, a.pos), rB = Vec3Sub(c->contact_point, b.pos);
+            Vec3 P = Vec3Scale(c->contact_normal, c->normal_impulse), Pm = Vec3Scale(P, -1.0f);
+            push(w, &a, Pm, Vec3Cross(rA, Pm));
+            push(w, &b, P, Vec3Cross(rB, P));
+            if (c->friction > 0.0f)
+                for (int j = 0; j < 2; j++) {
+                    Vec3 T = Vec3Scale(c->tangent[j], c->tangent_impulse[j]), Tm = Vec3Scale(T, -1.0f);
+                    push(w, &a, Tm, Vec3Cross(rA, Tm));
+                    push(w, &b, T, Vec3Cross(rB, T));
+                }
+        }
+    }
+    free(matched);
     for (int it = 0; it < w->settings.solver_iterations; it++) {                             /* :1223, :1414-1488 */
         for (int i = 0; i < K->count; i++) {
             ContactConstraint* c = &K->constraints[i];

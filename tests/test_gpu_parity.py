@@ -654,6 +654,66 @@ def test_packed_fp32x2_sweep_is_bit_exact(product, truth, monkeypatch, kind, n, 
     lockstep(product, truth, kind, n, 31, steps, every=3)
 
 
+@pytest.mark.parametrize("kind,n,steps,factor,schedule", [
+    (bb.SCENE_MIXED, 1500, 60, 1.0, bb.SOLVER_EXACT), (bb.SCENE_SDF, 800, 60, 0.85, bb.SOLVER_EXACT),
+    (bb.SCENE_BALLS, 3000, 40, 1.0, bb.SOLVER_EXACT), (bb.SCENE_MIXED, 1000, 50, 0.9, bb.SOLVER_EXACT_FLOW)])
+def test_warm_starting_is_bit_exact_with_its_sequential_definition(product, checkers, kind, n, steps, factor, schedule):
+    """Extension (ballbox_ext.h BallboxSetWarmStarting): matched contacts start from the previous step's impulses and
+    a pre-pass applies them.  Checked against the sequential definition in oracle/bbx_oracle.c, state and constraint
+    list, every few steps.  (The reference itself has no warm starting: parity for this feature is pinned by the
+    restatement only.)"""
+    o = checkers["oracle"]
+    g, c = product.build_scene(kind, n, 17), o.build_scene(kind, n, 17)
+    g.set_warm_starting(factor); c.set_warm_starting(factor)
+    product.dll.BallboxSetSolverSchedule(g.ptr, schedule)
+    for s in range(steps):
+        g.step(DT); c.step(DT, pruned=True)
+        if s % 4 == 0 or s == steps - 1:
+            mm = parity.compare_worlds(g, c)
+            assert not mm, f"step {s}: {mm[:4]}"
+    cold = product.build_scene(kind, n, 17)
+    for s in range(steps):
+        cold.step(DT)
+    assert parity.compare_worlds(g, cold, constraints=False), "warm starting changed nothing"
+
+
+def test_warm_starting_batch_and_world_reset(product, checkers):
+    """Batched worlds (block-per-group solver, per-contact graph) with warm starting equal independent oracle worlds;
+    resetting a world forgets its impulses: after the reset it equals a fresh oracle world started from the snapshot state."""
+    o = checkers["oracle"]
+    d = product.dll
+    n_worlds = 20
+    s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
+    batch = d.CreatePhysicsWorldBatch(n_worlds, s, b, c)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(n_worlds)]
+    refs = []
+    for i, v in enumerate(views):
+        d.BbxSceneBuild(v.ptr, bb.SCENE_RLWORLD, 0, 900 + i)
+        r = o.build_scene(bb.SCENE_RLWORLD, 0, 900 + i)
+        r.set_warm_starting(1.0)
+        refs.append(r)
+    views[0].set_warm_starting(1.0)                                 # the batch steps with one setting
+    assert d.BatchUpload(batch) == 0
+    assert d.BatchSnapshot(batch) == 0                              # snapshot = initial state
+    assert d.PhysicsStepBatch(batch, DT, 40) == 0, d.BatchGetLastError(batch)
+    for r in refs:
+        for _ in range(40):
+            r.step(DT)
+    ids = (bb.C.c_int * 2)(3, 11)
+    assert d.BatchResetWorlds(batch, ids, 2) == 0
+    for i in (3, 11):                                               # same initial state, no remembered impulses
+        refs[i] = o.build_scene(bb.SCENE_RLWORLD, 0, 900 + i)
+        refs[i].set_warm_starting(1.0)
+    assert d.PhysicsStepBatch(batch, DT, 25) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    for i, (v, r) in enumerate(zip(views, refs)):
+        for _ in range(25):
+            r.step(DT)
+        mm = parity.compare_worlds(v, r)
+        assert not mm, f"world {i}: {mm[:4]}"
+    d.DestroyPhysicsWorldBatch(batch)
+
+
 def test_overflow_is_reported_by_a_bodies_only_download(product):
     """Resident stepping never looks at the host; a step that dropped contacts (max_collisions too small) must
     still surface at the next download, also when only the bodies are fetched."""

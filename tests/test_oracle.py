@@ -85,3 +85,31 @@ def test_callback_order_is_the_reference_order(checkers):
         assert phases == sorted(phases)
         logs.append(log)
     assert all(l == logs[0] for l in logs)
+
+
+def test_warm_starting_definition(checkers):
+    """Warm starting is an extension (ballbox_ext.h), defined sequentially in the restatement only.  Factor 0 is the
+    reference's behaviour bit for bit; factor 1 with TWO sweeps leaves a sphere pile less interpenetrated than the
+    reference's eight cold sweeps, which is what the feature is for."""
+    import numpy as np
+    o = checkers["oracle"]
+
+    def run(factor, iters):
+        w = o.build_scene(bb.SCENE_BALLS, 400, 9)
+        w.w.settings.solver_iterations = iters
+        if factor is not None:
+            w.set_warm_starting(factor)
+        pens = []
+        for s in range(200):
+            w.step(1 / 60, pruned=True)
+            if s >= 150:
+                k = w.constraints()
+                ss = k[(k["a_type"] == 0) & (k["b_type"] == 0)]
+                pens.append(float(ss["penetration"].mean()))
+        return w, float(np.mean(pens))
+
+    cold8, pen_cold8 = run(None, 8)
+    zero8, _ = run(0.0, 8)
+    assert not parity.compare_worlds(cold8, zero8)
+    _, pen_warm2 = run(1.0, 2)
+    assert pen_warm2 < 0.8 * pen_cold8, (pen_warm2, pen_cold8)
