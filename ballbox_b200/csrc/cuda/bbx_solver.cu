@@ -59,9 +59,12 @@ __device__ __forceinline__ float inv_mass_sum(float imA, float imB, float3 rA, f
 // node[2c] = (dynamic gid A or -1, position in A's chain, length of A's chain, successor on A), node[2c+1] = same for B
 // warm > 0 (extension, mode 0 only): a contact found in the previous step's table starts from warm x its final impulses
 // and is flagged (c_nrm.w = 1) for k_warm_apply
-__global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, float allowed, float dt, int mode, int per_contact, float warm)
+// count_nodes (level path): the statistics n_solver / n_nodes are summed here (the other paths do it in their frontier kernels)
+__global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, float allowed, float dt, int mode, int per_contact, float warm,
+                                                  int count_nodes)
 {
     int n = min(dv.ctr->n_contacts, dv.cap_contacts);
+    int my_solver = 0, my_nodes = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
         int4 id = dv.c_ids[c];
         float4 pt4 = dv.c_pt[c];
@@ -135,7 +138,13 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
             dv.indeg[c] = (dynA ? 1 : 0) + (dynB ? 1 : 0);
             if (dynA) atomicAdd(&dv.deg[a], 1);
             if (dynB) atomicAdd(&dv.deg[b], 1);
+            if (dynA || dynB) { my_solver += m; my_nodes++; }
         }
+    }
+    if (count_nodes) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { my_solver += __shfl_xor_sync(0xffffffffu, my_solver, o); my_nodes += __shfl_xor_sync(0xffffffffu, my_nodes, o); }
+        if ((threadIdx.x & 31) == 0 && my_nodes) { atomicAdd(&dv.ctr->n_solver, my_solver); atomicAdd(&dv.ctr->n_nodes, my_nodes); }
     }
 }
 
@@ -250,10 +259,13 @@ __device__ __forceinline__ void adj_write_links(const BbxDev& dv, int x, const u
 }
 
 // keep_sorted: the sorted list is written back (k_warm_apply walks it)
-__global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, int flow_records, int keep_sorted)
+// push_frontier (level path): the thread whose decrement takes a node's in-degree to zero appends it to level 0 of
+// its class queue (this used to be a pass over all contacts, k_frontier0)
+__global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, int flow_records, int keep_sorted, int push_frontier)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     bool has = false;
+    int ready = -1, ready_cls = -1;
     if (x < dv.N) {
         int s = dv.adj_start[x], e = dv.adj_start[x + 1];
         int d = e - s;
@@ -269,7 +281,8 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                     while (j >= 0 && adj_after(dv, loc[j], v)) { loc[j + 1] = loc[j]; j--; }
                     loc[j + 1] = v;
                 }
-                atomicSub(&dv.indeg[ADJ_NODE(loc[0])], 1);         // first node of this body has no predecessor here
+                // first node of this body has no predecessor here
+                if (atomicSub(&dv.indeg[ADJ_NODE(loc[0])], 1) == 1) { ready = ADJ_NODE(loc[0]); ready_cls = (int)((loc[0] >> 32) & 7u); }
                 adj_write_links(dv, x, loc, d, per_contact);
                 if (keep_sorted) for (int i = 0; i < d; i++) lst[i] = loc[i];
             } else {
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                     while (j >= 0 && adj_after(dv, lst[j], v)) { lst[j + 1] = lst[j]; j--; }
                     lst[j + 1] = v;
                 }
-                atomicSub(&dv.indeg[ADJ_NODE(lst[0])], 1);
+                if (atomicSub(&dv.indeg[ADJ_NODE(lst[0])], 1) == 1) { ready = ADJ_NODE(lst[0]); ready_cls = (int)((lst[0] >> 32) & 7u); }
                 adj_write_links(dv, x, lst, d, per_contact);
             }
             if (per_contact && flow_records && !keep_sorted) flow_init_body(dv, x);    // the body's versioned record starts at version 0
@@ -288,43 +301,18 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
     }
     unsigned int m = __ballot_sync(0xffffffffu, has);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&dv.ctr->n_touched, __popc(m));
-}
-
-__global__ void __launch_bounds__(256) k_frontier0(BbxDev dv)
-{
-    __shared__ int s_solver, s_nodes;
-    if (threadIdx.x == 0) { s_solver = 0; s_nodes = 0; }
-    __syncthreads();
-    int n = min(dv.ctr->n_contacts, dv.cap_contacts);
-    int n_round = (n + 31) & ~31;
-    int my_solver = 0, my_nodes = 0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += gridDim.x * blockDim.x) {
-        int cls = -1;
-        if (c < n) {
-            int4 id = dv.c_ids[c];
-            if (RUN_K(id.z) == 0) {
-                int4 l = dv.node[2 * (size_t)c];
-                if (l.x >= 0 || l.y >= 0) {
-                    my_solver += l.z; my_nodes++;
-                    if (dv.indeg[c] == 0) cls = l.w;
-                }
-            }
-        }
-        // level 0 of the class queues: most warps have nothing to append; the others group their lanes by class
-        const bool push = cls >= 0;
+    if (push_frontier) {
+        const bool push = ready >= 0;
         const unsigned int active = __ballot_sync(0xffffffffu, push);
         if (push) {
-            const unsigned int peers = __match_any_sync(active, cls);
+            const unsigned int peers = __match_any_sync(active, ready_cls);
             const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
             int base = 0;
-            if (lane == leader) base = atomicAdd(&dv.level_count[cls], __popc(peers));
+            if (lane == leader) base = atomicAdd(&dv.level_count[ready_cls], __popc(peers));
             base = __shfl_sync(peers, base, leader);
-            dv.queue_k[cls][base + __popc(peers & ((1u << lane) - 1u))] = c;
+            dv.queue_k[ready_cls][base + __popc(peers & ((1u << lane) - 1u))] = ready;
         }
     }
-    if (my_nodes) { atomicAdd(&s_solver, my_solver); atomicAdd(&s_nodes, my_nodes); }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_nodes) { atomicAdd(&dv.ctr->n_solver, s_solver); atomicAdd(&dv.ctr->n_nodes, s_nodes); }
 }
 
 // ---------------------------------------------------------------------------
@@ -1761,12 +1749,15 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     BBX_CUDA(d, cudaMemsetAsync(d->deg, 0, sizeof(int) * ((size_t)d->N + 1), d->stream));
     const float warm = (presolve_mode == 0 && !imported && p->warm_start > 0.0f) ? p->warm_start : 0.0f;
     if (warm > 0.0f) { int rcw = bbx_warm_ensure(d); if (rcw) return rcw; }
-    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, per_contact, warm);
+    // default path: level-scheduled kernel (single world, or batches the world solvers do not take)
+    const int levels_path = (!flow && !groups && !(use_world_warps(d, imported) && p->solver_schedule != BBX_SOLVER_EXACT_FLOW)) ? 1 : 0;
+    BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, per_contact, warm, (levels_path && iterations > 0) ? 1 : 0);
     if (iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);
     if (rc) return rc;
     BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0), per_contact);
-    BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, warm > 0.0f ? 1 : 0);
+    if (levels_path) BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 2 * BBX_NCLS * sizeof(int), d->stream));
+    BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, warm > 0.0f ? 1 : 0, levels_path);
     if (warm > 0.0f) BBX_LAUNCH(d, k_warm_apply, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, p->settings.friction);
     d->last_flow = flow; d->last_per_contact = per_contact;
     if (flow) {
@@ -1841,8 +1832,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         BBX_CUDA(d, cudaGetLastError());
         return 0;
     }
-    BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 2 * BBX_NCLS * sizeof(int), d->stream));
-    BBX_LAUNCH(d, k_frontier0, G, 256, 0, *d);
+    // (level 0 of the class queues was filled by k_adj_link)
 
     if (d->coop_blocks == 0) {
         int per_sm = 0, sms = 0, coop = 0;
