@@ -101,6 +101,8 @@ struct BbxDev {
     unsigned char *flags;   // N
     float4 *boxq;       // 2 per box, one 32-byte sector: [2b] = rotation, [2b+1] = (1/Ix, 1/Iy, 1/Iz) or 0 when static
     float4 *half;       // NB half extents, w unused
+    float4 *brec;       // 2 per body, one 32-byte sector, rebuilt before every presolve: (pos, 1/m) (1/I diag, flags bits): what
+                        // k_presolve gathers per contact side (one sector instead of four)
 
     // grid
     GridParams *grid;

@@ -57,6 +57,19 @@ __device__ __forceinline__ float inv_mass_sum(float imA, float imB, float3 rA, f
 //         masses, bias and accumulated impulses are the ones found in the host records
 // per_contact: every contact is its own scheduling node (flow solver), one half per body:
 // node[2c] = (dynamic gid A or -1, position in A's chain, length of A's chain, successor on A), node[2c+1] = same for B
+// per-body gather record of k_presolve: position, inverse mass, inverse inertia diagonal, flags
+__global__ void __launch_bounds__(256) k_body_records(BbxDev dv)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= dv.N) return;
+    const float4 p = dv.pos[g];
+    const F8 vw = ld256_cg(&dv.vel[2 * g]);
+    float3 iI;
+    if (g < dv.NS) iI = f3(vw.b.w, vw.b.w, vw.b.w);
+    else iI = xyz(dv.boxq[2 * (g - dv.NS) + 1]);
+    st256_cg(&dv.brec[2 * (size_t)g], make_float4(p.x, p.y, p.z, vw.a.w), make_float4(iI.x, iI.y, iI.z, __int_as_float((int)dv.flags[g])));
+}
+
 // warm > 0 (extension, mode 0 only): a contact found in the previous step's table starts from warm x its final impulses
 // and is flagged (c_nrm.w = 1) for k_warm_apply
 // count_nodes (level path): the statistics n_solver / n_nodes are summed here (the other paths do it in their frontier kernels)
@@ -72,20 +85,18 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         int a = id.x, b = id.y;
         float3 rA, rB, iA, iB; float imA, imB; bool dynA, dynB;
         {
-            unsigned char f = dv.flags[a];
-            dynA = !(f & BF_STATIC);
-            rA = v3sub(pt, xyz(dv.pos[a]));
-            imA = dv.vel[2 * a].w;                  // 0 for static bodies (:1266)
-            if (a < dv.NS) { float ii = dv.vel[2 * a + 1].w; iA = f3(ii, ii, ii); }
-            else iA = xyz(dv.boxq[2 * (a - dv.NS) + 1]);
+            F8 ra = ld256_nc(&dv.brec[2 * (size_t)a]);          // (pos, 1/m) (1/I, flags): k_body_records
+            dynA = !(__float_as_int(ra.b.w) & BF_STATIC);
+            rA = v3sub(pt, xyz(ra.a));
+            imA = ra.a.w;                           // 0 for static bodies (:1266)
+            iA = xyz(ra.b);
         }
         if (b >= 0) {
-            unsigned char f = dv.flags[b];
-            dynB = !(f & BF_STATIC);
-            rB = v3sub(pt, xyz(dv.pos[b]));
-            imB = dv.vel[2 * b].w;
-            if (b < dv.NS) { float ii = dv.vel[2 * b + 1].w; iB = f3(ii, ii, ii); }
-            else iB = xyz(dv.boxq[2 * (b - dv.NS) + 1]);
+            F8 rb = ld256_nc(&dv.brec[2 * (size_t)b]);
+            dynB = !(__float_as_int(rb.b.w) & BF_STATIC);
+            rB = v3sub(pt, xyz(rb.a));
+            imB = rb.a.w;
+            iB = xyz(rb.b);
         } else {                                    // SDF: "position" is the contact point (:1310-1311)
             dynB = false; rB = v3sub(pt, pt); imB = 0.0f; iB = f3(0.0f, 0.0f, 0.0f);
         }
@@ -99,7 +110,8 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         float mT1 = (s2 > 0.0f) ? 1.0f / s2 : 0.0f;
         float bias = (baumgarte / dt) * bb_fmaxf(0.0f, pt4.w - allowed);               // :1352-1354
         float4* L = dv.L + 4 * (size_t)c;
-        float4 keep = L[3];
+        float4 keep = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (mode != 0) keep = L[3];                                   // PhysicsStep never reads the old record
         if (mode == 2) { bias = L[0].w; mN = L[1].w; mT0 = L[2].w; mT1 = keep.w; }
         L[0] = make_float4(nrm.x, nrm.y, nrm.z, bias);
         L[1] = make_float4(rA.x, rA.y, rA.z, mN);
@@ -1751,6 +1763,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     if (warm > 0.0f) { int rcw = bbx_warm_ensure(d); if (rcw) return rcw; }
     // default path: level-scheduled kernel (single world, or batches the world solvers do not take)
     const int levels_path = (!flow && !groups && !(use_world_warps(d, imported) && p->solver_schedule != BBX_SOLVER_EXACT_FLOW)) ? 1 : 0;
+    BBX_LAUNCH(d, k_body_records, bbx_blocks(d->N, 256), 256, 0, *d);
     BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, per_contact, warm, (levels_path && iterations > 0) ? 1 : 0);
     if (iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);

@@ -97,7 +97,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->d_s_count, n_worlds); DALLOC(d->d_b_count, n_worlds);
 
     DALLOC(d->pos, N); DALLOC(d->vel, 2 * (size_t)N); DALLOC(d->mass, N); DALLOC(d->timer, N); DALLOC(d->flags, N);
-    DALLOC(d->boxq, 2 * NB); DALLOC(d->half, NB);
+    DALLOC(d->boxq, 2 * NB); DALLOC(d->half, NB); DALLOC(d->brec, 2 * N);
 
     DALLOC(d->grid, 1);
     DALLOC(d->cell_count, d->cap_cells + 1); DALLOC(d->cell_start, d->cap_cells + 1); DALLOC(d->cell_cursor, d->cap_cells + 1);
@@ -152,7 +152,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->r_s_inertia, d->r_s_timer, d->r_s_static, d->r_s_sleep, d->r_s_hascb, d->r_b_pos, d->r_b_size, d->r_b_rot,
         d->r_b_vel, d->r_b_force, d->r_b_mass, d->r_b_angvel, d->r_b_torque, d->r_b_inertia, d->r_b_timer, d->r_b_static,
         d->r_b_sleep, d->r_b_hascb, d->d_s_count, d->d_b_count, d->pos, d->vel, d->mass, d->timer, d->flags,
-        d->boxq, d->half, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
+        d->boxq, d->half, d->brec, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
         d->sdf_grid, d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
