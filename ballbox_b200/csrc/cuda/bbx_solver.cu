@@ -284,7 +284,32 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
         has = d > 0;
         if (has) {
             unsigned long long* lst = dv.adj + s;
-            if (d <= ADJ_LOCAL) {
+            if (d <= 8) {
+                // most lists: sorted in REGISTERS with a fixed 19-comparator network (the thread-private array of the
+                // general path lives in local memory: its dependent LDL/STL chain was half of this kernel's stall samples)
+                unsigned long long e0, e1, e2, e3, e4, e5, e6, e7;
+                e0 = lst[0];
+                e1 = d > 1 ? lst[1] : ~0ull; e2 = d > 2 ? lst[2] : ~0ull; e3 = d > 3 ? lst[3] : ~0ull;
+                e4 = d > 4 ? lst[4] : ~0ull; e5 = d > 5 ? lst[5] : ~0ull; e6 = d > 6 ? lst[6] : ~0ull; e7 = d > 7 ? lst[7] : ~0ull;
+#define ADJ_CE(a, b) { if (b != ~0ull && (a == ~0ull || adj_after(dv, a, b))) { unsigned long long t_ = a; a = b; b = t_; } }   /* ~0: padding, stays last */
+                ADJ_CE(e0, e1) ADJ_CE(e2, e3) ADJ_CE(e4, e5) ADJ_CE(e6, e7)
+                ADJ_CE(e0, e2) ADJ_CE(e1, e3) ADJ_CE(e4, e6) ADJ_CE(e5, e7)
+                ADJ_CE(e1, e2) ADJ_CE(e5, e6)
+                ADJ_CE(e0, e4) ADJ_CE(e1, e5) ADJ_CE(e2, e6) ADJ_CE(e3, e7)
+                ADJ_CE(e2, e4) ADJ_CE(e3, e5)
+                ADJ_CE(e1, e2) ADJ_CE(e3, e4) ADJ_CE(e5, e6)
+#undef ADJ_CE
+                if (atomicSub(&dv.indeg[ADJ_NODE(e0)], 1) == 1) { ready = ADJ_NODE(e0); ready_cls = (int)((e0 >> 32) & 7u); }
+#define ADJ_LINK(i, prev, cur, nxt_valid, nxt)                                                                         \
+                if (i < d) {                                                                                            \
+                    if (per_contact) dv.node[2 * (size_t)ADJ_NODE(cur) + ADJ_SIDE(cur)] = make_int4(x, i, d, (nxt_valid) ? ADJ_NODE(nxt) : -1); \
+                    else if (i > 0) ((int*)&dv.node[2 * (size_t)ADJ_NODE(prev) + 1])[ADJ_SIDE(prev)] = ADJ_NODE(cur) | ((int)((cur >> 32) & 7u) << 28); \
+                    if (keep_sorted) lst[i] = cur;                                                                      \
+                }
+                ADJ_LINK(0, e0, e0, d > 1, e1) ADJ_LINK(1, e0, e1, d > 2, e2) ADJ_LINK(2, e1, e2, d > 3, e3) ADJ_LINK(3, e2, e3, d > 4, e4)
+                ADJ_LINK(4, e3, e4, d > 5, e5) ADJ_LINK(5, e4, e5, d > 6, e6) ADJ_LINK(6, e5, e6, d > 7, e7) ADJ_LINK(7, e6, e7, false, e7)
+#undef ADJ_LINK
+            } else if (d <= ADJ_LOCAL) {
                 unsigned long long loc[ADJ_LOCAL];
                 for (int i = 0; i < d; i++) loc[i] = lst[i];
                 for (int i = 1; i < d; i++) {                      // insertion sort: lists are short
