@@ -153,6 +153,7 @@ struct BbxDev {
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels
     int tune_replay_blocks, tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_REPLAY_BLOCKS, BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL
     int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
+    int grp_unrolled;                            // BBX_GROUPS_UNROLLED: group solver over the unrolled graph (sweeps overlap)
     int no_groups;                               // BBX_WORLD_GROUPS=0: batched worlds use the warp-per-world kernel (A/B measurements)
     int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)
     unsigned long long *level_ns;                // optional trace: globaltimer at the end of each level of iteration 1 (first 4096)

@@ -123,6 +123,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->flow, 4 * (size_t)N); DALLOC(d->fq, C); DALLOC(d->fnd, 2 * (size_t)C); DALLOC(d->fimp, 2 * (size_t)C);
     BBX_CUDA(d, cudaMemsetAsync(d->fq, 0xff, sizeof(int) * (size_t)C, d->stream));
     // measurement switches (A/B runs of tools/ and profiles/r01_notes.md), read once per device state
+    { const char* e = getenv("BBX_GROUPS_UNROLLED"); d->grp_unrolled = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("BBX_WORLD_GROUPS"); d->no_groups = (e && e[0] == '0') ? 1 : 0; }
     { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("BBX_PACKED"); d->packed_sweep = (e && e[0] == '1') ? 1 : 0; }

@@ -623,13 +623,14 @@ def test_full_size_two_exact_schedules_agree(product):
 
 
 def test_full_size_batch_three_solvers_agree(product, monkeypatch):
-    """BASELINE config 5 at full size (4096 worlds x 256 bodies): the block-per-group solver, the warp-per-world
-    solver and the flow solver must produce identical worlds."""
+    """BASELINE config 5 at full size (4096 worlds x 256 bodies): the block-per-group solver, its variant over the
+    unrolled graph (sweeps overlap), the warp-per-world solver and the flow solver must produce identical worlds."""
     d = product.dll
     s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
     hashes = []
-    for mode in ("groups", "warps", "flow"):
+    for mode in ("groups", "unrolled", "warps", "flow"):
         monkeypatch.setenv("BBX_WORLD_GROUPS", "0" if mode == "warps" else "1")
+        monkeypatch.setenv("BBX_GROUPS_UNROLLED", "1" if mode == "unrolled" else "0")
         batch = d.CreatePhysicsWorldBatch(4096, s, b, c)
         views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in (0, 1, 777, 2048, 4095)]
         for i in range(4096):
@@ -643,7 +644,7 @@ def test_full_size_batch_three_solvers_agree(product, monkeypatch):
         assert st.overflow == 0
         hashes.append((st.contacts, tuple(v.state_hash() for v in views)))
         d.DestroyPhysicsWorldBatch(batch)
-    assert hashes[0] == hashes[1] == hashes[2] and hashes[0][0] > 1_000_000
+    assert hashes[0] == hashes[1] == hashes[2] == hashes[3] and hashes[0][0] > 1_000_000
 
 
 @pytest.mark.parametrize("kind,n,steps", [(bb.SCENE_MIXED, 2500, 40), (bb.SCENE_SDF, 1200, 30)])

@@ -34,3 +34,11 @@ print("error:", e)
 names = bb.World.STAGES
 print({k: round(out[i] / max(n.value, 1), 4) for i, k in enumerate(names)}, "total", round(sum(out) / max(n.value, 1), 3), "ms/step over", n.value)
 print("contacts", st.contacts, "solver", st.solver_contacts, "levels", st.levels, "pairs", st.candidate_pairs, "ovf", st.overflow)
+if os.environ.get("BBX_SOLVER_FLOW"):
+    import numpy as np
+    cnt = (C.c_int * (8 * 4096))(); ns = (C.c_ulonglong * 4097)()
+    d.BallboxDebugLevels.argtypes = [bb.WP, C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.c_int]
+    d.BallboxDebugLevels(d.BatchWorld(batch, 0), cnt, ns, 4096)
+    ud = int(np.frombuffer(ns, dtype=np.uint64)[4080])
+    its = d.BatchWorld(batch, 0).contents.settings.solver_iterations
+    print(f"flow solver: dependency depth of ALL iterations together = {ud} constraints; iteration 0 alone {st.levels}; {its} iterations one after the other {st.levels * its}")
