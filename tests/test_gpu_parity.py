@@ -191,6 +191,32 @@ def test_odd_geometry(product, truth):
         assert not mm, f"step {s}: {mm[:3]}"
 
 
+@pytest.mark.parametrize("extra", ["far_1e6", "far_1e30", "nan_sphere", "inf_sphere", "huge_radius"])
+def test_extreme_inputs_match_the_reference(product, truth, extra):
+    """Bodies far outside the pile (the grid must not blow up), non-finite sphere positions (every comparison with a
+    NaN is false: the reference never reports a contact for them) and a sphere that contains the whole scene."""
+    add = {"far_1e6": lambda w: w.add_sphere((1e6, 3.0, -2e6), 0.5), "far_1e30": lambda w: w.add_sphere((1e30, 3.0, 0.0), 0.5),
+           "nan_sphere": lambda w: w.add_sphere((float("nan"), 3.0, 0.0), 0.5), "inf_sphere": lambda w: w.add_sphere((float("inf"), 3.0, 0.0), 0.5),
+           "huge_radius": lambda w: w.add_sphere((0.0, 50.0, 0.0), 1e6)}[extra]
+
+    def build(lib):
+        w = lib.create_world(64, 64, 4096)
+        w.set_gravity((0, -9.8, 0))
+        g = w.add_box((0, -1, 0), (8, 1, 8)); lib.dll.SetBoxStatic(w.ptr, g, True)
+        for i in range(20):
+            w.add_sphere((-3 + 0.35 * i, 1.5 + 0.1 * (i % 3), -2 + 0.2 * i), 0.3)
+            w.add_box((-3 + 0.3 * i, 3.0, 2 - 0.2 * i), (0.2, 0.3, 0.25), w.quat_axis_angle((1, i + 1, 2), 0.3 * i))
+        add(w)
+        return w
+    g, c = build(product), build(truth)
+    for s in range(40):
+        g.step(DT); c.step(DT)
+        sa, sb = g.snapshot(), c.snapshot()
+        for f in ("s_pos", "s_vel", "s_angvel", "b_pos", "b_vel", "b_rot", "b_angvel"):
+            assert np.array_equal(sa[f], sb[f], equal_nan=True), (s, f)
+        assert len(g.constraints()) == len(c.constraints()), s
+
+
 def _sdf_scene(lib, fn_ptr):
     """Spheres and rotated boxes dropped onto a host-function SDF (no UseSDFDevice)."""
     w = lib.create_world(64, 32, 4096)
