@@ -323,6 +323,40 @@ __device__ __forceinline__ void st256_cg(float4* p, float4 a, float4 b)
                  :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
 }
 
+// The same accesses with an L2 eviction policy (createpolicy): the body state is re-read at every level and should stay
+// in L2 (evict_last), the level-major records stream through once per sweep (evict_first).
+__device__ __forceinline__ unsigned long long l2_policy_keep() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ unsigned long long l2_policy_stream() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ F8 ld256_cg_pol(const float4* p, unsigned long long pol)
+{
+    F8 r;
+    asm volatile("ld.global.cg.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ F8 ld256_nc_pol(const float4* p, unsigned long long pol)
+{
+    F8 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st256_cg_pol(float4* p, float4 a, float4 b, unsigned long long pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld128_cg_pol(const float4* p, unsigned long long pol)
+{
+    float4 r;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st128_cg_pol(float4* p, float4 v, unsigned long long pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 // order-preserving float <-> uint encoding for atomicMin/atomicMax
 __device__ __forceinline__ unsigned int f2ord(float f)
 {

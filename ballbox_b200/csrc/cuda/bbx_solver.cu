@@ -402,6 +402,26 @@ __device__ __forceinline__ void store_body(const BbxDev& dv, int g, const BodySt
     st256_cg(&dv.vel[2 * g], make_float4(s.v.x, s.v.y, s.v.z, s.im), make_float4(s.w.x, s.w.y, s.w.z, s.ii));
 }
 
+// level kernel: the same with an L2 "keep" policy
+__device__ __forceinline__ void load_body_keep(const BbxDev& dv, int g, BodyState& s, unsigned long long pol)
+{
+    F8 vw = ld256_cg_pol(&dv.vel[2 * g], pol);
+    float4 l = vw.a, a = vw.b;
+    s.v = xyz(l); s.w = xyz(a); s.im = l.w; s.ii = a.w;
+    s.box = g >= dv.NS;
+    if (s.box) {
+        int b = g - dv.NS;
+        F8 qi = ld256_nc_pol(&dv.boxq[2 * b], pol);
+        s.q = qi.a; s.iI = xyz(qi.b);
+        float3 u = f3(s.q.x, s.q.y, s.q.z);
+        s.k1 = s.q.w * s.q.w - v3dot(u, u); s.k2 = 2.0f * s.q.w;
+    }
+}
+__device__ __forceinline__ void store_body_keep(const BbxDev& dv, int g, const BodyState& s, unsigned long long pol)
+{
+    st256_cg_pol(&dv.vel[2 * g], make_float4(s.v.x, s.v.y, s.v.z, s.im), make_float4(s.w.x, s.w.y, s.w.z, s.ii), pol);
+}
+
 __device__ __forceinline__ void wake_body(const BbxDev& dv, int g)                      // :1373-1376, :1402-1405
 {
     unsigned char f = dv.flags[g];
@@ -821,6 +841,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     __shared__ LevelMap lm;
     __shared__ int s_pcnt[BBX_NCLS], s_pbase[BBX_NCLS];
     constexpr bool PACKED0 = false;                 // iteration 0 keeps the scalar sweep (register budget of the discovery pass)
+    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
     // work index of this thread: consecutive 32-node chunks go round-robin over the BLOCKS, so a level
@@ -866,26 +887,26 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 __stcg(&dv.Nd_k[k][p], make_int4(mbase, m, nd0.x, nd0.y));
                 bool hasA = nd0.x >= 0, hasB = nd0.y >= 0;
                 BodyState A, B;
-                if (hasA) load_body(dv, nd0.x, A);
-                if (hasB) load_body(dv, nd0.y, B);
+                if (hasA) load_body_keep(dv, nd0.x, A, pol_keep);
+                if (hasB) load_body_keep(dv, nd0.y, B, pol_keep);
                 // contact-order records are gathered once (two 256-bit loads, the next record in flight while
                 // the current constraint is swept), then written plane-major
                 const float4* L = dv.L + 4 * (size_t)c;
-                F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+                F8 lo = ld256_nc_pol(L, pol_stream), hi = ld256_nc_pol(L + 2, pol_stream);
                 PairState ps;
                 if (PACKED0) pair_from(A, B, hasA, hasB, ps);
                 for (int j = 0; j < m; j++, L += 4) {
                     float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
-                    if (j + 1 < m) { lo = ld256_nc(L + 4); hi = ld256_nc(L + 6); }
+                    if (j + 1 < m) { lo = ld256_nc_pol(L + 4, pol_stream); hi = ld256_nc_pol(L + 6, pol_stream); }
                     if (PACKED0) solve_constraint_packed(c0, c1, c2, c3, hasA, hasB, ps, sp);
                     else         solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     float4* M = dv.M + (size_t)(mbase + j);
-                    __stcg(M, c0); __stcg(M + PL, c1); __stcg(M + 2 * PL, c2); __stcg(M + 3 * PL, c3);
+                    st128_cg_pol(M, c0, pol_stream); st128_cg_pol(M + PL, c1, pol_stream); st128_cg_pol(M + 2 * PL, c2, pol_stream); st128_cg_pol(M + 3 * PL, c3, pol_stream);
                     dv.slot_of[c + j] = mbase + j;
                 }
                 if (PACKED0) pair_to(ps, hasA, hasB, A, B);
-                if (hasA) store_body(dv, nd0.x, A);            // (the bodies were woken by k_adj_link: one coalesced pass over the
-                if (hasB) store_body(dv, nd0.y, B);            //  touched bodies instead of a random flag access per node here)
+                if (hasA) store_body_keep(dv, nd0.x, A, pol_keep);    // (the bodies were woken by k_adj_link: one coalesced pass over the
+                if (hasB) store_body_keep(dv, nd0.y, B, pol_keep);    //  touched bodies instead of a random flag access per node here)
                 if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) != 1) sa = -1;
                 if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) != 1) sb = -1;
             }
@@ -964,24 +985,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 int4 nd = __ldcg(&dv.Nd_k[k][head[k] + idx]);
                 bool hasA = nd.z >= 0, hasB = nd.w >= 0;
                 BodyState A, B;
-                if (hasA) load_body(dv, nd.z, A);
-                if (hasB) load_body(dv, nd.w, B);
+                if (hasA) load_body_keep(dv, nd.z, A, pol_keep);
+                if (hasB) load_body_keep(dv, nd.w, B, pol_keep);
                 float4* M = dv.M + (size_t)nd.x;
                 // software pipeline: the record of constraint j+1 is in flight while constraint j is swept
-                float4 n0 = __ldcg(M), n1 = __ldcg(M + PL), n2 = __ldcg(M + 2 * PL), n3 = __ldcg(M + 3 * PL);
+                float4 n0 = ld128_cg_pol(M, pol_stream), n1 = ld128_cg_pol(M + PL, pol_stream), n2 = ld128_cg_pol(M + 2 * PL, pol_stream), n3 = ld128_cg_pol(M + 3 * PL, pol_stream);
                 PairState ps;
                 if (PACKED) pair_from(A, B, hasA, hasB, ps);
                 for (int j = 0; j < nd.y; j++, M++) {
                     if (PACKED && j > 0) { n0 = __ldcg(M); n1 = __ldcg(M + PL); n2 = __ldcg(M + 2 * PL); n3 = __ldcg(M + 3 * PL); }
                     float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
-                    if (!PACKED && j + 1 < nd.y) { n0 = __ldcg(M + 1); n1 = __ldcg(M + 1 + PL); n2 = __ldcg(M + 1 + 2 * PL); n3 = __ldcg(M + 1 + 3 * PL); }
+                    if (!PACKED && j + 1 < nd.y) { n0 = ld128_cg_pol(M + 1, pol_stream); n1 = ld128_cg_pol(M + 1 + PL, pol_stream); n2 = ld128_cg_pol(M + 1 + 2 * PL, pol_stream); n3 = ld128_cg_pol(M + 1 + 3 * PL, pol_stream); }
                     if (PACKED) solve_constraint_packed(c0, c1, c2, c3, hasA, hasB, ps, sp);
                     else        solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
-                    __stcg(M + 3 * PL, c3);
+                    st128_cg_pol(M + 3 * PL, c3, pol_stream);
                 }
                 if (PACKED) pair_to(ps, hasA, hasB, A, B);
-                if (hasA) store_body(dv, nd.z, A);
-                if (hasB) store_body(dv, nd.w, B);
+                if (hasA) store_body_keep(dv, nd.z, A, pol_keep);
+                if (hasB) store_body_keep(dv, nd.w, B, pol_keep);
             }
             grid.sync();
             if (it == 1 && tid == 0 && l < 4096) {
@@ -1675,6 +1696,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     const size_t PL = (size_t)dv.cap_contacts;
     if (tid == 0) { s_next = 0; level_start[0] = 0; }
     __syncthreads();
+    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();   // bodies stay in L2, records stream
     // ---- iteration 0: Kahn levels ----
     int head = 0, tail = n0, lvl = 0;
     bool bad = false;
@@ -1685,17 +1707,17 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
             const int gA = __float_as_int(nd.a.x), gB = __float_as_int(nd.b.x);
             const int sa = __float_as_int(nd.a.w), sb = __float_as_int(nd.b.w);
             const float4* L = dv.L + 4 * (size_t)c;
-            F8 lo = ld256_nc(L), hi = ld256_nc(L + 2);
+            F8 lo = ld256_nc_pol(L, pol_stream), hi = ld256_nc_pol(L + 2, pol_stream);
             float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
             const bool hasA = gA >= 0, hasB = gB >= 0;
             BodyState A, B;
-            if (hasA) load_body(dv, gA, A);
-            if (hasB) load_body(dv, gB, B);
+            if (hasA) load_body_keep(dv, gA, A, pol_keep);
+            if (hasB) load_body_keep(dv, gB, B, pol_keep);
             solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
-            if (hasA) store_body(dv, gA, A);
-            if (hasB) store_body(dv, gB, B);
+            if (hasA) store_body_keep(dv, gA, A, pol_keep);
+            if (hasB) store_body_keep(dv, gB, B, pol_keep);
             float4* M = dv.M + base + p;
-            __stcg(M, c0); __stcg(M + PL, c1); __stcg(M + 2 * PL, c2); __stcg(M + 3 * PL, c3);
+            st128_cg_pol(M, c0, pol_stream); st128_cg_pol(M + PL, c1, pol_stream); st128_cg_pol(M + 2 * PL, c2, pol_stream); st128_cg_pol(M + 3 * PL, c3, pol_stream);
             __stcg(&gd[p], make_int4(gA, gB, c, 0));
             dv.slot_of[c] = (int)(base + p);
             if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < gcap) __stcg(&queue[q], sa); }
@@ -1738,15 +1760,15 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
                 int2 d = dc;
                 if (p != s0 + tid) { int4 t4 = __ldcg(&gd[p]); d = make_int2(t4.x, t4.y); }      // (levels wider than the block)
                 float4* M = dv.M + base + p;
-                float4 c0 = __ldcg(M), c1 = __ldcg(M + PL), c2 = __ldcg(M + 2 * PL), c3 = __ldcg(M + 3 * PL);
+                float4 c0 = ld128_cg_pol(M, pol_stream), c1 = ld128_cg_pol(M + PL, pol_stream), c2 = ld128_cg_pol(M + 2 * PL, pol_stream), c3 = ld128_cg_pol(M + 3 * PL, pol_stream);
                 const bool hasA = d.x >= 0, hasB = d.y >= 0;
                 BodyState A, B;
-                if (hasA) load_body(dv, d.x, A);
-                if (hasB) load_body(dv, d.y, B);
+                if (hasA) load_body_keep(dv, d.x, A, pol_keep);
+                if (hasB) load_body_keep(dv, d.y, B, pol_keep);
                 solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
-                if (hasA) store_body(dv, d.x, A);
-                if (hasB) store_body(dv, d.y, B);
-                __stcg(M + 3 * PL, c3);
+                if (hasA) store_body_keep(dv, d.x, A, pol_keep);
+                if (hasB) store_body_keep(dv, d.y, B, pol_keep);
+                st128_cg_pol(M + 3 * PL, c3, pol_stream);
             }
             __syncthreads();
         }
