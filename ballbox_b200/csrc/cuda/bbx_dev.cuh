@@ -352,6 +352,12 @@ __device__ __forceinline__ float4 ld128_cg_pol(const float4* p, unsigned long lo
     asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
     return r;
 }
+__device__ __forceinline__ int4 ld128i_cg_pol(const int4* p, unsigned long long pol)
+{
+    int4 r;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ void st128_cg_pol(float4* p, float4 v, unsigned long long pol)
 {
     asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");

@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
             int4 nd0 = make_int4(-1, -1, 0, 0);
             if (live) {
                 c = __ldcg(&dv.queue_k[k][p]);
-                F8 rec = ld256_nc((const float4*)&dv.node[2 * (size_t)c]);       // ids, run length, successors: one sector
+                F8 rec = ld256_nc_pol((const float4*)&dv.node[2 * (size_t)c], pol_stream);       // ids, run length, successors: one sector
                 nd0 = make_int4(__float_as_int(rec.a.x), __float_as_int(rec.a.y), __float_as_int(rec.a.z), 0);
                 sa = __float_as_int(rec.b.x); sb = __float_as_int(rec.b.y);
                 m = nd0.z;
@@ -982,7 +982,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= pref[kk]) { k = kk; kbase = pref[kk]; }
                 int idx = t - kbase;
                 if (idx >= cnt[k]) continue;
-                int4 nd = __ldcg(&dv.Nd_k[k][head[k] + idx]);
+                int4 nd = ld128i_cg_pol(&dv.Nd_k[k][head[k] + idx], pol_stream);
                 bool hasA = nd.z >= 0, hasB = nd.w >= 0;
                 BodyState A, B;
                 if (hasA) load_body_keep(dv, nd.z, A, pol_keep);
@@ -1703,7 +1703,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     while (head < tail) {
         for (int p = head + tid; p < tail; p += GRP_THREADS) {
             const int c = __ldcg(&queue[p]);
-            F8 nd = ld256_nc((const float4*)&dv.node[2 * (size_t)c]);    // (gid A, pos, len, successor on A) (same for B)
+            F8 nd = ld256_nc_pol((const float4*)&dv.node[2 * (size_t)c], pol_stream);    // (gid A, pos, len, successor on A) (same for B)
             const int gA = __float_as_int(nd.a.x), gB = __float_as_int(nd.b.x);
             const int sa = __float_as_int(nd.a.w), sb = __float_as_int(nd.b.w);
             const float4* L = dv.L + 4 * (size_t)c;
@@ -1740,7 +1740,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     // swept (descriptors are static), so that after the barrier the body loads can be issued at once; the next
     // level's records are pulled into L2 at the same time (prefetch, no registers).
     int2 dn = make_int2(-1, -1);
-    { const int pn = level_start[0] + tid; if (pn < level_start[1]) { int4 t4 = __ldcg(&gd[pn]); dn = make_int2(t4.x, t4.y); } }
+    { const int pn = level_start[0] + tid; if (pn < level_start[1]) { int4 t4 = ld128i_cg_pol(&gd[pn], pol_stream); dn = make_int2(t4.x, t4.y); } }
     for (int it = 1; it < sp.iterations; it++) {
         for (int l = 0; l < n_levels; l++) {
             const int s0 = level_start[l], s1 = level_start[l + 1];
@@ -1750,7 +1750,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
                 const int pn = level_start[ln] + tid;
                 dn = make_int2(-1, -1);
                 if (pn < level_start[ln + 1]) {
-                    int4 t4 = __ldcg(&gd[pn]); dn = make_int2(t4.x, t4.y);
+                    int4 t4 = ld128i_cg_pol(&gd[pn], pol_stream); dn = make_int2(t4.x, t4.y);
                     const float4* Mn = dv.M + base + pn;
                     prefetch_l2(Mn); prefetch_l2(Mn + PL); prefetch_l2(Mn + 2 * PL);
                     if (n_levels > 1) prefetch_l2(Mn + 3 * PL);
@@ -1758,7 +1758,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
             }
             for (int p = s0 + tid; p < s1; p += GRP_THREADS) {
                 int2 d = dc;
-                if (p != s0 + tid) { int4 t4 = __ldcg(&gd[p]); d = make_int2(t4.x, t4.y); }      // (levels wider than the block)
+                if (p != s0 + tid) { int4 t4 = ld128i_cg_pol(&gd[p], pol_stream); d = make_int2(t4.x, t4.y); }      // (levels wider than the block)
                 float4* M = dv.M + base + p;
                 float4 c0 = ld128_cg_pol(M, pol_stream), c1 = ld128_cg_pol(M + PL, pol_stream), c2 = ld128_cg_pol(M + 2 * PL, pol_stream), c3 = ld128_cg_pol(M + 3 * PL, pol_stream);
                 const bool hasA = d.x >= 0, hasB = d.y >= 0;
