@@ -841,7 +841,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     __shared__ LevelMap lm;
     __shared__ int s_pcnt[BBX_NCLS], s_pbase[BBX_NCLS];
     constexpr bool PACKED0 = false;                 // iteration 0 keeps the scalar sweep (register budget of the discovery pass)
-    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+    const bool big = dv.ctr->n_contacts > BBX_L2_STREAM_CONTACTS;
+    const unsigned long long pol_keep = big ? l2_policy_keep() : l2_policy_normal(), pol_stream = big ? l2_policy_stream() : l2_policy_normal();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
     // work index of this thread: consecutive 32-node chunks go round-robin over the BLOCKS, so a level
@@ -1696,7 +1697,8 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     const size_t PL = (size_t)dv.cap_contacts;
     if (tid == 0) { s_next = 0; level_start[0] = 0; }
     __syncthreads();
-    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();   // bodies stay in L2, records stream
+    const bool big = dv.ctr->n_contacts > BBX_L2_STREAM_CONTACTS;     // bodies stay in L2, records stream
+    const unsigned long long pol_keep = big ? l2_policy_keep() : l2_policy_normal(), pol_stream = big ? l2_policy_stream() : l2_policy_normal();
     // ---- iteration 0: Kahn levels ----
     int head = 0, tail = n0, lvl = 0;
     bool bad = false;
