@@ -382,8 +382,8 @@ def main():
     stepb = step_bytes(r["ns"], r["nb"], P_, r["contacts"], D_, I)
     step_ach = stepb / (r["ms"] / args.steps * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of k_solve_levels for this exact scene (C3, 1M bodies, settle
-    # 1500) from the ncu capture summarised in profiles/r01h_launches_c3_1M.md; null for any other scene
-    traffic = 6007.4e6 + 1995.6e6 if (args.bodies == 1_000_000 and args.settle == 1500) else None
+    # 1500) from the ncu capture summarised in profiles/r01i_launches_c3_1M.md; null for any other scene
+    traffic = 5021.3e6 + 1595.0e6 if (args.bodies == 1_000_000 and args.settle == 1500) else None
     roofline = {"bound": "hbm", "kernel": "k_solve_levels", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "bound by waiting (grid barrier 46-51 % of stall samples, issue slots 24-33 % active), not by HBM: profiles/r01_notes.md",
