@@ -345,6 +345,8 @@ def main():
     dist = None
     if world_size > 1:
         import torch.distributed as dist
+        # stdout carries the ONE JSON line: NCCL's own banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
