@@ -388,7 +388,7 @@ def main():
     traffic = 5021.3e6 + 1595.0e6 if (args.bodies == 1_000_000 and args.settle == 1500) else None
     roofline = {"bound": "hbm", "kernel": "k_solve_levels", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "bound by waiting (grid barrier 46-51 % of stall samples, issue slots 24-33 % active), not by HBM: profiles/r01_notes.md",
+                "note": "bound by waiting (barriers 48 % of stall samples, issue slots 23 % active), not by HBM: profiles/r01i_ncu_solve_levels.md, profiles/r01_notes.md",
                 "algorithmic_bytes_per_launch": sb, "ms_per_launch": solve_ms,
                 "whole_step": {"algorithmic_bytes": stepb, "achieved": step_ach, "frac": step_ach / peak}}
 
