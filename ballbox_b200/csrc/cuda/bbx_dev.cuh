@@ -171,6 +171,7 @@ struct BbxDev {
     // snapshot for per-world resets (allocated by bbx_dev_snapshot)
     float4 *snap_pos, *snap_vel, *snap_boxq; float *snap_timer; unsigned char *snap_flags; int *reset_ids;
     int forces_on_device;        // accumulators were written through the device views
+    int *wake_ids; int wake_cap; // scratch of bbx_dev_wake_bodies
     int imported_list;           // the device contact list was imported from the host in array order
     int wb_attr_set;             // dynamic shared memory attribute of the per-world solve kernel was set
 

@@ -1676,7 +1676,9 @@ __global__ void __launch_bounds__(256) k_frontier0_groups(BbxDev dv, int* gq, in
             int w = x < dv.NS ? x / dv.cap_s : (x - dv.NS) / dv.cap_b;
             int g = w / wpb;
             int slot = atomicAdd(&gq_count[g], 1);
-            if (slot < gcap) gq[(size_t)g * gcap + slot] = c;
+            // the LAST group may hold fewer than wpb worlds: its slice ends with the allocation, not after gcap slots
+            const long long glim = min((long long)gcap, (long long)dv.cap_contacts - (long long)g * gcap);
+            if (slot < glim) gq[(size_t)g * gcap + slot] = c;
         }
     }
     if (mine) atomicAdd(&s_solver, mine);
@@ -1689,7 +1691,11 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     __shared__ int level_start[GRP_LMAX + 2];
     __shared__ int s_next;
     const int g = blockIdx.x, tid = threadIdx.x;
-    const int n0 = min(gq_count[g], gcap);
+    // slots this group owns in queue / M / Nd: gcap, except for a ragged last group (fewer than wpb worlds), whose slice
+    // ends with the allocations; every append and the overflow test are bounded by it
+    const int glim = (int)min((long long)gcap, (long long)dv.cap_contacts - (long long)g * gcap);
+    if (gq_count[g] > glim) { if (tid == 0) atomicOr(&dv.ctr->overflow, 32); return; }
+    const int n0 = gq_count[g];
     if (n0 == 0) return;                                              // no dynamic contact in this group
     int* queue = gq + (size_t)g * gcap;                               // visiting order of the group
     const size_t base = (size_t)g * gcap;                             // the group's slice of M / Nd / slot numbers
@@ -1722,14 +1728,14 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
             st128_cg_pol(M, c0, pol_stream); st128_cg_pol(M + PL, c1, pol_stream); st128_cg_pol(M + 2 * PL, c2, pol_stream); st128_cg_pol(M + 3 * PL, c3, pol_stream);
             __stcg(&gd[p], make_int4(gA, gB, c, 0));
             dv.slot_of[c] = (int)(base + p);
-            if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < gcap) __stcg(&queue[q], sa); }
-            if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < gcap) __stcg(&queue[q], sb); }
+            if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) __stcg(&queue[q], sa); }
+            if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) __stcg(&queue[q], sb); }
         }
         __syncthreads();
         const int pushed = s_next;
         __syncthreads();
         head = tail; tail += pushed; lvl++;
-        if (tail > gcap || lvl > GRP_LMAX) { bad = true; break; }
+        if (tail > glim || lvl > GRP_LMAX) { bad = true; break; }
         if (tid == 0) { s_next = 0; level_start[lvl] = head; }
         __syncthreads();
     }
@@ -1788,10 +1794,12 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
 {
     __shared__ int s_next;
     const int g = blockIdx.x, tid = threadIdx.x;
-    int n_cur = min(gq_count[g], gcap);
+    const int glim = (int)min((long long)gcap, (long long)dv.cap_contacts - (long long)g * gcap);      // ragged last group, see k_solve_groups
+    if (gq_count[g] > glim) { if (tid == 0) atomicOr(&dv.ctr->overflow, 32); return; }
+    int n_cur = gq_count[g];
     if (n_cur == 0) return;                                           // no dynamic contact in this group
     int2* cur = reinterpret_cast<int2*>(dv.Nd_k[0] + (size_t)g * gcap);   // two wavefront lists of (constraint, sweep) in the group's
-    int2* nxt = cur + gcap;                                               // descriptor slice (int4 per slot = room for both)
+    int2* nxt = cur + glim;                                               // descriptor slice (int4 per slot = room for both)
     for (int p = tid; p < n_cur; p += GRP_THREADS) cur[p] = make_int2(gq[(size_t)g * gcap + p], 0);
     if (tid == 0) s_next = 0;
     __syncthreads();
@@ -1823,7 +1831,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
                 const int tgt = s & (ADJ_WRAP - 1), tit = (s & ADJ_WRAP) ? it + 1 : it;
                 if (tit < sp.iterations && atomicSub(&dv.indeg[tgt], 1) == 1) {
                     const int q = atomicAdd(&s_next, 1);
-                    if (q < gcap) __stcg(&nxt[q], make_int2(tgt, tit));
+                    if (q < glim) __stcg(&nxt[q], make_int2(tgt, tit));
                 }
             }
         }
@@ -1831,7 +1839,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
         const int pushed = s_next;
         __syncthreads();
         if (tid == 0) s_next = 0;
-        if (pushed > gcap) { bad = true; break; }
+        if (pushed > glim) { bad = true; break; }
         int2* t = cur; cur = nxt; nxt = t;
         n_cur = pushed; waves++;
         __syncthreads();

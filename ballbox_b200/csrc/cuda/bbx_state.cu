@@ -156,7 +156,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->boxq, d->half, d->brec, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
-        d->sdf_grid, d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
+        d->sdf_grid, d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->wake_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan, d->warm_key, d->warm_val, d->warm_epoch };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
@@ -534,6 +534,37 @@ extern "C" int bbx_dev_add_wrench(BbxDev* d, const float* sf, const float* st, c
     BBX_LAUNCH(d, k_add_wrench, bbx_blocks(d->N, 256), 256, 0, *d, sf, st, bf, bt);
     BBX_CUDA(d, cudaGetLastError());
     d->forces_on_device = 1;
+    return 0;
+}
+
+// Add*Force/Torque on a resident world (ballbox.h:420-423 & co.): the listed body slots wake up, whatever the force was
+__global__ void __launch_bounds__(256) k_wake_list(BbxDev dv, const int* ids, int n)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int g = ids[t];
+    if (g < 0 || g >= dv.N) return;
+    const unsigned char f = dv.flags[g];
+    if ((f & BF_VALID) && (f & BF_SLEEP)) { dv.flags[g] = f & (unsigned char)~BF_SLEEP; dv.timer[g] = 0.0f; }      // duplicates write the same values
+}
+
+extern "C" int bbx_dev_wake_bodies(BbxDev* d, const int* slots, int n)
+{
+    if (!d || (n > 0 && !slots)) return BBX_ERR_BAD_ARGUMENT;
+    if (d->has_err) return BBX_ERR_STICKY;
+    if (n <= 0) return 0;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    if (n > d->wake_cap) {
+        if (d->wake_ids) BBX_CUDA(d, cudaFree(d->wake_ids));
+        d->wake_ids = NULL; d->wake_cap = 0;
+        int cap = 1024;
+        while (cap < n) cap *= 2;
+        BBX_CUDA(d, cudaMalloc((void**)&d->wake_ids, sizeof(int) * (size_t)cap));
+        d->wake_cap = cap;
+    }
+    BBX_CUDA(d, cudaMemcpyAsync(d->wake_ids, slots, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, d->stream));   // pageable source: staged before the call returns
+    BBX_LAUNCH(d, k_wake_list, bbx_blocks(n, 256), 256, 0, *d, d->wake_ids, n);
+    BBX_CUDA(d, cudaGetLastError());
     return 0;
 }
 

@@ -47,6 +47,8 @@ struct PhysicsWorldBatch {
     float bake_lo[3], bake_hi[3];
     SDFFunction baked_fn;
     int uploaded, forces_dirty, n_callbacks, cb_dirty, timing;
+    int dev_ahead;                      /* device steps ran since the host arrays were last in sync (upload or body download) */
+    int *wake_ids; int n_wake, cap_wake;    /* bodies woken by Add*Force/Torque while the state is resident (:420-423) */
     CollisionContact* ev_contacts; int *ev_steps, *ev_worlds; int ev_cap;
     int has_err; char err[256];
 };
@@ -192,7 +194,7 @@ static void batch_free(struct PhysicsWorldBatch* b)
     for (int i = 0; i < 25; i++) bbx_host_free(arrs[i], b->pinned[i]);
     bbx_host_free(b->constraints, b->pinned_constraints);
     if (b->worlds) for (int w = 0; w < b->n_worlds; w++) free(b->worlds[w].collisions.contacts);
-    free(b->ev_contacts); free(b->ev_steps); free(b->ev_worlds);
+    free(b->ev_contacts); free(b->ev_steps); free(b->ev_worlds); free(b->wake_ids);
     free(b->s_count); free(b->b_count); free(b->s_cb); free(b->b_cb); free(b->ccount); free(b->worlds);
     b->magic = 0;
     free(b);
@@ -372,13 +374,27 @@ void SetManifoldSettings(PhysicsWorld* w, float tol, float pen_tol, int max_cont
 /* ------------------------------------------------------------------------- */
 static const Vec3 V0 = {0.0f, 0.0f, 0.0f};
 
-static void note_count(PhysicsWorld* w)
+static int batch_download(struct PhysicsWorldBatch* b, int what);
+
+/* RESIDENT coherence.  While the state lives in HBM the host arrays are stale after the first device step.  An edit
+ * of the host arrays that the device must see (a new body, a mass, a static flag, a sync-mode change) therefore
+ * first brings the host arrays up to date (one body download, only if device steps ran since the last sync) and then
+ * schedules a full re-upload before the next step.  Without this a re-upload would silently snap the simulation back
+ * to the last downloaded state. */
+static void host_edit_begin(PhysicsWorld* w)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return;
+    struct PhysicsWorldBatch* b = p->batch;
+    if (b->dev && b->uploaded && b->dev_ahead && !b->has_err) batch_download(b, BBX_DL_BODIES);
+}
+static void host_edit_end(PhysicsWorld* w)
 {
     BbxWorldPriv* p = priv_of(w);
     if (!p) return;
     p->batch->s_count[p->index] = p->spheres.count;
     p->batch->b_count[p->index] = p->boxes.count;
-    p->batch->uploaded = 0;             /* topology changed: resident state must be re-uploaded */
+    p->batch->uploaded = 0;             /* host arrays are the truth again: re-upload before the next step */
 }
 
 int AddSphere(PhysicsWorld* world, Vec3 position, float radius)
@@ -386,14 +402,29 @@ int AddSphere(PhysicsWorld* world, Vec3 position, float radius)
     if (!world || !world->spheres) return -1;
     SphereSystem* s = world->spheres;
     if (s->count >= s->capacity) return -1;
+    host_edit_begin(world);
     int i = s->count;
     s->positions[i] = position; s->radii[i] = radius;
     s->velocities[i] = V0; s->forces[i] = V0; s->angular_velocities[i] = V0; s->torques[i] = V0;
     s->masses[i] = 1.0f;
     s->inertias[i] = (2.0f / 5.0f) * s->masses[i] * radius * radius;
     s->count++;
-    note_count(world);
+    host_edit_end(world);
     return i;
+}
+
+/* ballbox.h:382-386 / :747-752: plain writes into a system's arrays (no world argument).  COMPAT worlds see them at
+ * the next PhysicsStep like any direct array write; a RESIDENT world needs BallboxUpload, as for every host-side write. */
+void UpdateSphere(SphereSystem* system, int index, Vec3 position)
+{
+    if (!system || index < 0 || index >= system->count) return;
+    system->positions[index] = position;
+}
+void UpdateBox(BoxSystem* system, int index, Vec3 position, Quat rotation)
+{
+    if (!system || index < 0 || index >= system->count) return;
+    system->positions[index] = position;
+    system->rotations[index] = rotation;
 }
 
 void SetSphereMass(PhysicsWorld* world, int i, float mass)
@@ -401,9 +432,11 @@ void SetSphereMass(PhysicsWorld* world, int i, float mass)
     if (!world || !world->spheres) return;
     SphereSystem* s = world->spheres;
     if (i < 0 || i >= s->count || mass <= 0.0f) return;
+    host_edit_begin(world);
     s->masses[i] = mass;
     float r = s->radii[i];
     s->inertias[i] = (2.0f / 5.0f) * mass * r * r;
+    host_edit_end(world);
 }
 
 void SetSphereStatic(PhysicsWorld* world, int i, bool is_static)
@@ -411,11 +444,30 @@ void SetSphereStatic(PhysicsWorld* world, int i, bool is_static)
     if (!world || !world->spheres) return;
     SphereSystem* s = world->spheres;
     if (i < 0 || i >= s->count) return;
+    host_edit_begin(world);
     s->is_static[i] = is_static;
     if (is_static) { s->velocities[i] = V0; s->angular_velocities[i] = V0; s->forces[i] = V0; s->torques[i] = V0; }
+    host_edit_end(world);
 }
 
-static void mark_forces(PhysicsWorld* w) { BbxWorldPriv* p = priv_of(w); if (p) p->batch->forces_dirty = 1; }
+/* Add*Force/Torque wake a sleeping body even when the force is zero (:420-423, :434-437, :793-796, :807-810).  The
+ * host's is_sleeping is stale while the state is resident, so the body is ALSO put on a wake list that the next
+ * resident step applies on the device before it integrates (bbx_dev_wake_bodies). */
+static void mark_forces(PhysicsWorld* w, int is_box, int i)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return;
+    struct PhysicsWorldBatch* b = p->batch;
+    b->forces_dirty = 1;
+    if (!b->uploaded) return;                          /* the next step uploads the host flags themselves */
+    if (b->n_wake == b->cap_wake) {
+        int cap = b->cap_wake ? 2 * b->cap_wake : 256;
+        int* q = (int*)realloc(b->wake_ids, sizeof(int) * (size_t)cap);
+        if (!q) return;
+        b->wake_ids = q; b->cap_wake = cap;
+    }
+    b->wake_ids[b->n_wake++] = is_box ? b->n_worlds * b->cap_s + p->index * b->cap_b + i : p->index * b->cap_s + i;
+}
 
 void AddSphereForce(PhysicsWorld* world, int i, Vec3 f)
 {
@@ -424,7 +476,7 @@ void AddSphereForce(PhysicsWorld* world, int i, Vec3 f)
     if (i < 0 || i >= s->count) return;
     if (s->is_sleeping[i]) { s->is_sleeping[i] = false; s->sleep_timers[i] = 0.0f; }
     s->forces[i] = Vec3Add(s->forces[i], f);
-    mark_forces(world);
+    mark_forces(world, 0, i);
 }
 
 void AddSphereTorque(PhysicsWorld* world, int i, Vec3 t)
@@ -434,7 +486,7 @@ void AddSphereTorque(PhysicsWorld* world, int i, Vec3 t)
     if (i < 0 || i >= s->count) return;
     if (s->is_sleeping[i]) { s->is_sleeping[i] = false; s->sleep_timers[i] = 0.0f; }
     s->torques[i] = Vec3Add(s->torques[i], t);
-    mark_forces(world);
+    mark_forces(world, 0, i);
 }
 
 static Vec3 box_inertia(float m, Vec3 half)
@@ -449,6 +501,7 @@ int AddBox(PhysicsWorld* world, Vec3 position, Vec3 size, Quat rotation)
     if (!world || !world->boxes) return -1;
     BoxSystem* b = world->boxes;
     if (b->count >= b->capacity) return -1;
+    host_edit_begin(world);
     int i = b->count;
     b->positions[i] = position; b->sizes[i] = size; b->rotations[i] = rotation;
     b->velocities[i] = V0; b->forces[i] = V0; b->angular_velocities[i] = V0; b->torques[i] = V0;
@@ -456,7 +509,7 @@ int AddBox(PhysicsWorld* world, Vec3 position, Vec3 size, Quat rotation)
     b->inertias[i] = box_inertia(b->masses[i], size);
     b->is_static[i] = false; b->is_sleeping[i] = false; b->sleep_timers[i] = 0.0f;
     b->count++;
-    note_count(world);
+    host_edit_end(world);
     return i;
 }
 
@@ -465,8 +518,10 @@ void SetBoxMass(PhysicsWorld* world, int i, float mass)
     if (!world || !world->boxes) return;
     BoxSystem* b = world->boxes;
     if (i < 0 || i >= b->count || mass <= 0.0f) return;
+    host_edit_begin(world);
     b->masses[i] = mass;
     b->inertias[i] = box_inertia(mass, b->sizes[i]);
+    host_edit_end(world);
 }
 
 void SetBoxStatic(PhysicsWorld* world, int i, bool is_static)
@@ -474,8 +529,10 @@ void SetBoxStatic(PhysicsWorld* world, int i, bool is_static)
     if (!world || !world->boxes) return;
     BoxSystem* b = world->boxes;
     if (i < 0 || i >= b->count) return;
+    host_edit_begin(world);
     b->is_static[i] = is_static;
     if (is_static) { b->velocities[i] = V0; b->angular_velocities[i] = V0; b->forces[i] = V0; b->torques[i] = V0; }
+    host_edit_end(world);
 }
 
 void AddBoxForce(PhysicsWorld* world, int i, Vec3 f)
@@ -485,7 +542,7 @@ void AddBoxForce(PhysicsWorld* world, int i, Vec3 f)
     if (i < 0 || i >= b->count) return;
     if (b->is_sleeping[i]) { b->is_sleeping[i] = false; b->sleep_timers[i] = 0.0f; }
     b->forces[i] = Vec3Add(b->forces[i], f);
-    mark_forces(world);
+    mark_forces(world, 1, i);
 }
 
 void AddBoxTorque(PhysicsWorld* world, int i, Vec3 t)
@@ -495,7 +552,7 @@ void AddBoxTorque(PhysicsWorld* world, int i, Vec3 t)
     if (i < 0 || i >= b->count) return;
     if (b->is_sleeping[i]) { b->is_sleeping[i] = false; b->sleep_timers[i] = 0.0f; }
     b->torques[i] = Vec3Add(b->torques[i], t);
-    mark_forces(world);
+    mark_forces(world, 1, i);
 }
 
 static void recount_callbacks(struct PhysicsWorldBatch* b)
@@ -619,7 +676,7 @@ static int batch_upload(struct PhysicsWorldBatch* b)
     if (rc) return rc;
     for (int w = 0; w < b->n_worlds; w++) { b->s_count[w] = b->worlds[w].spheres.count; b->b_count[w] = b->worlds[w].boxes.count; }
     rc = batch_check_dev(b, bbx_dev_upload(b->dev, &b->hb));
-    if (!rc) { b->uploaded = 1; b->cb_dirty = 0; }
+    if (!rc) { b->uploaded = 1; b->cb_dirty = 0; b->dev_ahead = 0; b->n_wake = 0; }
     return rc;
 }
 
@@ -743,7 +800,7 @@ static int batch_download(struct PhysicsWorldBatch* b, int what)
 {
     if (!b->dev) return 0;
     int rc = 0;
-    if (what & BBX_DL_BODIES) rc = batch_check_dev(b, bbx_dev_download(b->dev, &b->hb));
+    if (what & BBX_DL_BODIES) { rc = batch_check_dev(b, bbx_dev_download(b->dev, &b->hb)); if (!rc) b->dev_ahead = 0; }
     if (!rc && (what & BBX_DL_CONSTRAINTS)) {
         rc = batch_check_dev(b, bbx_dev_download_constraints(b->dev, b->constraints, b->cap_c, b->ccount));
         if (!rc) for (int w = 0; w < b->n_worlds; w++) b->worlds[w].constraints.count = b->ccount[w];
@@ -862,6 +919,11 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
         if ((rc = batch_check_dev(b, bbx_dev_upload_callback_flags(b->dev, &b->hb)))) return rc;
         b->cb_dirty = 0;
     }
+    if (b->n_wake > 0) {                     /* Add*Force/Torque on resident bodies: wake them on the device (:420-423) */
+        if ((rc = batch_check_dev(b, bbx_dev_wake_bodies(b->dev, b->wake_ids, b->n_wake)))) return rc;
+        b->n_wake = 0;
+    }
+    b->dev_ahead = 1;
     if (b->n_callbacks > 0) {
         /* Events are appended on the device right after detection and replayed here, after the
          * steps, in (step, emission) order.  Chunks bound the size of the event buffer. */
@@ -1045,7 +1107,13 @@ int PhysicsStepN(PhysicsWorld* world, float dt, int steps)
     return batch_step(p->batch, dt, steps);
 }
 
-void BallboxSetSyncMode(PhysicsWorld* w, int mode) { BbxWorldPriv* p = priv_of(w); if (p) { p->batch->sync_mode = mode; p->batch->uploaded = 0; } }
+void BallboxSetSyncMode(PhysicsWorld* w, int mode)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p) return;
+    host_edit_begin(w);                  /* leaving RESIDENT: the host arrays become the truth, so make them current first */
+    p->batch->sync_mode = mode; p->batch->uploaded = 0;
+}
 int  BallboxUpload(PhysicsWorld* w) { BbxWorldPriv* p = priv_of(w); return p ? batch_upload(p->batch) : BBX_ERR_BAD_ARGUMENT; }
 int  BallboxDownload(PhysicsWorld* w, int what) { BbxWorldPriv* p = priv_of(w); return p ? batch_download(p->batch, what) : BBX_ERR_BAD_ARGUMENT; }
 int  BallboxSynchronize(PhysicsWorld* w)
@@ -1149,6 +1217,7 @@ int BatchAddWrenchDevice(PhysicsWorldBatch* b, const float* sf, const float* st,
     if (!batch_ok(b)) return BBX_ERR_BAD_ARGUMENT;
     int rc;
     if (!b->uploaded && (rc = batch_upload(b))) return rc;
+    b->dev_ahead = 1;
     return batch_check_dev(b, bbx_dev_add_wrench(b->dev, sf, st, bf, bt));
 }
 int BatchSnapshot(PhysicsWorldBatch* b)
@@ -1161,6 +1230,7 @@ int BatchSnapshot(PhysicsWorldBatch* b)
 int BatchResetWorlds(PhysicsWorldBatch* b, const int* ids, int n)
 {
     if (!batch_ok(b) || !b->dev) return BBX_ERR_BAD_ARGUMENT;
+    b->dev_ahead = 1;
     return batch_check_dev(b, bbx_dev_restore_worlds(b->dev, ids, n));
 }
 

@@ -236,6 +236,7 @@ Vec3  QuatRotateVec3(Quat q, Vec3 v);
 SphereSystem* CreateSphereSystem(int capacity);
 void DestroySphereSystem(SphereSystem* system);
 int  AddSphere(PhysicsWorld* world, Vec3 position, float radius);
+void UpdateSphere(SphereSystem* system, int index, Vec3 position);            /* defined with external linkage at ref :382 */
 void SetSphereMass(PhysicsWorld* world, int index, float mass);
 void SetSphereStatic(PhysicsWorld* world, int index, bool is_static);
 void AddSphereForce(PhysicsWorld* world, int index, Vec3 force);
@@ -245,6 +246,7 @@ void AddSphereTorque(PhysicsWorld* world, int index, Vec3 torque);
 BoxSystem* CreateBoxSystem(int capacity);
 void DestroyBoxSystem(BoxSystem* system);
 int  AddBox(PhysicsWorld* world, Vec3 position, Vec3 size, Quat rotation);
+void UpdateBox(BoxSystem* system, int index, Vec3 position, Quat rotation);   /* defined with external linkage at ref :747 */
 void SetBoxMass(PhysicsWorld* world, int index, float mass);
 void SetBoxStatic(PhysicsWorld* world, int index, bool is_static);
 void AddBoxForce(PhysicsWorld* world, int index, Vec3 force);

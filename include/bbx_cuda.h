@@ -77,6 +77,9 @@ void bbx_dev_set_stream(BbxDev* dev, void* cuda_stream);
 int  bbx_dev_upload(BbxDev* dev, const BbxHostBodies* hb);
 /* forces and torques only (AddSphereForce & co. between resident steps) */
 int  bbx_dev_upload_forces(BbxDev* dev, const BbxHostBodies* hb);
+/* body slots (sphere (w,i) = w*cap_s + i, box (w,i) = n_worlds*cap_s + w*cap_b + i) that Add*Force/Torque touched since the
+ * last upload: a sleeping one wakes up, timer 0 (ballbox.h:420-423, :434-437, :793-796, :807-810), even for a zero force */
+int  bbx_dev_wake_bodies(BbxDev* dev, const int* slots, int n);
 int  bbx_dev_step(BbxDev* dev, const BbxStepParams* params, int steps);
 int  bbx_dev_download(BbxDev* dev, const BbxHostBodies* hb);
 /* Overlap helpers of the drop-in PhysicsStep (host arrays in, host arrays out):
