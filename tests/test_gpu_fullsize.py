@@ -73,7 +73,7 @@ def test_c4_full_size_settled_sdf_terrain_against_pruned_reference(product, trut
 def test_c2_full_size_settled_balls_against_pruned_reference(product, truth):
     """BASELINE config 2 (100k spheres in six walls), settled 300 steps."""
     g, c, st = settle_then_compare(product, truth, bb.SCENE_BALLS, 100_000, 300)
-    assert st.contacts > 250_000, st.contacts
+    assert st.contacts > 150_000, st.contacts
     g.destroy(); c.destroy()
 
 
