@@ -9,10 +9,14 @@ scene, device resident.  Workloads (BASELINE.json configs):
       configuration the headline metric "body-steps/sec at 1M bodies" is quoted
       on).  A single world does not shard (sequential-order Gauss-Seidel), so at
       N > 1 every rank steps its own replica ("replicas only", weak scaling).
-  c5  4096 independent 256-body worlds per GPU, batched RL style; the batch is
-      the workload that shards (no collective on the step path, one NCCL
-      all-reduce of the statistics after the last step).  Reported next to c3
-      under "batched_worlds" at every N.
+  c5  ONE batch of 4096 independent 256-body worlds, batched RL style, partitioned
+      over the N GPUs (world w -> rank w // (4096/N), seeds by global world id:
+      ballbox_b200/sharding.py): the workload that shards.  No collective on the
+      step path, one NCCL all-reduce of the statistics after the last step.
+      Reported under "batched_worlds" at every N: "strong" (4096 worlds in total,
+      4096/N per GPU, with an order-independent 64-bit checksum of all worlds'
+      state hashes that must be identical at every N) and, at N > 1, "weak"
+      (4096 worlds per GPU).
 
 `--impl reference` times the reference's own CPU PhysicsStep (oracle/_ref, the
 unmodified header; falls back to the C port under oracle/) on a bounded sample.
@@ -32,6 +36,7 @@ sys.path.insert(0, ROOT)
 
 DT = 1.0 / 60.0
 WORKLOAD_C3 = "c3_mixed_pile_500k_spheres_500k_boxes_6_walls"
+SOLVE_KERNEL = "k_solve_levels"
 
 
 def load_peaks():
@@ -120,6 +125,65 @@ def cpu_sample(n_bodies=4000, steps=12, threads=1):
                       f"{dt / steps * 1e3:.1f} ms/step"}
 
 
+def cpu_sample_c5(settle=30, steps=30):
+    """Config 5 on ALL host cores: one reference world per thread (the reference is single-threaded and
+    has no global state, so independent worlds run side by side; ctypes releases the GIL during a call)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from ballbox_b200 import binding as bb, sharding
+    lib, kind = checker_lib()
+    threads = os.cpu_count() or 1
+    worlds = [lib.build_scene(bb.SCENE_RLWORLD, 0, sharding.world_seed(i)) for i in range(threads)]
+
+    def run(w, n):
+        for _ in range(n):
+            w.step(DT)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda w: run(w, settle), worlds))
+        t0 = time.perf_counter()
+        list(ex.map(lambda w: run(w, steps), worlds))
+        el = time.perf_counter() - t0
+    bodies = sum(w.n_spheres + w.n_boxes for w in worlds)
+    for w in worlds:
+        w.destroy()
+    return {"value": bodies * steps / el, "unit": "body-steps/s", "cores": threads, "kind": kind,
+            "sample": f"config 5: {threads} worlds of 256 bodies (seeds of worlds 0..{threads - 1}), one world per thread on "
+                      f"{threads} threads, {settle} untimed + {steps} timed full all-pairs PhysicsStep calls each; "
+                      f"{el / steps * 1e3:.2f} ms per step of all {threads} worlds"}
+
+
+STATE_S = ("pos", "vel", "angvel", "sleeping", "timer", "force", "torque")
+STATE_B = ("pos", "rot", "vel", "angvel", "sleeping", "timer", "force", "torque")
+
+
+def cpu_pruned_same_size(res, steps=1):
+    """The reference's own stage functions at the SAME size and state as the GPU arm (C3, 1M bodies, settled):
+    detection through the CPU grid of oracle/ref_shim.c (RefPhysicsStepPruned, identical results to the
+    all-pairs loops, tests/test_oracle.py) because the stock O(N^2) loops need ~9 h per step at this size."""
+    from ballbox_b200 import binding as bb
+    lib, kind = checker_lib()
+    g = res["world"]
+    g.download(bb.DL_BODIES)
+    c = lib.build_scene(bb.SCENE_MIXED, res["n_dynamic"], res["seed"])
+    sa, da = g.sphere_arrays(), c.sphere_arrays()
+    for k in STATE_S:
+        da[k][...] = sa[k]
+    sa, da = g.box_arrays(), c.box_arrays()
+    for k in STATE_B:
+        da[k][...] = sa[k]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c.step(DT, pruned=True)
+    el = time.perf_counter() - t0
+    bodies = c.n_spheres + c.n_boxes
+    contacts = len(c.constraints())
+    c.destroy()
+    return {"value": bodies * steps / el, "unit": "body-steps/s", "cores": 1, "kind": kind + "+cpu_grid",
+            "ms_per_step": el / steps * 1e3, "contacts": contacts,
+            "sample": f"same size and state as the GPU arm: {bodies} bodies, state copied from the settled GPU world, {steps} "
+                      f"step(s) of the reference's stage functions with the all-pairs loops replaced by a CPU grid "
+                      f"(oracle/ref_shim.c), 1 thread, no warm-up step"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -187,7 +251,8 @@ def run_c3(args, lib, torch, barrier, rank):
     from ballbox_b200 import binding as bb
     n = args.bodies
     t_build = time.perf_counter()
-    w = lib.build_scene(bb.SCENE_MIXED, n, 20261019 + rank)
+    seed = 20261019 + rank
+    w = lib.build_scene(bb.SCENE_MIXED, n, seed)
     w.set_sync_mode(bb.SYNC_RESIDENT)
     lib.dll.BallboxSetDevice(w.ptr, torch.cuda.current_device())
     w.upload()
@@ -208,7 +273,7 @@ def run_c3(args, lib, torch, barrier, rank):
            "launches": int(s1.kernel_launches - s0.kernel_launches), "clocks": clocks,
            "contacts": s1.contacts, "solver_contacts": s1.solver_contacts, "touched": s1.touched_bodies,
            "levels": s1.levels, "pairs": s1.candidate_pairs, "iters": iters, "ns": s1.spheres, "nb": s1.boxes,
-           "overflow": s1.overflow, "build_s": t_build, "settle_s": t_settle, "world": w}
+           "overflow": s1.overflow, "build_s": t_build, "settle_s": t_settle, "world": w, "seed": seed, "n_dynamic": n}
     return res
 
 
@@ -272,44 +337,63 @@ def run_small_config(lib, torch, kind, n, settle, steps, label):
     return out
 
 
-def run_c5(args, lib, torch, barrier, rank):
-    """4096 independent 256-body worlds per GPU."""
-    import ctypes as C
-    from ballbox_b200 import binding as bb
-    n_worlds = args.worlds
-    s, b, c = lib.scene_capacity(bb.SCENE_RLWORLD, 0)
-    batch = lib.dll.CreatePhysicsWorldBatch(n_worlds, s, b, c)
-    if not batch:
-        raise RuntimeError("CreatePhysicsWorldBatch failed")
-    for i in range(n_worlds):
-        lib.dll.BbxSceneBuild(lib.dll.BatchWorld(batch, i), bb.SCENE_RLWORLD, 0, 7000 + rank * n_worlds + i)
-    lib.dll.BatchSetDevice(batch, torch.cuda.current_device())
+def run_batched(args, lib, torch, barrier, ids):
+    """One rank's shard (global world ids `ids`) of a batch of independent 256-body worlds."""
+    from ballbox_b200 import binding as bb, sharding
     stream = torch.cuda.current_stream()
-    lib.dll.BatchSetStream(batch, C.c_void_p(stream.cuda_stream))
-
-    def chk():
-        e = lib.dll.BatchGetLastError(batch)
-        if e:
-            raise RuntimeError(e.decode())
-    lib.dll.BatchUpload(batch); chk()
+    shard = sharding.WorldShard(lib, ids, bb.SCENE_RLWORLD, device=torch.cuda.current_device(), stream=stream.cuda_stream)
     done = 0
-    while done < args.settle:
-        k = min(50, args.settle - done)
-        lib.dll.PhysicsStepBatch(batch, DT, k); lib.dll.BatchSynchronize(batch); chk(); done += k
-    lib.dll.PhysicsStepBatch(batch, DT, args.warmup); lib.dll.BatchSynchronize(batch); chk()
-    st0 = bb.BallboxStats(); lib.dll.BatchGetStats(batch, C.byref(st0))
+    while done < args.settle_worlds:
+        k = min(50, args.settle_worlds - done)
+        shard.step(DT, k); done += k
+    hash_settled = sharding.combine_hashes(shard.world_hashes().values())
+    shard.step(DT, args.warmup)
+    st0 = shard.stats()
     barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    lib.dll.PhysicsStepBatch(batch, DT, args.steps)
+    shard.step(DT, args.steps, sync=False)
     e1.record(stream)
-    torch.cuda.synchronize(); barrier(); chk()
+    torch.cuda.synchronize(); barrier(); shard.synchronize()
     ms = e0.elapsed_time(e1)
-    st = bb.BallboxStats(); lib.dll.BatchGetStats(batch, C.byref(st))
-    out = {"ms": ms, "bodies": st.spheres + st.boxes, "contacts": st.contacts, "levels": st.levels, "worlds": n_worlds,
-           "launches": int(st.kernel_launches - st0.kernel_launches), "overflow": st.overflow}
-    lib.dll.DestroyPhysicsWorldBatch(batch)
+    st = shard.stats()
+    hash_final = sharding.combine_hashes(shard.world_hashes().values())
+    out = {"ms": ms, "bodies": st.spheres + st.boxes, "contacts": st.contacts, "levels": st.levels, "worlds": len(ids),
+           "launches": int(st.kernel_launches - st0.kernel_launches), "overflow": st.overflow,
+           "hash_settled": hash_settled, "hash_final": hash_final}
+    shard.destroy()
     return out
+
+
+def pcie_probe(torch, barrier, mbytes=256, reps=4):
+    """Pinned-memory copy bandwidth of THIS rank while every rank copies at the same time (GB/s, CUDA events):
+    the host-side limit the drop-in call's 621 MB/step constraint download runs into at N > 1."""
+    n = mbytes << 20
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    out = {}
+    for name, (dst, src) in (("d2h_gbs", (host, dev)), ("h2d_gbs", (dev, host))):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize(); barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record(); torch.cuda.synchronize(); barrier()
+        out[name] = n * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return out
+
+
+def load_traffic(args, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (profiles/solver_traffic.json), only when it was taken on exactly this scene and kernel; else null."""
+    p = os.path.join(ROOT, "profiles", "solver_traffic.json")
+    try:
+        t = json.load(open(p))
+    except Exception:
+        return None, None
+    if t.get("bodies") != args.bodies or t.get("settle") != args.settle or t.get("kernel") != kernel:
+        return None, None
+    return float(t["dram_read_bytes"]) + float(t["dram_write_bytes"]), t.get("source")
 
 
 def main():
@@ -319,13 +403,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bodies", type=int, default=1_000_000, help="dynamic bodies of the C3 scene")
-    ap.add_argument("--worlds", type=int, default=4096, help="C5 worlds per GPU")
+    ap.add_argument("--worlds", type=int, default=4096, help="C5: worlds of the ONE batch that is partitioned over the GPUs "
+                    "(strong scaling); the weak figure at N > 1 uses this many worlds per GPU")
     ap.add_argument("--settle", type=int, default=1500, help="untimed settle steps before measuring (a 160-unit tall pile needs ~1500)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--settle-worlds", type=int, default=300, help="untimed settle steps of the batched worlds")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--ref-bodies", type=int, default=4000, help="size of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--skip-batched", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-pruned", action="store_true", help="skip the same-size CPU leg (reference stage functions + CPU grid at 1M bodies, ~30 s)")
     ap.add_argument("--skip-others", action="store_true", help="do not time configs 2 and 4 (N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -383,30 +470,66 @@ def main():
     achieved = sb / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
     stepb = step_bytes(r["ns"], r["nb"], P_, r["contacts"], D_, I)
     step_ach = stepb / (r["ms"] / args.steps * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of k_solve_levels for this exact scene (C3, 1M bodies, settle
-    # 1500) from the ncu capture summarised in profiles/r01i_launches_c3_1M.md; null for any other scene
-    traffic = 5021.3e6 + 1595.0e6 if (args.bodies == 1_000_000 and args.settle == 1500) else None
-    roofline = {"bound": "hbm", "kernel": "k_solve_levels", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    traffic, traffic_src = load_traffic(args, SOLVE_KERNEL)
+    roofline = {"bound": "hbm", "kernel": SOLVE_KERNEL, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "note": "bound by waiting (barriers 48 % of stall samples, issue slots 23 % active), not by HBM: profiles/r01i_ncu_solve_levels.md, profiles/r01_notes.md",
                 "algorithmic_bytes_per_launch": sb, "ms_per_launch": solve_ms,
                 "whole_step": {"algorithmic_bytes": stepb, "achieved": step_ach, "frac": step_ach / peak}}
 
-    e2e = run_e2e(r, args.e2e_steps) if rank == 0 or dist is not None else None
+    barrier()
+    e2e = run_e2e(r, args.e2e_steps)
     if dist is not None:
-        e2e_total = sum_over_ranks(e2e["value"])
-        e2e = dict(e2e, value=e2e_total)
+        # every rank makes the drop-in call at the same time: the whole-job figure is the sum; the per-rank times and the
+        # pinned-copy bandwidth each rank sees while all ranks copy show what saturates (one host's PCIe / memory path)
+        per_rank = [None] * world_size
+        dist.all_gather_object(per_rank, {"ms_per_step": e2e["ms_per_step"], "bodies_only_ms_per_step": e2e["bodies_only"]["ms_per_step"]})
+        probe = pcie_probe(torch, barrier)
+        probes = [None] * world_size
+        dist.all_gather_object(probes, probe)
+        e2e = dict(e2e, value=sum_over_ranks(e2e["value"]), ms_per_step=max(p["ms_per_step"] for p in per_rank),
+                   per_rank_ms_per_step=[round(p["ms_per_step"], 3) for p in per_rank],
+                   concurrent_pinned_copy_gbs={"d2h_per_rank": [round(p["d2h_gbs"], 1) for p in probes],
+                                               "h2d_per_rank": [round(p["h2d_gbs"], 1) for p in probes],
+                                               "d2h_sum": round(sum(p["d2h_gbs"] for p in probes), 1)})
+        e2e["bodies_only"] = dict(e2e["bodies_only"], value=sum_over_ranks(e2e["bodies_only"]["value"]))
+    elif rank == 0:
+        e2e["pinned_copy_gbs"] = {k: round(v, 1) for k, v in pcie_probe(torch, barrier).items()}
+    same_size_cpu = None
+    if rank == 0 and world_size == 1 and not args.skip_cpu and not args.skip_pruned:
+        same_size_cpu = cpu_pruned_same_size(r)
     r["world"].destroy()
 
     batched = None
     if not args.skip_batched:
-        b = run_c5(args, lib, torch, barrier, rank)
-        bms = max_over_ranks(b["ms"])
-        btot = sum_over_ranks(b["bodies"])
-        batched = {"workload": f"c5_{args.worlds}_worlds_x_256_bodies_per_gpu", "value": btot * args.steps / (bms * 1e-3),
-                   "unit": "body-steps/s", "ms_per_step": bms / args.steps, "worlds_per_gpu": args.worlds,
-                   "bodies_total": int(btot), "contacts_rank0": b["contacts"], "levels_rank0": b["levels"],
-                   "launches": b["launches"], "scaling": "weak"}
+        from ballbox_b200 import sharding
+
+        def leg(ids, scaling):
+            b = run_batched(args, lib, torch, barrier, ids)
+            if b["overflow"]:
+                raise SystemExit(f"bench.py: device buffer overflow flags {b['overflow']} in the batched worlds")
+            bms = max_over_ranks(b["ms"])
+            # the ONE collective of the design: statistics (and the checksum of checksums) after the last step
+            tot = sharding.reduce_stats(sharding.pack_stats(b["bodies"] * args.steps, b["contacts"], b["worlds"], b["hash_final"]),
+                                        dist, device="cuda")
+            tot0 = sharding.reduce_stats(sharding.pack_stats(0, 0, 0, b["hash_settled"]), dist, device="cuda")
+            return {"scaling": scaling, "worlds_total": int(tot["worlds"]), "worlds_per_gpu": b["worlds"],
+                    "value": tot["body_steps"] / (bms * 1e-3), "unit": "body-steps/s", "ms_per_step": bms / args.steps,
+                    "bodies_total": int(tot["body_steps"] / args.steps), "contacts_total": int(tot["contacts"]),
+                    "levels_rank0": b["levels"], "launches_rank0": b["launches"],
+                    "checksum_after_settle": "%016x" % sharding.unpack_hash(tot0),
+                    "checksum_final": "%016x" % sharding.unpack_hash(tot),
+                    "checksum_steps": args.settle_worlds + args.warmup + args.steps}
+        strong = leg(sharding.strong_world_ids(rank, world_size, args.worlds), "strong")
+        batched = {"workload": f"c5_one_batch_of_{args.worlds}_worlds_x_256_bodies_partitioned_over_{world_size}_gpus",
+                   "value": strong["value"], "unit": "body-steps/s", "ms_per_step": strong["ms_per_step"],
+                   "settle_steps": args.settle_worlds, "strong": strong,
+                   "checksum_note": "sum modulo 2^64 of the FNV-1a state hashes of all worlds (seeded by global world id): "
+                                    "identical at every N for equal --steps/--warmup; checksum_after_settle does not depend on them"}
+        if world_size > 1:
+            batched["weak"] = leg(sharding.rank_world_ids(rank, world_size, args.worlds), "weak")
+        else:
+            batched["weak"] = dict(strong, scaling="weak")
 
     others = None
     if rank == 0 and world_size == 1 and not args.skip_others:
@@ -419,6 +542,9 @@ def main():
     cpu = None
     if rank == 0 and world_size == 1 and not args.skip_cpu:
         cpu = cpu_sample(args.ref_bodies, args.cpu_steps)
+        cpu["batched_worlds_all_cores"] = cpu_sample_c5()
+        if same_size_cpu:
+            cpu["reference_pruned_1M"] = same_size_cpu
 
     if rank == 0:
         line = {"metric": "body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world_size,

@@ -109,3 +109,23 @@ def test_c5_full_size_batch_sampled_worlds_against_reference(product, truth):
     st = bb.BallboxStats(); d.BatchGetStats(batch, bb.C.byref(st))
     assert st.overflow == 0 and st.contacts > 3_000_000, st.contacts
     d.DestroyPhysicsWorldBatch(batch)
+
+
+@pytest.mark.parametrize("total,ranks", [(64, 2), (50, 4)])
+def test_partitioned_batch_is_world_for_world_identical_to_the_single_batch(product, total, ranks):
+    """SURVEY 8e on hardware: ONE batch of `total` worlds stepped as a whole, and the same worlds stepped
+    as the `ranks` shards of ballbox_b200.sharding (what bench.py --gpus N builds per GPU; here one after
+    the other on cuda:0).  Every world's state hash and the order-independent checksum must agree."""
+    from ballbox_b200 import sharding
+    whole = sharding.WorldShard(product, sharding.strong_world_ids(0, 1, total), bb.SCENE_RLWORLD, device=0)
+    whole.step(DT, 120)
+    ref = whole.world_hashes()
+    whole.destroy()
+    merged = {}
+    for r in range(ranks):
+        sh = sharding.WorldShard(product, sharding.strong_world_ids(r, ranks, total), bb.SCENE_RLWORLD, device=0)
+        sh.step(DT, 120)
+        merged.update(sh.world_hashes())
+        sh.destroy()
+    assert merged == ref
+    assert sharding.combine_hashes(merged.values()) == sharding.combine_hashes(ref.values())
