@@ -30,9 +30,12 @@
 #define PH_SSDF 3
 #define PH_BSDF 4
 
-#define BBX_NUM_SMS 148
+// launch grids are sized from the device's SM count (BbxDev::num_sms, cudaDevAttrMultiProcessorCount); every use
+// sits in a host function whose BbxDev* is called d
+#define BBX_NUM_SMS (d->num_sms)
 #define BBX_TIMING_MARKS 7       // step start, after K1, broadphase, narrowphase, presolve+graph, solve kernel, K12
 #define BBX_TIMING_STEPS 256
+#define BBX_TRACE_WARPS 8192       // per-warp trace slots behind level_ns[4104] (BBX_TRACE_LEVEL)
 #define BBX_NCLS 8               // solver node classes by run length: 1 (no box), 1 (box), 2, 3, 4, 5-6, 7-8, 9+
 
 struct GridParams {
@@ -69,7 +72,8 @@ struct StepCounters {
     int n_big;
     int fq_ticket;           // flow solver: chunk tickets handed out in iterations 1..I-1
     int n_hit_bb_edge;       // ... with an EDGE-EDGE axis (stored from the back of hit_ids)
-    int pad2[3];
+    int replay_done;         // k_solve_levels ran iterations 1..I-1 itself (more levels than the staged replay's tables hold)
+    int pad2[2];
 };
 
 struct BbxDev {
@@ -147,14 +151,12 @@ struct BbxDev {
     int last_per_contact;                        // the last solve used one node per constraint (layout of `node`)
     int last_flow;                               // the last solve ran on the flow solver (impulses live in fimp)
     int flow_blocks;                             // co-resident blocks of k_solve_flow
-    int packed_sweep;                            // BBX_PACKED=1: level replay with packed FP32x2 arithmetic (bit-exact, measured slower: register spills)
-    int kahn_blocks, fused_kahn;                 // co-resident blocks of k_kahn_levels; BBX_FUSED_KAHN=1: level discovery fused with sweep 0
-    int rp_blocks, replay_mode;                  // co-resident blocks of k_replay_pairs; BBX_REPLAY=2 selects it
+    int num_sms;                                 // cudaDevAttrMultiProcessorCount of `device`
+    int replay_mode;                             // BBX_REPLAY: 1 (default) staged replay kernel (bbx_replay.cu), 0 replay inside k_solve_levels
+    int replay_blocks;                           // co-resident blocks of k_replay_staged
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels
-    int tune_replay_blocks, tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_REPLAY_BLOCKS, BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL
+    int tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL
     int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
-    int grp_unrolled;                            // BBX_GROUPS_UNROLLED: group solver over the unrolled graph (sweeps overlap)
-    int no_groups;                               // BBX_WORLD_GROUPS=0: batched worlds use the warp-per-world kernel (A/B measurements)
     int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)
     unsigned long long *level_ns;                // optional trace: globaltimer at the end of each level of iteration 1 (first 4096)
     // level-major copies streamed by iterations >= 1

@@ -69,6 +69,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     d->err = (char*)calloc(256, 1);
     d->device = device;
     BBX_CUDA(d, cudaSetDevice(device));
+    BBX_CUDA(d, cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, device));
     d->stream = 0;
     d->n_worlds = n_worlds; d->cap_s = cap_s; d->cap_b = cap_b;
     long long NS = (long long)n_worlds * cap_s, NB = (long long)n_worlds * cap_b;
@@ -123,18 +124,13 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->flow, 4 * (size_t)N); DALLOC(d->fq, C); DALLOC(d->fnd, 2 * (size_t)C); DALLOC(d->fimp, 2 * (size_t)C);
     BBX_CUDA(d, cudaMemsetAsync(d->fq, 0xff, sizeof(int) * (size_t)C, d->stream));
     // measurement switches (A/B runs of tools/ and profiles/r01_notes.md), read once per device state
-    { const char* e = getenv("BBX_GROUPS_UNROLLED"); d->grp_unrolled = (e && e[0] == '1') ? 1 : 0; }
-    { const char* e = getenv("BBX_WORLD_GROUPS"); d->no_groups = (e && e[0] == '0') ? 1 : 0; }
     { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
-    { const char* e = getenv("BBX_PACKED"); d->packed_sweep = (e && e[0] == '1') ? 1 : 0; }
-    { const char* e = getenv("BBX_FUSED_KAHN"); d->fused_kahn = (e && e[0] == '0') ? 0 : 1; }       // default: fused (measured, r01_notes.md)
-    { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && atoi(e) == 2) ? 2 : 0; }
+    { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && e[0] == '0') ? 0 : 1; }          // default: staged replay kernel
     { const char* e = getenv("BBX_SOLVE_BLOCKS"); d->tune_solve_blocks = e ? atoi(e) : 0; }
-    { const char* e = getenv("BBX_REPLAY_BLOCKS"); d->tune_replay_blocks = e ? atoi(e) : 0; }
     { const char* e = getenv("BBX_FLOW_BLOCKS"); d->tune_flow_blocks = e ? atoi(e) : 0; }
     { const char* e = getenv("BBX_FLOW_GATHER"); d->tune_flow_gather = e ? atoi(e) : 0; }
     { const char* e = getenv("BBX_TRACE_LEVEL"); d->trace_level = e ? atoi(e) : 0; }
-    DALLOC(d->level_ns, 4096 + 8);
+    DALLOC(d->level_ns, 4096 + 8 + 4 * BBX_TRACE_WARPS);      // level times, debug counters, per-warp trace of one level
     DALLOC(d->ctr, 1);
     DALLOC(d->sort_keys, C);
     d->export_buf = NULL;          // allocated on first constraint download

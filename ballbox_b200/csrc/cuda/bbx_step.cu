@@ -611,6 +611,16 @@ extern "C" int bbx_dev_run_stage(BbxDev* d, const BbxStepParams* p, int stage)
     return rc;
 }
 
+// debug (BBX_TRACE_LEVEL=l+1): per warp of the staged replay, level l of iteration 1: start ns, data-ready ns, end ns, class << 16 | chunks
+extern "C" int bbx_dev_debug_warp_trace(BbxDev* d, unsigned long long* out, int n_warps)
+{
+    if (!d || !out || n_warps < 0 || n_warps > BBX_TRACE_WARPS) return BBX_ERR_BAD_ARGUMENT;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    BBX_CUDA(d, cudaMemcpy(out, d->level_ns + 4104, sizeof(unsigned long long) * 4 * (size_t)n_warps, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // debug: per-level node counts (per class) and end-of-level timestamps of iteration 1
 extern "C" int bbx_dev_debug_levels(BbxDev* d, int* counts, unsigned long long* ns, int max_levels)
 {

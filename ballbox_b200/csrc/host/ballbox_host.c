@@ -1178,6 +1178,13 @@ int BallboxDebugLevels(PhysicsWorld* w, int* counts8, unsigned long long* ns, in
     return batch_check_dev(p->batch, bbx_dev_debug_levels(p->batch->dev, counts8, ns, max_levels));
 }
 
+int BallboxDebugWarpTrace(PhysicsWorld* w, unsigned long long* out, int n_warps)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p || !p->batch->dev) return BBX_ERR_BAD_ARGUMENT;
+    return batch_check_dev(p->batch, bbx_dev_debug_warp_trace(p->batch->dev, out, n_warps));
+}
+
 static int batch_ok(PhysicsWorldBatch* b) { return b && b->magic == BBX_MAGIC; }
 int  BatchSetDevice(PhysicsWorldBatch* b, int device) { return batch_ok(b) ? BallboxSetDevice(&b->worlds[0].pub, device) : BBX_ERR_BAD_ARGUMENT; }
 void BatchSetStream(PhysicsWorldBatch* b, void* s) { if (batch_ok(b)) BallboxSetStream(&b->worlds[0].pub, s); }

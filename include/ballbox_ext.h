@@ -116,6 +116,7 @@ void BallboxSetStageTiming(PhysicsWorld* world, int on);
 int  BallboxGetStageTiming(PhysicsWorld* world, float* out6, int* steps);
 
 int  BallboxDebugLevels(PhysicsWorld* world, int* counts8, unsigned long long* ns, int max_levels);
+int  BallboxDebugWarpTrace(PhysicsWorld* world, unsigned long long* out4, int n_warps);   /* BBX_TRACE_LEVEL=l+1: per warp of the staged replay in level l, iteration 1: start, data ready, end (ns), constraints<<16|chunks */
 
 /* ---- batches of independent worlds (RL style).  All worlds of a batch share
  * one device context and are stepped by the same kernels; worlds never

@@ -648,15 +648,13 @@ def test_full_size_two_exact_schedules_agree(product):
     assert a.stats().contacts > 500_000
 
 
-def test_full_size_batch_three_solvers_agree(product, monkeypatch):
-    """BASELINE config 5 at full size (4096 worlds x 256 bodies): the block-per-group solver, its variant over the
-    unrolled graph (sweeps overlap), the warp-per-world solver and the flow solver must produce identical worlds."""
+def test_full_size_batch_two_exact_schedules_agree(product):
+    """BASELINE config 5 at full size (4096 worlds x 256 bodies): the block-per-group solver and the flow solver (two
+    independent implementations of the reference's per-body constraint order) must produce identical worlds."""
     d = product.dll
     s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
     hashes = []
-    for mode in ("groups", "unrolled", "warps", "flow"):
-        monkeypatch.setenv("BBX_WORLD_GROUPS", "0" if mode == "warps" else "1")
-        monkeypatch.setenv("BBX_GROUPS_UNROLLED", "1" if mode == "unrolled" else "0")
+    for mode in ("groups", "flow"):
         batch = d.CreatePhysicsWorldBatch(4096, s, b, c)
         views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in (0, 1, 777, 2048, 4095)]
         for i in range(4096):
@@ -670,15 +668,35 @@ def test_full_size_batch_three_solvers_agree(product, monkeypatch):
         assert st.overflow == 0
         hashes.append((st.contacts, tuple(v.state_hash() for v in views)))
         d.DestroyPhysicsWorldBatch(batch)
-    assert hashes[0] == hashes[1] == hashes[2] == hashes[3] and hashes[0][0] > 1_000_000
+    assert hashes[0] == hashes[1] and hashes[0][0] > 1_000_000
 
 
 @pytest.mark.parametrize("kind,n,steps", [(bb.SCENE_MIXED, 2500, 40), (bb.SCENE_SDF, 1200, 30)])
-def test_packed_fp32x2_sweep_is_bit_exact(product, truth, monkeypatch, kind, n, steps):
-    """BBX_PACKED=1 replays the levels with fma.rn.f32x2 (both bodies of a constraint in one instruction); every
-    packed operation must round like the scalar one it replaces (sphere-sphere, box-box and mixed pairs)."""
-    monkeypatch.setenv("BBX_PACKED", "1")
+def test_in_kernel_replay_is_bit_exact(product, truth, monkeypatch, kind, n, steps):
+    """BBX_REPLAY=0: iterations 1..I-1 inside k_solve_levels (the round-1 replay loop, still the path of schedules deeper
+    than the staged replay's tables); the default staged replay kernel is what every other test runs."""
+    monkeypatch.setenv("BBX_REPLAY", "0")
     lockstep(product, truth, kind, n, 31, steps, every=3)
+
+
+def test_schedule_deeper_than_the_staged_replay_tables(product, truth):
+    """A column of 700 touching spheres on a static box: contact (i, i+1) shares a body with (i+1, i+2), so the exact
+    schedule is ~700 levels deep, more than RS_MAXLEV = 256: k_solve_levels must run the replay itself."""
+    def build(lib):
+        w = lib.create_world(800, 4, 4000)
+        w.set_gravity((0.0, -9.8, 0.0))
+        w.w.settings.solver_iterations = 8
+        g = w.add_box((0.0, -1.0, 0.0), (5.0, 1.0, 5.0))
+        lib.dll.SetBoxStatic(w.ptr, g, True)
+        for i in range(700):
+            w.add_sphere((0.0, 0.45 + 0.9 * i, 0.0), 0.5)
+        return w
+    g, c = build(product), build(truth)
+    for s in range(6):
+        g.step(DT); c.step(DT)
+        mm = parity.compare_worlds(g, c)
+        assert not mm, f"step {s}: {mm[:3]}"
+    assert g.stats().levels > 256, g.stats().levels
 
 
 @pytest.mark.parametrize("kind,n,steps,factor,schedule", [

@@ -43,15 +43,21 @@ lib.dll.BallboxDebugLevels.argtypes = [bb.WP, C.POINTER(C.c_int), C.POINTER(C.c_
 lib.dll.BallboxDebugLevels(w.ptr, cnt, ns, 4096)
 fd = np.frombuffer(ns, dtype=np.uint64)[4088:4096].astype(np.float64)
 if os.environ.get("BBX_TRACE_LEVEL"):
-    n3 = fd[2] - fd[4] - fd[6]
-    print(f"level trace (level {os.environ['BBX_TRACE_LEVEL']}, iteration 1): warps with work={fd[2]:.0f} mean busy us={fd[0]/max(fd[2],1)/1e3:.2f} max busy us={fd[1]/1e3:.2f} | "
-          f"1 chunk: n={fd[4]:.0f} mean={fd[3]/max(fd[4],1)/1e3:.2f} us | 2 chunks: n={fd[6]:.0f} mean={fd[5]/max(fd[6],1)/1e3:.2f} us | 3+ chunks: n={n3:.0f} mean={fd[7]/max(n3,1)/1e3:.2f} us")
-elif fd[5] > 0:
-    ud = int(np.frombuffer(ns, dtype=np.uint64)[4080])
-    print(f"flow solver: dependency depth of ALL iterations together = {ud} constraints (iteration 0 alone: {w.stats().levels}; "
-          f"{w.w.settings.solver_iterations} iterations one after the other would be {w.stats().levels * w.w.settings.solver_iterations})")
-    print(f"flow solver (last step): chunk visits={fd[0]:.0f} processing passes={fd[1]:.0f} spin passes={fd[2]:.0f} failed lane polls={fd[3]:.0f} "
-          f"warp wait/busy cycles={fd[4]/max(fd[5],1):.3f} replay (after iteration 0) ms={(fd[7]-fd[6])/1e6:.3f}")
+    NW = 2 * 148 * 8
+    tr = (C.c_ulonglong * (4 * NW))()
+    lib.dll.BallboxDebugWarpTrace.argtypes = [bb.WP, C.POINTER(C.c_ulonglong), C.c_int]
+    lib.dll.BallboxDebugWarpTrace(w.ptr, tr, NW)
+    t = np.frombuffer(tr, dtype=np.uint64).reshape(NW, 4).astype(np.int64)
+    t0 = t[:, 0].min()
+    work = t[:, 2] > 0
+    print(f"warp trace of level {int(os.environ['BBX_TRACE_LEVEL']) - 1}, iteration 1: {work.sum()} of {NW} warps with work; "
+          f"level start spread {(t[:, 0].max() - t0) / 1e3:.2f} us; last warp ends at {(t[work, 2].max() - t0) / 1e3:.2f} us")
+    busy = (t[:, 2] - t[:, 0])[work] / 1e3; wait = (t[:, 1] - t[:, 0])[work] / 1e3
+    print(f"  busy us: mean {busy.mean():.2f} p50 {np.median(busy):.2f} p90 {np.percentile(busy, 90):.2f} max {busy.max():.2f} | first data wait us: mean {wait.mean():.2f} max {wait.max():.2f}")
+    m = (t[:, 3] >> 16)[work]; nc = (t[:, 3] & 0xffff)[work]
+    for mm in sorted(set(m.tolist())):
+        sel = m == mm
+        print(f"  head node m={mm}: warps {sel.sum()} chunks/warp {nc[sel].mean():.2f} busy mean {busy[sel].mean():.2f} max {busy[sel].max():.2f} end mean {((t[work, 2][sel] - t0) / 1e3).mean():.2f}")
 cnt = np.frombuffer(cnt, dtype=np.int32).reshape(-1, 8)[:L]; ns = np.frombuffer(ns, dtype=np.uint64)[:L + 1].astype(np.int64)
 dt_us = np.diff(ns)[1:] / 1e3
 print("levels", L, "nodes/level (first 12):", cnt.sum(1)[:12].tolist())
