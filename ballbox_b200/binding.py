@@ -392,6 +392,13 @@ class World:
         self.check()
         return {k: float(out[i]) for i, k in enumerate(self.STAGES)}, n.value
 
+    def replay_timing(self):
+        """(ms of k_replay_staged summed, steps) for the steps covered by the last stage_timing() call."""
+        ms, n = C.c_float(), C.c_int()
+        self.lib.dll.BallboxGetReplayTiming.argtypes = [WP, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        self.lib.dll.BallboxGetReplayTiming(self.ptr, C.byref(ms), C.byref(n))
+        return float(ms.value), n.value
+
     def set_stream(self, cuda_stream: int):
         self.lib.dll.BallboxSetStream(self.ptr, C.c_void_p(cuda_stream))
 

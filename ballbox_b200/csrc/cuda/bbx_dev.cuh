@@ -33,7 +33,7 @@
 // launch grids are sized from the device's SM count (BbxDev::num_sms, cudaDevAttrMultiProcessorCount); every use
 // sits in a host function whose BbxDev* is called d
 #define BBX_NUM_SMS (d->num_sms)
-#define BBX_TIMING_MARKS 7       // step start, after K1, broadphase, narrowphase, presolve+graph, solve kernel, K12
+#define BBX_TIMING_MARKS 8       // step start, after K1, broadphase, narrowphase, presolve+graph, solve kernels, K12; [7] = between k_solve_levels and k_replay_staged
 #define BBX_TIMING_STEPS 256
 #define BBX_TRACE_WARPS 8192       // per-warp trace slots behind level_ns[4104] (BBX_TRACE_LEVEL)
 #define BBX_NCLS 8               // solver node classes by run length: 1 (no box), 1 (box), 2, 3, 4, 5-6, 7-8, 9+
@@ -153,6 +153,8 @@ struct BbxDev {
     int flow_blocks;                             // co-resident blocks of k_solve_flow
     int num_sms;                                 // cudaDevAttrMultiProcessorCount of `device`
     int replay_mode;                             // BBX_REPLAY: 1 (default) staged replay kernel (bbx_replay.cu), 0 replay inside k_solve_levels
+    float replay_ms_sum; int replay_steps;       // k_replay_staged alone, summed by the last bbx_dev_get_timing
+    unsigned char* timing_has7;                  // host array [BBX_TIMING_STEPS]: step s recorded mark 7
     int replay_blocks;                           // co-resident blocks of k_replay_staged
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels
     int tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL

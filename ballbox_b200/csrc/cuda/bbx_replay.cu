@@ -81,7 +81,7 @@ struct ReplayCtx {
 
 // the chunks warp w owns in level l: descriptor pointer of this lane in the first one, number of chunks, and the
 // number of nodes from this lane's first node to the end of the class (lane is live in chunk r iff r * 32 < left)
-struct WarpWork { const int4* p; int nc; int left; };
+struct WarpWork { const int4* p; int nc; int left; int stride; };   // stride: slots between a node's consecutive records
 __device__ __forceinline__ WarpWork level_work(const BbxDev& dv, const ReplayCtx& cx, int l, int w, int lane)
 {
     const int* b = cx.t_b + l * BBX_NCLS;
@@ -95,6 +95,7 @@ __device__ __forceinline__ WarpWork level_work(const BbxDev& dv, const ReplayCtx
     ww.nc = min(q, nchunks - first);
     ww.left = cnt - (first * 32 + lane);
     ww.p = dv.Nd_k[k] + (cx.t_head[l * BBX_NCLS + k] + first * 32 + lane);
+    ww.stride = k <= 4 ? cnt : 1;                                            // RECORD SLOTS, bbx_solver.cu
     return ww;
 }
 // descriptor of the warp's chunk r -> ring slot
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(
     while (nit < I && w >= t_nw[nl]) { if (++nl == n_levels) { nl = 0; nit++; } }
     bool staged_rec = false;
     WarpWork nx;
-    nx.p = NULL; nx.nc = 0; nx.left = 0;
+    nx.p = NULL; nx.nc = 0; nx.left = 0; nx.stride = 1;
     if (nit < I) {
         nx = level_work(dv, cx, nl, w, lane);
         issue_desc(cx, nx, 0, 0);
@@ -260,10 +261,11 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(
                     if (live) {
                         float4* M = dv.M + (size_t)nd.x;
                         float4 n0, n1, n2, n3;
-                        for (int j = 0; j < nd.y; j++, M++) {
+                        for (int j = 0; j < nd.y; j++, M += ww.stride) {
                             if (j + 1 < nd.y) {
-                                n0 = ld128_cg_pol(M + 1, cx.pol_stream); n1 = ld128_cg_pol(M + 1 + cx.PL, cx.pol_stream);
-                                n2 = ld128_cg_pol(M + 1 + 2 * cx.PL, cx.pol_stream); n3 = ld128_cg_pol(M + 1 + 3 * cx.PL, cx.pol_stream);
+                                const float4* Mn = M + ww.stride;
+                                n0 = ld128_cg_pol(Mn, cx.pol_stream); n1 = ld128_cg_pol(Mn + cx.PL, cx.pol_stream);
+                                n2 = ld128_cg_pol(Mn + 2 * cx.PL, cx.pol_stream); n3 = ld128_cg_pol(Mn + 3 * cx.PL, cx.pol_stream);
                             }
                             solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                             st128_cg_pol(M + 3 * cx.PL, c3, cx.pol_stream);

@@ -157,7 +157,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
     if (d->ctr_host) cudaFreeHost(d->ctr_host);
-    if (d->timing_ev) { for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventDestroy(d->timing_ev[i]); free(d->timing_ev); }
+    if (d->timing_ev) { for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventDestroy(d->timing_ev[i]); free(d->timing_ev); free(d->timing_has7); }
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     if (d->ev_upload) cudaEventDestroy(d->ev_upload);
     if (d->ev_chain) cudaEventDestroy(d->ev_chain);

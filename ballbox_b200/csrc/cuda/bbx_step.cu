@@ -31,6 +31,7 @@ extern "C" void bbx_dev_set_timing(BbxDev* d, int on)
     if (on && !d->timing_ev) {
         d->timing_cap = BBX_TIMING_STEPS;
         d->timing_ev = (cudaEvent_t*)calloc((size_t)d->timing_cap * BBX_TIMING_MARKS, sizeof(cudaEvent_t));
+        d->timing_has7 = (unsigned char*)calloc((size_t)d->timing_cap, 1);
         cudaSetDevice(d->device);
         for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventCreate(&d->timing_ev[i]);
     }
@@ -51,8 +52,25 @@ extern "C" int bbx_dev_get_timing(BbxDev* d, float* out6, int* steps)
             BBX_CUDA(d, cudaEventElapsedTime(&ms, d->timing_ev[s * BBX_TIMING_MARKS + k], d->timing_ev[s * BBX_TIMING_MARKS + k + 1]));
             out6[k] += ms;
         }
+    d->replay_ms_sum = 0.0f; d->replay_steps = 0;
+    for (int s = 0; s < d->timing_steps; s++)
+        if (d->timing_has7[s]) {
+            float ms = 0.0f;
+            BBX_CUDA(d, cudaEventElapsedTime(&ms, d->timing_ev[s * BBX_TIMING_MARKS + 7], d->timing_ev[s * BBX_TIMING_MARKS + 5]));
+            d->replay_ms_sum += ms; d->replay_steps++;
+            d->timing_has7[s] = 0;
+        }
     if (steps) *steps = d->timing_steps;
     d->timing_steps = 0;
+    return 0;
+}
+
+// k_replay_staged alone (iterations 1..I-1 of the level schedule): ms summed over the steps of the last bbx_dev_get_timing call
+extern "C" int bbx_dev_get_replay_timing(BbxDev* d, float* ms, int* steps)
+{
+    if (!d || !ms) return BBX_ERR_BAD_ARGUMENT;
+    *ms = d->replay_ms_sum;
+    if (steps) *steps = d->replay_steps;
     return 0;
 }
 

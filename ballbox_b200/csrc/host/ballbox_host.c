@@ -1171,6 +1171,13 @@ int BallboxGetStageTiming(PhysicsWorld* w, float* out6, int* steps)
     return p->batch->dev ? batch_check_dev(p->batch, bbx_dev_get_timing(p->batch->dev, out6, steps)) : 0;
 }
 
+int BallboxGetReplayTiming(PhysicsWorld* w, float* ms, int* steps)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p || !ms || !p->batch->dev) return BBX_ERR_BAD_ARGUMENT;
+    return batch_check_dev(p->batch, bbx_dev_get_replay_timing(p->batch->dev, ms, steps));
+}
+
 int BallboxDebugLevels(PhysicsWorld* w, int* counts8, unsigned long long* ns, int max_levels)
 {
     BbxWorldPriv* p = priv_of(w);

@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 DT = 1.0 / 60.0
 WORKLOAD_C3 = "c3_mixed_pile_500k_spheres_500k_boxes_6_walls"
-SOLVE_KERNEL = "k_solve_levels"
+SOLVE_KERNEL = "k_replay_staged"
 
 
 def load_peaks():
@@ -242,6 +242,8 @@ def time_resident(world, steps, warmup, torch, barrier):
     barrier()
     ms = e0.elapsed_time(e1)
     stages, covered = world.stage_timing()
+    replay_ms, replay_steps = world.replay_timing()
+    stages["replay_kernel"] = replay_ms * covered / max(replay_steps, 1)      # part of solve_kernel (same normalisation)
     world.set_stage_timing(False)
     s1 = world.stats()
     return ms, stages, covered, s0, s1
@@ -465,16 +467,26 @@ def main():
     value = total_bodies * args.steps / (ms * 1e-3)
     I = r["iters"]
     C_, D_, P_ = r["solver_contacts"], r["touched"], r["pairs"]
+    # The solve is two launches: k_solve_levels (iteration 0: level discovery fused with the first sweep) and
+    # k_replay_staged (iterations 1..I-1), the dominant kernel of the step.  Both are timed live with CUDA events on the
+    # step stream; algorithmic bytes per SURVEY.md 8d: one iteration = C*116 + D*48.
     solve_ms = r["stages_ms_per_step"]["solve_kernel"]
+    replay_ms = r["stages_ms_per_step"]["replay_kernel"]
     sb = solver_bytes(C_, D_, I)
-    achieved = sb / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+    rb = solver_bytes(C_, D_, max(I - 1, 0))
+    achieved = rb / (replay_ms * 1e-3) / 1e9 if replay_ms > 0 else 0.0
+    solve_ach = sb / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
     stepb = step_bytes(r["ns"], r["nb"], P_, r["contacts"], D_, I)
     step_ach = stepb / (r["ms"] / args.steps * 1e-3) / 1e9
     traffic, traffic_src = load_traffic(args, SOLVE_KERNEL)
     roofline = {"bound": "hbm", "kernel": SOLVE_KERNEL, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "note": "bound by waiting (barriers 48 % of stall samples, issue slots 23 % active), not by HBM: profiles/r01i_ncu_solve_levels.md, profiles/r01_notes.md",
-                "algorithmic_bytes_per_launch": sb, "ms_per_launch": solve_ms,
+                "note": "iterations 1..I-1 of the exact level schedule; bound by the 51 x 7 grid-synchronised levels (about half of "
+                        "every level is barrier + first gather) and by instruction issue while sweeping (~950 warp instructions "
+                        "per constraint, reference arithmetic without FMA contraction), not by HBM: profiles/r02_notes.md",
+                "algorithmic_bytes_per_launch": rb, "ms_per_launch": replay_ms,
+                "whole_solve": {"kernels": "k_solve_levels + k_replay_staged", "algorithmic_bytes": sb, "ms": solve_ms,
+                                "achieved": solve_ach, "frac": solve_ach / peak},
                 "whole_step": {"algorithmic_bytes": stepb, "achieved": step_ach, "frac": step_ach / peak}}
 
     barrier()
@@ -552,7 +564,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_C3, "bodies_per_gpu": r["bodies"], "replicas": world_size,
                            "parallelism": "replicas only (a single world does not shard)",
-                           "settle_steps": args.settle, "solver": "exact level-scheduled Gauss-Seidel",
+                           "settle_steps": args.settle, "solver": "exact level-scheduled Gauss-Seidel (k_solve_levels + k_replay_staged)",
                            "solver_iterations": I, "l2_policy": "inputs larger than L2 (state + constraints > 126 MB)",
                            "contacts": r["contacts"], "candidate_pairs": P_, "touched_bodies": D_, "levels": r["levels"]},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": r["launches"], "clocks": r["clocks"],

@@ -139,6 +139,8 @@ int  bbx_dev_stats(BbxDev* dev, BallboxStats* out);
  * and resets the accumulation. */
 void bbx_dev_set_timing(BbxDev* dev, int on);
 int  bbx_dev_get_timing(BbxDev* dev, float* out6, int* steps);
+/* the staged replay kernel alone (part of out6[4]), for the steps covered by the last bbx_dev_get_timing call */
+int  bbx_dev_get_replay_timing(BbxDev* dev, float* ms, int* steps);
 /* debug trace of the last step: node counts per level and class (8 ints per level), and
  * ns[l+1] = globaltimer at the end of level l of solver iteration 1 (ns[l+1]-ns[l] = level time, l >= 1) */
 int  bbx_dev_debug_levels(BbxDev* dev, int* counts, unsigned long long* ns, int max_levels);

@@ -33,7 +33,8 @@ torch.cuda.profiler.start()
 w.step_n(1 / 60, a.steps); w.synchronize()
 torch.cuda.profiler.stop()
 tm, n = w.stage_timing()
-print({k: round(v / max(n, 1), 4) for k, v in tm.items()}, "ms/step over", n, flush=True)
+rms, rn = w.replay_timing()
+print({k: round(v / max(n, 1), 4) for k, v in tm.items()}, "ms/step over", n, "| k_replay_staged alone: %.4f ms" % (rms / max(rn, 1)), flush=True)
 
 import ctypes as C
 import numpy as np
