@@ -800,3 +800,122 @@ def test_batch_edge_settings(product, truth, schedule):
             mm = parity.compare_worlds(views[i], refs[i])
             assert not mm, f"{case}: world {i}: {mm[:3]}"
         d.DestroyPhysicsWorldBatch(batch)
+
+
+def _resting_scene(lib):
+    """two spheres and a box at rest in free space without gravity, next to a static box: they fall asleep after 0.5 s
+    (a body with a contact never sleeps in the reference: every impulse application wakes it, ballbox.h:1373-1376)"""
+    w = lib.create_world(8, 8, 256)
+    w.set_gravity((0.0, 0.0, 0.0))
+    g = w.add_box((0.0, -1.0, 0.0), (10.0, 1.0, 10.0)); lib.dll.SetBoxStatic(w.ptr, g, True)
+    w.add_sphere((0.0, 0.6, 0.0), 0.5); w.add_sphere((3.0, 0.55, 1.0), 0.5)
+    w.add_box((-3.0, 0.45, 0.0), (0.4, 0.4, 0.4))
+    return w
+
+
+def test_resident_force_wakes_a_sleeping_body(product, truth):
+    """Add*Force/Torque on a body that went to sleep while the state is RESIDENT (ballbox.h:420-423: the call wakes the body,
+    also for a zero force).  The host flags are stale then, so the wake has to reach the device."""
+    g, c = _resting_scene(product), _resting_scene(truth)
+    g.set_sync_mode(bb.SYNC_RESIDENT)
+    g.step_n(DT, 100)
+    for _ in range(100):
+        c.step(DT)
+    assert c.sphere_arrays()["sleeping"][:2].all() and c.box_arrays()["sleeping"][1], "scene did not fall asleep"
+    for lib, w in ((product, g), (truth, c)):                            # no download: the host flags of g still say "awake"
+        lib.dll.AddSphereForce(w.ptr, 0, bb.Vec3(40.0, -20.0, 0.0))      # a push (towards the static box)
+        lib.dll.AddSphereTorque(w.ptr, 1, bb.Vec3(0.0, 0.0, 0.0))        # zero torque: still wakes (:434-437)
+        lib.dll.AddBoxForce(w.ptr, 1, bb.Vec3(0.0, -30.0, 5.0))
+    g.step_n(DT, 30)
+    for _ in range(30):
+        c.step(DT)
+    g.download(bb.DL_BODIES)
+    mm = parity.compare_worlds(g, c, constraints=False)
+    assert not mm, mm[:3]
+    assert abs(float(c.sphere_arrays()["pos"][0][0])) > 1e-3, "the push did not move the reference sphere"
+
+
+def test_batch_force_wakes_a_sleeping_body(product, truth):
+    """the same through PhysicsStepBatch (always resident)"""
+    d = product.dll
+    batch = d.CreatePhysicsWorldBatch(3, 8, 8, 256)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(3)]
+    refs = [_resting_scene(truth) for _ in range(3)]
+    for v in views:
+        v.set_gravity((0.0, 0.0, 0.0))
+        gb = v.add_box((0.0, -1.0, 0.0), (10.0, 1.0, 10.0)); d.SetBoxStatic(v.ptr, gb, True)
+        v.add_sphere((0.0, 0.6, 0.0), 0.5); v.add_sphere((3.0, 0.55, 1.0), 0.5)
+        v.add_box((-3.0, 0.45, 0.0), (0.4, 0.4, 0.4))
+    assert d.PhysicsStepBatch(batch, DT, 100) == 0, d.BatchGetLastError(batch)
+    for r in refs:
+        for _ in range(100):
+            r.step(DT)
+        assert r.sphere_arrays()["sleeping"][:2].all()
+    d.AddSphereForce(views[1].ptr, 0, bb.Vec3(40.0, -20.0, 0.0)); truth.dll.AddSphereForce(refs[1].ptr, 0, bb.Vec3(40.0, -20.0, 0.0))
+    d.AddBoxTorque(views[2].ptr, 1, bb.Vec3(0.0, 9.0, 0.0)); truth.dll.AddBoxTorque(refs[2].ptr, 1, bb.Vec3(0.0, 9.0, 0.0))
+    assert d.PhysicsStepBatch(batch, DT, 25) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES) == 0, d.BatchGetLastError(batch)
+    for i, r in enumerate(refs):
+        for _ in range(25):
+            r.step(DT)
+        mm = parity.compare_worlds(views[i], r, constraints=False)
+        assert not mm, f"world {i}: {mm[:3]}"
+    d.DestroyPhysicsWorldBatch(batch)
+
+
+def test_resident_edits_do_not_snap_back_to_stale_host_state(product, truth):
+    """AddSphere / AddBox / Set*Mass / Set*Static / BallboxSetSyncMode on a RESIDENT world whose host arrays are stale:
+    the device state must survive the re-upload the edit causes (the library downloads first)."""
+    g, c = product.build_scene(bb.SCENE_MIXED, 200, 77), truth.build_scene(bb.SCENE_MIXED, 200, 77, )
+    g.set_sync_mode(bb.SYNC_RESIDENT)
+    g.step_n(DT, 40)
+    for _ in range(40):
+        c.step(DT)
+    for lib, w in ((product, g), (truth, c)):                      # no download in between: the host arrays of g are 40 steps old
+        lib.dll.SetSphereMass(w.ptr, 5, 3.5)
+        lib.dll.SetBoxMass(w.ptr, 9, 0.25)
+        lib.dll.SetSphereStatic(w.ptr, 11, True)
+        lib.dll.SetBoxStatic(w.ptr, 12, True)
+    g.step_n(DT, 20)
+    for _ in range(20):
+        c.step(DT)
+    g.download(bb.DL_BODIES)
+    mm = parity.compare_worlds(g, c, constraints=False)
+    assert not mm, f"after the mass / static edits: {mm[:3]}"
+    g.step_n(DT, 10)
+    for _ in range(10):
+        c.step(DT)
+    g.set_sync_mode(bb.SYNC_COMPAT)                                # leaving RESIDENT with stale host arrays
+    for _ in range(5):
+        g.step(DT); c.step(DT)
+    mm = parity.compare_worlds(g, c)
+    assert not mm, f"after the mode change: {mm[:3]}"
+
+
+def test_ragged_last_group_overflow_is_an_error_not_a_stray_write(product):
+    """More worlds than the group solver has blocks, not a multiple of the worlds per block: the last group holds fewer
+    worlds, so its slice of the queue / record arrays is shorter.  Its world produces more contacts than max_collisions:
+    that has to end in the overflow error (it used to write past the allocations), and a batch whose last world
+    stays within its capacity must step normally."""
+    d = product.dll
+    for dense in (False, True):
+        n_worlds = 6 * 148 + 1                                     # one more than the solver's resident blocks on B200: 2 worlds per block, last block 1
+        batch = d.CreatePhysicsWorldBatch(n_worlds, 12, 2, 24)
+        assert batch
+        for i in range(n_worlds):
+            v = bb.World(product, d.BatchWorld(batch, i), owned=False)
+            v.set_gravity((0.0, -9.8, 0.0))
+            gb = v.add_box((0.0, -1.0, 0.0), (4.0, 1.0, 4.0)); d.SetBoxStatic(v.ptr, gb, True)
+            v.add_sphere((0.0, 0.45, 0.0), 0.5)
+            if i == n_worlds - 1 and dense:
+                for j in range(10):                                # 11 spheres in one spot: 55 sphere pairs + 11 ground contacts > 24
+                    v.add_sphere((0.01 * j, 0.45, 0.01 * j), 0.5)
+        rc = d.PhysicsStepBatch(batch, DT, 3)
+        d.BatchSynchronize(batch)
+        rc2 = d.BatchDownload(batch, bb.DL_BODIES)
+        err = d.BatchGetLastError(batch)
+        if dense:
+            assert (rc or rc2) and err and (b"overflow" in err.lower() or b"exceeds" in err.lower()), (rc, rc2, err)      # BBX_ERR_OVERFLOW
+        else:
+            assert rc == 0 and rc2 == 0 and not err, err
+        d.DestroyPhysicsWorldBatch(batch)
