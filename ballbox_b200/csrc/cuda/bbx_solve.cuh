@@ -202,9 +202,11 @@ struct LevelMap { int head[BBX_NCLS]; int cnt[BBX_NCLS]; int pref[BBX_NCLS + 1];
 
 __device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level, bool first_level)
 {
-    // called by one thread; heads advance by the previous level's counts
+    // called by one thread; heads advance by the previous level's counts.  The flattened index space starts with the
+    // HEAVIEST class (pref[7] = 0 <= pref[6] <= ... <= pref[0]; pref[8] = total): the partial last round of a level then
+    // consists of the lightest chunks
     int run = 0;
-    for (int k = 0; k < BBX_NCLS; k++) {
+    for (int k = BBX_NCLS - 1; k >= 0; k--) {
         if (first_level) lm.head[k] = 0; else lm.head[k] += lm.cnt[k];
         lm.cnt[k] = __ldcg(&lc_level[k]);
         lm.pref[k] = run;

@@ -430,9 +430,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
         const int rounds = (total + stride - 1) / stride;            // uniform over the grid: every thread takes part in the flushes
         for (int r = 0; r < rounds; r++) {
             const int t = wtid + r * stride;
-            int k = 0;
+            int k = BBX_NCLS - 1;
             #pragma unroll
-            for (int kk = 1; kk < BBX_NCLS; kk++) if (t >= lm.pref[kk]) k = kk;
+            for (int kk = BBX_NCLS - 2; kk >= 0; kk--) if (t >= lm.pref[kk]) k = kk;
             int idx = t - lm.pref[k];
             bool live = t < total && idx < lm.cnt[k];
             int p = lm.head[k] + idx;
