@@ -44,6 +44,7 @@ struct GridParams {
     int   nx, ny, nz;
     int   cells_per_world;
     int   n_cells;           // cells_per_world * n_worlds
+    int   n_scan;            // n_cells + 1: entries of the cell table that this step's scan has to cover
     float small_cut;         // largest bounding radius that goes into the grid
     int   overflow;
 };

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <vector>
 #include "bbx_dev.cuh"
+#include <nvtx3/nvToolsExt.h>          // header-only; ranges are pushed only with BBX_NVTX=1
 
 void bbx_timing_mark(BbxDev* d, int mark)
 {
@@ -85,21 +86,30 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
     BbxStepParams q = *p;
     d->imported_list = 0;
     if (d->forces_on_device) { q.has_forces = 1; d->forces_on_device = 0; }
+    // BBX_NVTX=1: one NVTX range per stage on the enqueueing thread (tracing)
+    static const int nvtx_on = (getenv("BBX_NVTX") && getenv("BBX_NVTX")[0] == '1') ? 1 : 0;
+#define BBX_RANGE(name) do { if (nvtx_on) { nvtxRangePop(); nvtxRangePushA(name); } } while (0)
     for (int s = 0; s < steps; s++) {
         int rc;
+        if (nvtx_on) nvtxRangePushA("bbx:integrate_velocities");
         bbx_timing_mark(d, 0);
         if ((rc = bbx_stage_integrate_velocities(d, &q))) return rc;   // stages 1-2
         bbx_timing_mark(d, 1);
+        BBX_RANGE("bbx:broadphase");
         if ((rc = bbx_stage_broadphase(d, &q))) return rc;             // stage 3: pair finding (+ sphere-sphere)
         bbx_timing_mark(d, 2);
+        BBX_RANGE("bbx:narrowphase");
         if ((rc = bbx_stage_narrowphase(d, &q))) return rc;            // stage 3: contact generation
         if (q.want_callbacks && (rc = bbx_stage_collect_events(d, &q))) return rc;
         bbx_timing_mark(d, 3);
+        BBX_RANGE("bbx:presolve_graph_solve");
         if ((rc = bbx_stage_solve(d, &q))) return rc;                  // stage 4 (marks 4 inside, before the solve kernel)
         if (q.warm_start > 0.0f && (rc = bbx_stage_warm_save(d, &q))) return rc;
         bbx_timing_mark(d, 5);
+        BBX_RANGE("bbx:integrate_positions_sleep");
         if ((rc = bbx_stage_integrate_positions(d, &q))) return rc;    // stages 5-6
         bbx_timing_mark(d, 6);
+        if (nvtx_on) nvtxRangePop();
         if (d->timing_on && d->timing_steps < d->timing_cap) d->timing_steps++;
         q.has_forces = 0;                                              // forces were consumed and cleared by step 0
         d->steps++;
