@@ -74,7 +74,8 @@ struct StepCounters {
     int fq_ticket;           // flow solver: chunk tickets handed out in iterations 1..I-1
     int n_hit_bb_edge;       // ... with an EDGE-EDGE axis (stored from the back of hit_ids)
     int replay_done;         // k_solve_levels ran iterations 1..I-1 itself (more levels than the staged replay's tables hold)
-    int pad2[2];
+    int n_surv_bb;           // box-box candidates not separated by a face axis (compacted into cand_sb by k_bb_face)
+    int pad2[1];
 };
 
 struct BbxDev {

@@ -211,6 +211,16 @@ BBX_HDI bool sat_axes(const Obb& A, const Obb& B, float& minPd, float3& smallest
     return true;
 }
 
+// The six face-axis tests of SATCollision alone (same overlap_on_axis, same order): false = separated.  A pair that
+// fails here fails sat_axes at the same axis, so filtering with it first changes nothing.
+BBX_HDI bool sat_face_axes_overlap(const Obb& A, const Obb& B)
+{
+    float pd;
+    for (int i = 0; i < 3; i++) if (!overlap_on_axis(A, B, A.ax[i], pd)) return false;
+    for (int i = 0; i < 3; i++) if (!overlap_on_axis(A, B, B.ax[i], pd)) return false;
+    return true;
+}
+
 // SATCollision :1088-1108 (contact point by axis type) + the normal flip of
 // CheckBoxCollisionWithData :1121-1129
 BBX_HDI void sat_point(const Obb& A, const Obb& B, int axisType, float3& nrm, float3& pt)
