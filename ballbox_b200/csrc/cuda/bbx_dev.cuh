@@ -138,6 +138,8 @@ struct BbxDev {
     int  *queue_k[BBX_NCLS];                     // node ids (first contact of the run)
     int4 *Nd_k[BBX_NCLS];                        // (first M slot, constraint count, dynamic gid A, dynamic gid B)
     int *slot_of;                                // cap_contacts: contact -> M slot
+    int2 *link;                                  // cap_contacts: (successor on body A's chain, on body B's chain) of the node headed by contact c,
+                                                 // each = node | class << 28, -1 = none (level path)
     // warm starting (extension): open-addressing table (body A, body B, k) -> final impulses of the previous step
     unsigned long long *warm_key; float4 *warm_val; unsigned int warm_mask;
     int *warm_epoch;                             // per world: bumped by a world reset, stored with every entry (stale entries miss)
@@ -356,6 +358,20 @@ __device__ __forceinline__ void st256_cg_pol(float4* p, float4 a, float4 b, unsi
 {
     asm volatile("st.global.cg.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
                  :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st32_pol(int* p, int v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st64_pol(int2* p, int2 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1,%2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ int2 ld64_pol(const int2* p, unsigned long long pol)
+{
+    int2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
 }
 __device__ __forceinline__ float4 ld128_cg_pol(const float4* p, unsigned long long pol)
 {

@@ -119,7 +119,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
         for (int k = 0; k < BBX_NCLS; k++) { DALLOC(d->queue_k[k], C / min_len[k] + 64); DALLOC(d->Nd_k[k], C / min_len[k] + 64); }
     }
     d->cap_levels = C < (1 << 20) ? C : (1 << 20);
-    DALLOC(d->slot_of, C); DALLOC(d->level_count, ((size_t)d->cap_levels + 4) * BBX_NCLS);
+    DALLOC(d->slot_of, C); DALLOC(d->link, C); DALLOC(d->level_count, ((size_t)d->cap_levels + 4) * BBX_NCLS);
     DALLOC(d->M, 4 * (size_t)C);
     DALLOC(d->flow, 4 * (size_t)N); DALLOC(d->fq, C); DALLOC(d->fnd, 2 * (size_t)C); DALLOC(d->fimp, 2 * (size_t)C);
     BBX_CUDA(d, cudaMemsetAsync(d->fq, 0xff, sizeof(int) * (size_t)C, d->stream));
@@ -152,7 +152,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->boxq, d->half, d->brec, d->grid, d->cell_count, d->cell_start, d->cell_cursor, d->body_cell, d->sorted_id,
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
-        d->sdf_grid, d->slot_of, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->wake_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
+        d->sdf_grid, d->slot_of, d->link, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->wake_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan, d->warm_key, d->warm_val, d->warm_epoch };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
@@ -345,6 +345,9 @@ extern "C" int bbx_dev_upload_forces(BbxDev* d, const BbxHostBodies* hb)
         BBX_CUDA(d, cudaMemcpyAsync(d->r_b_force, hb->b_force, 12 * NB, cudaMemcpyHostToDevice, d->stream));
         BBX_CUDA(d, cudaMemcpyAsync(d->r_b_torque, hb->b_torque, 12 * NB, cudaMemcpyHostToDevice, d->stream));
     }
+    // the host arrays are pinned: the copies run later, so the caller must bbx_dev_wait_upload() before it clears them
+    if (!d->ev_upload) BBX_CUDA(d, cudaEventCreateWithFlags(&d->ev_upload, cudaEventDisableTiming));
+    BBX_CUDA(d, cudaEventRecord(d->ev_upload, d->stream));
     return 0;
 }
 

@@ -935,7 +935,10 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
             if (hf && (rc = batch_check_dev(b, bbx_dev_upload_forces(b->dev, &b->hb)))) return rc;
             if ((rc = fill_params(b, dt, hf, 1, &prm))) return rc;
             if ((rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, chunk)))) return rc;
-            if (hf) zero_host_forces(b);
+            if (hf) {                            /* the force arrays are pinned: clear them only after the queued copies have read them */
+                if ((rc = batch_check_dev(b, bbx_dev_wait_upload(b->dev)))) return rc;
+                zero_host_forces(b);
+            }
             if ((rc = replay_events(b))) return rc;
             done += chunk;
         }
@@ -946,7 +949,11 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
     if (hf && (rc = batch_check_dev(b, bbx_dev_upload_forces(b->dev, &b->hb)))) return rc;
     if ((rc = fill_params(b, dt, hf, 0, &prm))) return rc;
     rc = batch_check_dev(b, bbx_dev_step(b->dev, &prm, steps));
-    if (hf) zero_host_forces(b);
+    if (hf) {                                    /* the force arrays are pinned: clear them only after the queued copies have read them */
+        int rc2 = batch_check_dev(b, bbx_dev_wait_upload(b->dev));
+        if (!rc) rc = rc2;
+        zero_host_forces(b);
+    }
     return rc;
 }
 
