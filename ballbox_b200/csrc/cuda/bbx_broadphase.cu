@@ -103,7 +103,7 @@ __global__ void k_step_reset(BbxDev dv)
 {
     StepCounters* c = dv.ctr;
     c->n_sorted = 0; c->n_cand_sb = 0; c->n_cand_bb = 0; c->n_contacts = 0; c->n_solver = 0; c->n_touched = 0;
-    c->n_levels = 0; c->n_ss_tests = 0; c->n_frontier0 = 0; c->n_mslots = 0; c->n_nodes = 0; c->fq_tail = 0; c->fq_head = 0; c->fq_ticket = 0; c->n_hit_bb = 0; c->n_hit_bb_edge = 0; c->n_surv_bb = 0;
+    c->n_levels = 0; c->n_ss_tests = 0; c->n_frontier0 = 0; c->n_mslots = 0; c->n_nodes = 0; c->fq_tail = 0; c->fq_head = 0; c->fq_ticket = 0; c->n_hit_bb = 0; c->n_hit_bb_edge = 0; c->n_surv_bb = 0; c->n_deferred = 0;
     c->bounds[0] = c->bounds[1] = c->bounds[2] = 0xffffffffu;
     c->bounds[3] = c->bounds[4] = c->bounds[5] = 0u;
 }

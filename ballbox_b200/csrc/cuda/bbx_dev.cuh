@@ -75,7 +75,7 @@ struct StepCounters {
     int n_hit_bb_edge;       // ... with an EDGE-EDGE axis (stored from the back of hit_ids)
     int replay_done;         // k_solve_levels ran iterations 1..I-1 itself (more levels than the staged replay's tables hold)
     int n_surv_bb;           // box-box candidates not separated by a face axis (compacted into cand_sb by k_bb_face)
-    int pad2[1];
+    int n_deferred;          // level kernel: heavy terminal nodes held back for the last level (list in adj_cursor)
 };
 
 struct BbxDev {
@@ -159,6 +159,7 @@ struct BbxDev {
     int replay_mode;                             // BBX_REPLAY: 1 (default) staged replay kernel (bbx_replay.cu), 0 replay inside k_solve_levels
     float replay_ms_sum; int replay_steps;       // k_replay_staged alone, summed by the last bbx_dev_get_timing
     unsigned char* timing_has7;                  // host array [BBX_TIMING_STEPS]: step s recorded mark 7
+    int last_deferred;                           // n_deferred as of the last bbx_dev_stats
     int replay_blocks;                           // co-resident blocks of k_replay_staged
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels
     int tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL

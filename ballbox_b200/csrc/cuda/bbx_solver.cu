@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(128) k_warm_apply(BbxDev dv, int per_contact, 
 #define SOLVE_THREADS 256
 #define SOLVE_BLOCKS_PER_SM 2
 #define PEND_ROUNDS 4                  // rounds of a level between two block-aggregated appends
+#define DEFER_MIN_CLASS 3              // node classes 3.. (>= 3 constraints per node) may be deferred when terminal
 
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_levels(BbxDev dv, SolveParams sp)
 {
@@ -420,9 +421,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     // contiguous and handed out from the END of the array by a counter.  Bottom and top together hold one slot per
     // solver constraint <= cap_contacts, so they cannot meet.
     int lvl = 0, mbase = 0;
+    // thin schedules only (fewer than 8 chunks per warp and level on average would still be "fat": there a level's time is
+    // its total work, not its longest node, and an extra level only costs a barrier)
+    const bool defer_on = __ldcg(&dv.ctr->n_nodes) < 256 * (int)(gridDim.x * (SOLVE_THREADS / 32));
+    bool injected = false;
     if (threadIdx.x == 0) level_map_load(lm, lc, true);
     __syncthreads();
-    while (lm.pref[BBX_NCLS] > 0) {
+    for (;;) {
+        if (lm.pref[BBX_NCLS] == 0) {
+            // frontier empty: the deferred terminal nodes (if any) form the last level
+            // (L2 reads: the counter shares a line with fields this kernel read at its start, and L1 is not coherent)
+            const int nd = (defer_on && !injected) ? __ldcg(&dv.ctr->n_deferred) : 0;
+            if (nd <= 0) break;
+            if (lvl + 2 >= dv.cap_levels) { if (tid == 0) atomicOr(&dv.ctr->overflow, 16); break; }
+            // every block must have read this level's (zero) counts before the first count is raised: a block that
+            // loaded them later would take the level for an ordinary one and skip this branch
+            grid.sync();
+            for (int i = tid; i < nd; i += stride) {
+                const int e = __ldcg(&dv.adj_cursor[i]), kk = (e >> 28) & 7;
+                dv.queue_k[kk][lm.head[kk] + atomicAdd(&lc[lvl * BBX_NCLS + kk], 1)] = e & 0x0fffffff;
+            }
+            injected = true;
+            grid.sync();
+            if (threadIdx.x == 0) level_map_load(lm, lc + lvl * BBX_NCLS, false);
+            __syncthreads();
+            continue;
+        }
         if (lvl + 2 >= dv.cap_levels) { if (tid == 0) atomicOr(&dv.ctr->overflow, 16); break; }
         if (tid < BBX_NCLS) lc[(lvl + 2) * BBX_NCLS + tid] = 0;
         int* lc_next = lc + (lvl + 1) * BBX_NCLS;
@@ -481,6 +505,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 if (hasB) store_body_keep(dv, nd0.y, B, pol_keep);    //  touched bodies instead of a random flag access per node here)
                 if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) != 1) sa = -1;
                 if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) != 1) sb = -1;
+                if (defer_on) {
+                    // DEFERRED TERMINAL NODES: a heavy node (>= 3 constraints) without successors -- typically the probes of a box
+                    // on the SDF, always last in the box's chain -- may run at any later time.  In a thin schedule every level
+                    // waits for its longest node, so these are collected and swept together in ONE extra level at the end.
+                    if (sa >= 0 && ((sa >> 28) & 7) >= DEFER_MIN_CLASS) {
+                        const int2 l2 = ld64_pol(&dv.link[sa & 0x0fffffff], pol_stream);
+                        if (l2.x < 0 && l2.y < 0) { dv.adj_cursor[atomicAdd(&dv.ctr->n_deferred, 1)] = sa; sa = -1; }
+                    }
+                    if (sb >= 0 && ((sb >> 28) & 7) >= DEFER_MIN_CLASS) {
+                        const int2 l2 = ld64_pol(&dv.link[sb & 0x0fffffff], pol_stream);
+                        if (l2.x < 0 && l2.y < 0) { dv.adj_cursor[atomicAdd(&dv.ctr->n_deferred, 1)] = sb; sb = -1; }
+                    }
+                }
             }
             // successors that became ready join the next level of their own class
             if (sa >= 0) pend[np++] = sa;

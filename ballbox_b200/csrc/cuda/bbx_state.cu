@@ -491,8 +491,12 @@ extern "C" int bbx_dev_stats(BbxDev* d, BallboxStats* out)
     out->levels = c->n_levels; out->overflow = c->overflow | (gp.overflow ? 4 : 0); out->grid_cells = gp.n_cells;
     out->reserved[0] = c->n_cand_sb; out->reserved[1] = c->n_cand_bb; out->reserved[2] = c->n_ss_tests;
     out->reserved[3] = c->n_big; out->reserved[4] = c->n_events;
+    d->last_deferred = c->n_deferred;
     return 0;
 }
+
+// debug: heavy terminal nodes the level kernel held back for its last level in the step bbx_dev_stats last looked at
+extern "C" int bbx_dev_debug_deferred(BbxDev* d) { return d ? d->last_deferred : 0; }
 
 // ---------------------------------------------------------------------------
 // zero-copy views, device-side wrench application, per-world reset

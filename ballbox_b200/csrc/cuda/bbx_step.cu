@@ -431,7 +431,7 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
 __global__ void k_import_reset(BbxDev dv, int n)
 {
     StepCounters* c = dv.ctr;
-    c->n_contacts = n; c->n_cand_sb = 0; c->n_cand_bb = 0; c->n_hit_bb = 0; c->n_hit_bb_edge = 0; c->n_surv_bb = 0; c->n_solver = 0; c->n_touched = 0;
+    c->n_contacts = n; c->n_cand_sb = 0; c->n_cand_bb = 0; c->n_hit_bb = 0; c->n_hit_bb_edge = 0; c->n_surv_bb = 0; c->n_deferred = 0; c->n_solver = 0; c->n_touched = 0;
     c->n_levels = 0; c->n_frontier0 = 0; c->n_mslots = 0; c->n_nodes = 0; c->fq_tail = 0; c->fq_head = 0; c->fq_ticket = 0;
 }
 

@@ -1192,6 +1192,12 @@ int BallboxDebugLevels(PhysicsWorld* w, int* counts8, unsigned long long* ns, in
     return batch_check_dev(p->batch, bbx_dev_debug_levels(p->batch->dev, counts8, ns, max_levels));
 }
 
+int BallboxDebugDeferred(PhysicsWorld* w)
+{
+    BbxWorldPriv* p = priv_of(w);
+    return (p && p->batch->dev) ? bbx_dev_debug_deferred(p->batch->dev) : 0;
+}
+
 int BallboxDebugWarpTrace(PhysicsWorld* w, unsigned long long* out, int n_warps)
 {
     BbxWorldPriv* p = priv_of(w);

@@ -117,6 +117,7 @@ int  BallboxGetStageTiming(PhysicsWorld* world, float* out6, int* steps);
 int  BallboxGetReplayTiming(PhysicsWorld* world, float* ms, int* steps);      /* k_replay_staged alone (part of out6[4]); call after BallboxGetStageTiming */
 
 int  BallboxDebugLevels(PhysicsWorld* world, int* counts8, unsigned long long* ns, int max_levels);
+int  BallboxDebugDeferred(PhysicsWorld* world);   /* after BallboxGetStats: heavy terminal nodes the last step swept in its extra final level */
 int  BallboxDebugWarpTrace(PhysicsWorld* world, unsigned long long* out4, int n_warps);   /* BBX_TRACE_LEVEL=l+1: per warp of the staged replay in level l, iteration 1: start, data ready, end (ns), constraints<<16|chunks */
 
 /* ---- batches of independent worlds (RL style).  All worlds of a batch share

@@ -919,3 +919,32 @@ def test_ragged_last_group_overflow_is_an_error_not_a_stray_write(product):
         else:
             assert rc == 0 and rc2 == 0 and not err, err
         d.DestroyPhysicsWorldBatch(batch)
+
+
+def test_deferred_terminal_nodes_keep_the_trajectory(product, truth):
+    """Thin schedules hold heavy terminal nodes (the probes of a box on the SDF) back for one extra last level.  This must
+    not change a bit: an 8k-body SDF scene is stepped in lockstep with the reference while boxes land on the terrain,
+    compared every 10 steps, and the mechanism must have been in use."""
+    g, c = product.build_scene(bb.SCENE_SDF, 8000, 4711), truth.build_scene(bb.SCENE_SDF, 8000, 4711)
+    deferred = 0
+    for s in range(160):
+        g.step(DT); c.step(DT, pruned=True)
+        if s % 10 == 9:
+            mm = parity.compare_worlds(g, c)
+            assert not mm, f"step {s}: {mm[:3]}"
+            g.stats()
+            deferred = max(deferred, product.dll.BallboxDebugDeferred(g.ptr))
+    assert deferred > 0, "no heavy terminal node was deferred: the test does not cover the mechanism"
+
+
+def test_resident_stepping_is_deterministic_at_scale(product):
+    """Two worlds from the same seed, resident, 200k bodies on the SDF while the contact graph grows from nothing to
+    240k contacts: equal state hashes every 50 steps (a grid-wide race in the level kernel once showed up only here)."""
+    a, b = product.build_scene(bb.SCENE_SDF, 200_000, 20261019), product.build_scene(bb.SCENE_SDF, 200_000, 20261019)
+    for w in (a, b):
+        w.set_sync_mode(bb.SYNC_RESIDENT)
+    for block in range(4):
+        a.step_n(DT, 50); b.step_n(DT, 50)
+        a.download(bb.DL_BODIES); b.download(bb.DL_BODIES)
+        assert a.state_hash() == b.state_hash(), f"after {50 * (block + 1)} steps"
+    assert a.stats().contacts == b.stats().contacts > 200_000
