@@ -948,3 +948,15 @@ def test_resident_stepping_is_deterministic_at_scale(product):
         a.download(bb.DL_BODIES); b.download(bb.DL_BODIES)
         assert a.state_hash() == b.state_hash(), f"after {50 * (block + 1)} steps"
     assert a.stats().contacts == b.stats().contacts > 200_000
+
+
+def test_mid_size_pile_trajectory_in_lockstep(product, truth):
+    """20k mixed bodies falling into a pile, in lockstep with the reference (pruned driver) for 120 steps, compared every
+    20: the schedule grows from a few levels to dozens, with fat levels, manifold nodes and the staged replay's packing."""
+    g, c = product.build_scene(bb.SCENE_MIXED, 20_000, 99), truth.build_scene(bb.SCENE_MIXED, 20_000, 99)
+    for s in range(120):
+        g.step(DT); c.step(DT, pruned=True)
+        if s % 20 == 19:
+            mm = parity.compare_worlds(g, c)
+            assert not mm, f"step {s}: {mm[:3]}"
+    assert g.stats().levels >= 10
