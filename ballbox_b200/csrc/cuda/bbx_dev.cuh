@@ -156,7 +156,7 @@ struct BbxDev {
     int last_flow;                               // the last solve ran on the flow solver (impulses live in fimp)
     int flow_blocks;                             // co-resident blocks of k_solve_flow
     int num_sms;                                 // cudaDevAttrMultiProcessorCount of `device`
-    int replay_mode;                             // BBX_REPLAY: 1 (default) staged replay kernel (bbx_replay.cu), 0 replay inside k_solve_levels
+    int replay_mode;                             // BBX_REPLAY: 1 (default) staged replay kernel (bbx_replay.cu) unless the schedule is thin, 2 always, 0 replay inside k_solve_levels
     float replay_ms_sum; int replay_steps;       // k_replay_staged alone, summed by the last bbx_dev_get_timing
     unsigned char* timing_has7;                  // host array [BBX_TIMING_STEPS]: step s recorded mark 7
     int last_deferred;                           // n_deferred as of the last bbx_dev_stats

@@ -220,6 +220,7 @@ __device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level
 #define ADJ_SIDE(e) ((int)(((unsigned int)(e)) >> 31))
 
 #define RS_MAXLEV 256                  // levels whose tables the staged replay (bbx_replay.cu) keeps in shared memory
+#define RS_MIN_NODES_PER_LEVEL 8192     // thinner schedules replay inside k_solve_levels
 #define FLOW_DBG 4088                  // level_ns[FLOW_DBG..+8): debug counters of the flow solver / level trace
 
 // host entry points of the other solver translation units

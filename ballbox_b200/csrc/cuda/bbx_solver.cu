@@ -546,8 +546,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
         lvl++;
     }
     const int n_levels = lvl;
-    // iterations 1..I-1: in k_replay_staged (first_only) unless the schedule is deeper than its tables
-    const bool own_replay = !sp.first_only || n_levels > RS_MAXLEV;
+    // iterations 1..I-1: in k_replay_staged (first_only) unless the schedule is deeper than its tables or THIN: below ~8k
+    // nodes per level (less than one chunk for every ninth warp) a level is barrier + one chunk, and the plain replay
+    // loop below has the shorter path per level (100k spheres, 4.2k nodes per level: 1.28 vs 1.61 ms; at 11k nodes per
+    // level the two are equal, at 85k the staged replay wins by 0.55 ms)
+    // (first_only == 2, BBX_REPLAY=2: the staged replay also for thin schedules -- test coverage)
+    const bool own_replay = !sp.first_only || n_levels > RS_MAXLEV ||
+                            (sp.first_only == 1 && __ldcg(&dv.ctr->n_nodes) < RS_MIN_NODES_PER_LEVEL * n_levels);
     if (tid == 0) { dv.ctr->n_levels = n_levels; dv.ctr->replay_done = own_replay ? 1 : 0; }
     if (!own_replay) return;
     if (tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); dv.level_ns[4096 + 1] = ns; }
@@ -856,7 +861,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     if (d->trace_level > 0) { sp.gather = d->trace_level; BBX_CUDA(d, cudaMemsetAsync(d->level_ns + FLOW_DBG, 0, 8 * sizeof(unsigned long long), d->stream)); }
     // iteration 0 (level discovery fused with the first sweep) in k_solve_levels; iterations 1..I-1 replay the recorded
     // level-major order in k_replay_staged (BBX_REPLAY=0: inside k_solve_levels, the round-1 replay loop)
-    sp.first_only = (iterations > 1 && d->replay_mode == 1) ? 1 : 0;
+    sp.first_only = (iterations > 1 && d->replay_mode != 0) ? d->replay_mode : 0;
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
     BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));

@@ -679,6 +679,14 @@ def test_in_kernel_replay_is_bit_exact(product, truth, monkeypatch, kind, n, ste
     lockstep(product, truth, kind, n, 31, steps, every=3)
 
 
+@pytest.mark.parametrize("kind,n,steps", [(bb.SCENE_MIXED, 2500, 60), (bb.SCENE_SDF, 1200, 50), (bb.SCENE_BALLS, 4000, 40)])
+def test_staged_replay_on_thin_schedules_is_bit_exact(product, truth, monkeypatch, kind, n, steps):
+    """BBX_REPLAY=2 forces k_replay_staged where the default would replay inside k_solve_levels (thin schedules): small
+    scenes with empty classes, ragged chunks and levels that most warps skip."""
+    monkeypatch.setenv("BBX_REPLAY", "2")
+    lockstep(product, truth, kind, n, 77, steps, every=3)
+
+
 def test_schedule_deeper_than_the_staged_replay_tables(product, truth):
     """A column of 700 touching spheres on a static box: contact (i, i+1) shares a body with (i+1, i+2), so the exact
     schedule is ~700 levels deep, more than RS_MAXLEV = 256: k_solve_levels must run the replay itself."""
