@@ -81,7 +81,7 @@ struct ReplayCtx {
 
 // the chunks warp w owns in level l: descriptor pointer of this lane in the first one, number of chunks, and the
 // number of nodes from this lane's first node to the end of the class (lane is live in chunk r iff r * 32 < left)
-struct WarpWork { const int4* p; int nc; int left; int stride; };   // stride: slots between a node's consecutive records
+struct WarpWork { const int4* p; int nc; int left; int stride; int cls; };   // stride: slots between a node's consecutive records
 __device__ __forceinline__ WarpWork level_work(const BbxDev& dv, const ReplayCtx& cx, int l, int w, int lane)
 {
     const int* b = cx.t_b + l * BBX_NCLS;
@@ -95,9 +95,26 @@ __device__ __forceinline__ WarpWork level_work(const BbxDev& dv, const ReplayCtx
     ww.nc = min(q, nchunks - first);
     ww.left = cnt - (first * 32 + lane);
     ww.p = dv.Nd_k[k] + (cx.t_head[l * BBX_NCLS + k] + first * 32 + lane);
+    ww.cls = k;
     ww.stride = k <= 4 ? cnt : 1;                                            // RECORD SLOTS, bbx_solver.cu
     return ww;
 }
+// the next (iteration, level) after (it, l) in which warp w owns chunks, searched 32 levels at a time by the warp's
+// lanes (a lane-serial scan over the levels cost the warps at the upper end of a thin level's range ~1.5 us: they
+// have no work in the following, smaller levels and walk to the next iteration -- and a thin level lasts as long as
+// its slowest warp); nit = I when there is none
+__device__ __forceinline__ void next_work(const ReplayCtx& cx, int n_levels, int I, int w, int lane, int it, int l, int& nit, int& nl)
+{
+    int base = l + 1;
+    for (;;) {
+        if (base >= n_levels) { base = 0; if (++it >= I) { nit = I; nl = 0; return; } }
+        const int lv = base + lane;
+        const unsigned int m = __ballot_sync(0xffffffffu, lv < n_levels && w < cx.t_nw[lv]);
+        if (m) { nit = it; nl = base + __ffs(m) - 1; return; }
+        base += 32;
+    }
+}
+
 // descriptor of the warp's chunk r -> ring slot
 __device__ __forceinline__ void issue_desc(const ReplayCtx& cx, const WarpWork& ww, int r, int slot)
 {
@@ -196,10 +213,10 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(
     // (nit, nl): the next (iteration, level) in which this warp owns chunks; the first two descriptors are staged as
     // soon as the warp is done with its previous level, the first record just before the barrier the warp arrives at
     int nit = 1, nl = 0;
-    while (nit < I && w >= t_nw[nl]) { if (++nl == n_levels) { nl = 0; nit++; } }
+    if (I > 1) next_work(cx, n_levels, I, w, lane, 1, -1, nit, nl); else nit = I;
     bool staged_rec = false;
     WarpWork nx;
-    nx.p = NULL; nx.nc = 0; nx.left = 0; nx.stride = 1;
+    nx.p = NULL; nx.nc = 0; nx.left = 0; nx.stride = 1; nx.cls = 0;
     if (nit < I) {
         nx = level_work(dv, cx, nl, w, lane);
         issue_desc(cx, nx, 0, 0);
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(
                         }
                         if (r + 2 < ww.nc) issue_desc(cx, ww, r + 2, r & 1);
                     } else {
-                        do { if (++nl == n_levels) { nl = 0; nit++; } } while (nit < I && w >= t_nw[nl]);
+                        next_work(cx, n_levels, I, w, lane, it, l, nit, nl);
                         if (nit < I) {
                             nx = level_work(dv, cx, nl, w, lane);
                             issue_desc(cx, nx, 0, 0);
@@ -277,7 +294,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(
                     cost += nd.y;
                     live = live_n; nd = nd_n;
                 }
-                if (trace) { tr[2] = gtime_ns(); tr[3] = ((unsigned long long)cost << 16) | (unsigned long long)ww.nc; }
+                if (trace) { tr[2] = gtime_ns(); tr[3] = ((unsigned long long)ww.cls << 32) | ((unsigned long long)cost << 16) | (unsigned long long)ww.nc; }
                 // the warp's next head chunk: its descriptor has landed during the last sweep; start its first record
                 staged_rec = false;
                 if (nit < I) {

@@ -55,7 +55,11 @@ if os.environ.get("BBX_TRACE_LEVEL"):
           f"level start spread {(t[:, 0].max() - t0) / 1e3:.2f} us; last warp ends at {(t[work, 2].max() - t0) / 1e3:.2f} us")
     busy = (t[:, 2] - t[:, 0])[work] / 1e3; wait = (t[:, 1] - t[:, 0])[work] / 1e3
     print(f"  busy us: mean {busy.mean():.2f} p50 {np.median(busy):.2f} p90 {np.percentile(busy, 90):.2f} max {busy.max():.2f} | first data wait us: mean {wait.mean():.2f} max {wait.max():.2f}")
-    m = (t[:, 3] >> 16)[work]; nc = (t[:, 3] & 0xffff)[work]
+    m = ((t[:, 3] >> 16) & 0xffff)[work]; nc = (t[:, 3] & 0xffff)[work]; cls = (t[:, 3] >> 32)[work]
+    order = np.argsort(-busy)[:6]
+    widx = np.nonzero(work)[0]
+    print("  slowest warps (warp index, class, chunks, constraints, first data wait us, busy us):",
+          [(int(widx[o]), int(cls[o]), int(nc[o]), int(m[o]), round(float(wait[o]), 2), round(float(busy[o]), 2)) for o in order])
     for mm in sorted(set(m.tolist())):
         sel = m == mm
         print(f"  head node m={mm}: warps {sel.sum()} chunks/warp {nc[sel].mean():.2f} busy mean {busy[sel].mean():.2f} max {busy[sel].max():.2f} end mean {((t[work, 2][sel] - t0) / 1e3).mean():.2f}")
