@@ -541,6 +541,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
         }
         mbase += lm.cnt[0] + lm.cnt[1] + 2 * lm.cnt[2] + 3 * lm.cnt[3] + 4 * lm.cnt[4];
         grid.sync();
+        if (tid == 0 && lvl < 2000) {                                 // debug trace: end of level `lvl` of iteration 0
+            unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+            dv.level_ns[2048 + lvl] = ns;
+        }
         if (threadIdx.x == 0) level_map_load(lm, lc + (lvl + 1) * BBX_NCLS, false);
         __syncthreads();
         lvl++;

@@ -657,6 +657,6 @@ extern "C" int bbx_dev_debug_levels(BbxDev* d, int* counts, unsigned long long* 
     BBX_CUDA(d, cudaStreamSynchronize(d->stream));
     int n = max_levels < 4096 ? max_levels : 4096;
     BBX_CUDA(d, cudaMemcpy(counts, d->level_count, sizeof(int) * (size_t)n * BBX_NCLS, cudaMemcpyDeviceToHost));
-    BBX_CUDA(d, cudaMemcpy(ns, d->level_ns, sizeof(unsigned long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost));
+    BBX_CUDA(d, cudaMemcpy(ns, d->level_ns, sizeof(unsigned long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost));   // [0..n]: replay, [2048..]: iteration 0 (when n = 4096)
     return 0;
 }

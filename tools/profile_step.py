@@ -63,6 +63,10 @@ if os.environ.get("BBX_TRACE_LEVEL"):
     for mm in sorted(set(m.tolist())):
         sel = m == mm
         print(f"  head node m={mm}: warps {sel.sum()} chunks/warp {nc[sel].mean():.2f} busy mean {busy[sel].mean():.2f} max {busy[sel].max():.2f} end mean {((t[work, 2][sel] - t0) / 1e3).mean():.2f}")
+ns0 = np.frombuffer(ns, dtype=np.uint64)[2048:2048 + L].astype(np.int64)
+if L > 1 and ns0.min() > 0:
+    d0 = np.diff(ns0) / 1e3
+    print("iteration 0 level time us (levels 1..):", np.round(d0[:40], 1).tolist(), "sum ms:", round(d0.sum() / 1e3, 4))
 cnt = np.frombuffer(cnt, dtype=np.int32).reshape(-1, 8)[:L]; ns = np.frombuffer(ns, dtype=np.uint64)[:L + 1].astype(np.int64)
 dt_us = np.diff(ns)[1:] / 1e3
 print("levels", L, "nodes/level (first 12):", cnt.sum(1)[:12].tolist())
