@@ -164,6 +164,7 @@ struct BbxDev {
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels
     int tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL
     int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
+    int find_pairs_mode;                         // BBX_FIND_PAIRS: 0 lane-per-body walk, 1 flattened warp walk, unset (-1): by batch size
     int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)
     unsigned long long *level_ns;                // optional trace: globaltimer at the end of each level of iteration 1 (first 4096)
     // level-major copies streamed by iterations >= 1

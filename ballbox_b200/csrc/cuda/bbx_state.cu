@@ -124,6 +124,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->flow, 4 * (size_t)N); DALLOC(d->fq, C); DALLOC(d->fnd, 2 * (size_t)C); DALLOC(d->fimp, 2 * (size_t)C);
     BBX_CUDA(d, cudaMemsetAsync(d->fq, 0xff, sizeof(int) * (size_t)C, d->stream));
     // measurement switches (A/B runs of tools/ and profiles/r01_notes.md), read once per device state
+    { const char* e = getenv("BBX_FIND_PAIRS"); d->find_pairs_mode = e ? (e[0] == '0' ? 0 : 1) : -1; }
     { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1); }   // 1 (default): staged replay kernel unless the schedule is thin; 2: always; 0: never
     { const char* e = getenv("BBX_SOLVE_BLOCKS"); d->tune_solve_blocks = e ? atoi(e) : 0; }

@@ -968,3 +968,26 @@ def test_mid_size_pile_trajectory_in_lockstep(product, truth):
             mm = parity.compare_worlds(g, c)
             assert not mm, f"step {s}: {mm[:3]}"
     assert g.stats().levels >= 10
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_both_cell_walks_find_the_same_pairs(product, truth, monkeypatch, mode):
+    """BBX_FIND_PAIRS=0 (one lane per body) and =1 (candidates of a warp flattened) on a single world and on a batch; the
+    default picks by batch size, so each environment setting forces the other kernel somewhere."""
+    monkeypatch.setenv("BBX_FIND_PAIRS", mode)
+    lockstep(product, truth, bb.SCENE_MIXED, 3000, 5, 30, every=3)
+    d = product.dll
+    s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
+    batch = d.CreatePhysicsWorldBatch(20, s, b, c)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(20)]
+    for i, v in enumerate(views):
+        d.BbxSceneBuild(v.ptr, bb.SCENE_RLWORLD, 0, 900 + i)
+    assert d.PhysicsStepBatch(batch, DT, 40) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    for i in (0, 7, 19):
+        w = truth.build_scene(bb.SCENE_RLWORLD, 0, 900 + i)
+        for _ in range(40):
+            w.step(DT)
+        mm = parity.compare_worlds(views[i], w)
+        assert not mm, f"world {i}: {mm[:3]}"
+    d.DestroyPhysicsWorldBatch(batch)
