@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         if (per_contact) {
             dv.node[2 * (size_t)c] = make_int4(dynA ? a : -1, 0, 0, -1);
             dv.node[2 * (size_t)c + 1] = make_int4(dynB ? b : -1, 0, 0, -1);
+            st64_pol(&dv.link[c], make_int2(-1, -1), pol_links);        // group solver: successors in the dense array (see below)
             dv.indeg[c] = (dynA ? 1 : 0) + (dynB ? 1 : 0);
             if (dynA) atomicAdd(&dv.deg[a], 1);
             if (dynB) atomicAdd(&dv.deg[b], 1);
@@ -244,15 +245,20 @@ __device__ __forceinline__ bool adj_after(const BbxDev& dv, unsigned long long a
     return (a >> 32) > (v >> 32) || ((a >> 32) == (v >> 32) && node_before(dv, ADJ_NODE(v), ADJ_NODE(a)));
 }
 
-__device__ __forceinline__ void adj_write_links(const BbxDev& dv, int x, const unsigned long long* lst, int d, int per_contact)
+__device__ __forceinline__ void adj_write_links(const BbxDev& dv, int x, const unsigned long long* lst, int d, int per_contact, int flow_records)
 {
-    if (per_contact) {
-        // (position, length) and successor of every constraint in this body's chain
+    if (per_contact && flow_records) {
+        // flow solver: (position, length) and successor of every constraint in this body's chain
         for (int i = 0; i < d; i++) {
             const int cur = ADJ_NODE(lst[i]);
             const int nxt = (i + 1 < d) ? ADJ_NODE(lst[i + 1]) : -1;
             dv.node[2 * (size_t)cur + ADJ_SIDE(lst[i])] = make_int4(x, i, d, nxt);
         }
+    } else if (per_contact) {
+        // group solver: only the successor, into the dense link array (a 16-byte half of a node record per (constraint,
+        // side) was a DRAM read-modify-write each)
+        for (int i = 1; i < d; i++)
+            st32_pol((int*)&dv.link[ADJ_NODE(lst[i - 1])] + ADJ_SIDE(lst[i - 1]), ADJ_NODE(lst[i]), l2_policy_normal());
     } else {
         for (int i = 1; i < d; i++) {
             const unsigned long long e2 = lst[i];
@@ -295,7 +301,8 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                 if (atomicSub(&dv.indeg[ADJ_NODE(e0)], 1) == 1) { ready = ADJ_NODE(e0); ready_cls = (int)((e0 >> 32) & 7u); }
 #define ADJ_LINK(i, prev, cur, nxt_valid, nxt)                                                                         \
                 if (i < d) {                                                                                            \
-                    if (per_contact) dv.node[2 * (size_t)ADJ_NODE(cur) + ADJ_SIDE(cur)] = make_int4(x, i, d, (nxt_valid) ? ADJ_NODE(nxt) : -1); \
+                    if (per_contact && flow_records) dv.node[2 * (size_t)ADJ_NODE(cur) + ADJ_SIDE(cur)] = make_int4(x, i, d, (nxt_valid) ? ADJ_NODE(nxt) : -1); \
+                    else if (per_contact) { if (i > 0) st32_pol((int*)&dv.link[ADJ_NODE(prev)] + ADJ_SIDE(prev), ADJ_NODE(cur), pol_links); } \
                     else if (i > 0) st32_pol((int*)&dv.link[ADJ_NODE(prev)] + ADJ_SIDE(prev), ADJ_NODE(cur) | ((int)((cur >> 32) & 7u) << 28), pol_links); \
                     if (keep_sorted) lst[i] = cur;                                                                      \
                 }
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                 }
                 // first node of this body has no predecessor here
                 if (atomicSub(&dv.indeg[ADJ_NODE(loc[0])], 1) == 1) { ready = ADJ_NODE(loc[0]); ready_cls = (int)((loc[0] >> 32) & 7u); }
-                adj_write_links(dv, x, loc, d, per_contact);
+                adj_write_links(dv, x, loc, d, per_contact, flow_records);
                 if (keep_sorted) for (int i = 0; i < d; i++) lst[i] = loc[i];
             } else {
                 for (int i = 1; i < d; i++) {
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(128) k_adj_link(BbxDev dv, int per_contact, in
                     lst[j + 1] = v;
                 }
                 if (atomicSub(&dv.indeg[ADJ_NODE(lst[0])], 1) == 1) { ready = ADJ_NODE(lst[0]); ready_cls = (int)((lst[0] >> 32) & 7u); }
-                adj_write_links(dv, x, lst, d, per_contact);
+                adj_write_links(dv, x, lst, d, per_contact, flow_records);
             }
             if (per_contact && flow_records && !keep_sorted) flow_init_body(dv, x);    // the body's versioned record starts at version 0
             wake_body(dv, x);              // :1373-1376, :1402-1405: every impulse application wakes the body, even a zero one
@@ -700,9 +707,10 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     while (head < tail) {
         for (int p = head + tid; p < tail; p += GRP_THREADS) {
             const int c = __ldcg(&queue[p]);
-            F8 nd = ld256_nc_pol((const float4*)&dv.node[2 * (size_t)c], pol_stream);    // (gid A, pos, len, successor on A) (same for B)
+            F8 nd = ld256_nc_pol((const float4*)&dv.node[2 * (size_t)c], pol_stream);    // (gid A, ...) (gid B, ...)
+            const int2 lk = ld64_pol(&dv.link[c], pol_stream);                           // successors on A's and B's chain
             const int gA = __float_as_int(nd.a.x), gB = __float_as_int(nd.b.x);
-            const int sa = __float_as_int(nd.a.w), sb = __float_as_int(nd.b.w);
+            const int sa = lk.x, sb = lk.y;
             const float4* L = dv.L + 4 * (size_t)c;
             F8 lo = ld256_nc_pol(L, pol_stream), hi = ld256_nc_pol(L + 2, pol_stream);
             float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
