@@ -159,6 +159,7 @@ struct BbxDev {
     int replay_mode;                             // BBX_REPLAY: 1 (default) staged replay kernel (bbx_replay.cu) unless the schedule is thin, 2 always, 0 replay inside k_solve_levels
     float replay_ms_sum; int replay_steps;       // k_replay_staged alone, summed by the last bbx_dev_get_timing
     unsigned char* timing_has7;                  // host array [BBX_TIMING_STEPS]: step s recorded mark 7
+    int slot_of_stale;                           // the last solve ran on the level kernels and slot_of has not been built for it yet
     int last_deferred;                           // n_deferred as of the last bbx_dev_stats
     int replay_blocks;                           // co-resident blocks of k_replay_staged
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels

@@ -225,4 +225,5 @@ __device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level
 
 // host entry points of the other solver translation units
 int bbx_flow_solve(BbxDev* d, const BbxStepParams* p, int iterations);
+int bbx_ensure_slot_of(BbxDev* d);
 int bbx_replay_staged(BbxDev* d, const SolveParams& sp);

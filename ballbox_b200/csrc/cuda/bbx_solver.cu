@@ -403,6 +403,8 @@ __global__ void __launch_bounds__(128) k_warm_apply(BbxDev dv, int per_contact, 
 #define PEND_ROUNDS 4                  // rounds of a level between two block-aggregated appends
 #define DEFER_MIN_CLASS 3              // node classes 3.. (>= 3 constraints per node) may be deferred when terminal
 
+__device__ __forceinline__ unsigned long long gtime0_ns() { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); return ns; }
+
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_levels(BbxDev dv, SolveParams sp)
 {
     cg::grid_group grid = cg::this_grid();
@@ -464,6 +466,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
         // one atomic per block and class instead of one per warp and class takes them off the critical path.
         int pend[2 * PEND_ROUNDS], np = 0;
         const int rounds = (total + stride - 1) / stride;            // uniform over the grid: every thread takes part in the flushes
+        const int w0t = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+        const bool tr0 = sp.gather == lvl + 1 && (threadIdx.x & 31) == 0 && w0t < BBX_TRACE_WARPS / 2;
+        unsigned long long* trp = dv.level_ns + 4104 + 8 * (size_t)w0t;
+        if (tr0) { for (int q = 0; q < 8; q++) trp[q] = 0; trp[0] = gtime0_ns(); }
         for (int r = 0; r < rounds; r++) {
             const int t = wtid + r * stride;
             int k = BBX_NCLS - 1;
@@ -481,6 +487,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 nd0 = make_int4(rec.x, rec.y, rec.z, 0);
                 sa = lk.x; sb = lk.y;
                 m = nd0.z;
+                if (tr0 && r == 0) trp[1] = gtime0_ns() + (unsigned long long)(m & 0);      // node + links have arrived
             }
             int slot0, mstride;
             if (k <= 4) {
@@ -500,18 +507,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 // the current constraint is swept), then written plane-major
                 const float4* L = dv.L + 4 * (size_t)c;
                 F8 lo = ld256_nc_pol(L, pol_stream), hi = ld256_nc_pol(L + 2, pol_stream);
+                if (tr0 && r == 0) trp[2] = gtime0_ns() + (unsigned long long)(__float_as_int(lo.a.x) & 0) + (unsigned long long)(hasA ? (__float_as_int(A.v.x) & 0) : 0);   // record + body A have arrived
                 for (int j = 0; j < m; j++, L += 4) {
                     float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
                     if (j + 1 < m) { lo = ld256_nc_pol(L + 4, pol_stream); hi = ld256_nc_pol(L + 6, pol_stream); }
                     solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     float4* M = dv.M + (size_t)(slot0 + j * mstride);
                     st128_cg_pol(M, c0, pol_stream); st128_cg_pol(M + PL, c1, pol_stream); st128_cg_pol(M + 2 * PL, c2, pol_stream); st128_cg_pol(M + 3 * PL, c3, pol_stream);
-                    dv.slot_of[c + j] = slot0 + j * mstride;
                 }
                 if (hasA) store_body_keep(dv, nd0.x, A, pol_keep);    // (the bodies were woken by k_adj_link: one coalesced pass over the
                 if (hasB) store_body_keep(dv, nd0.y, B, pol_keep);    //  touched bodies instead of a random flag access per node here)
+                if (tr0 && r == 0) trp[3] = gtime0_ns();                                     // sweeps and stores issued
                 if (sa >= 0 && atomicSub(&dv.indeg[sa & 0x0fffffff], 1) != 1) sa = -1;
                 if (sb >= 0 && atomicSub(&dv.indeg[sb & 0x0fffffff], 1) != 1) sb = -1;
+                if (tr0 && r == 0) trp[4] = gtime0_ns() + (unsigned long long)((sa | sb) & 0);      // in-degree atomics have returned
                 if (defer_on) {
                     // DEFERRED TERMINAL NODES: a heavy node (>= 3 constraints) without successors -- typically the probes of a box
                     // on the SDF, always last in the box's chain -- may run at any later time.  In a thin schedule every level
@@ -546,8 +555,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 np = 0;
             }
         }
+        if (tr0) { trp[5] = gtime0_ns(); trp[6] = (unsigned long long)rounds; }               // all rounds and flushes done
         mbase += lm.cnt[0] + lm.cnt[1] + 2 * lm.cnt[2] + 3 * lm.cnt[3] + 4 * lm.cnt[4];
         grid.sync();
+        if (tr0) trp[7] = gtime0_ns();
         if (tid == 0 && lvl < 2000) {                                 // debug trace: end of level `lvl` of iteration 0
             unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
             dv.level_ns[2048 + lvl] = ns;
@@ -788,6 +799,38 @@ static bool use_world_groups(const BbxDev* d, int imported, int schedule)
     return !imported && d->n_worlds >= 16 && schedule == BBX_SOLVER_EXACT && d->cap_s + d->cap_b <= GRP_WORLD_BODIES_MAX;
 }
 
+// contact -> record slot for the level path, built ON DEMAND (export of the constraint list, warm-start save): the level-major
+// queues hold the node's head contact, the descriptors its first slot and length.  Iteration 0 used to scatter these 4 bytes
+// per constraint itself: 24 MB of data, ~380 MB of DRAM read-modify-write traffic in the hottest kernel, for a table that
+// resident stepping never reads.
+__global__ void __launch_bounds__(256) k_build_slot_of(BbxDev dv)
+{
+    const int n_levels = dv.ctr->n_levels;
+    for (int l = blockIdx.x; l < n_levels; l += gridDim.x) {
+        for (int k = 0; k < BBX_NCLS; k++) {
+            const int cnt = dv.level_count[l * BBX_NCLS + k];
+            if (cnt == 0) continue;
+            int head = 0;
+            for (int l2 = 0; l2 < l; l2++) head += dv.level_count[l2 * BBX_NCLS + k];
+            const int stride = k <= 4 ? cnt : 1;                                  // RECORD SLOTS (k_solve_levels)
+            for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x) {
+                const int c = dv.queue_k[k][head + idx];
+                const int4 nd = dv.Nd_k[k][head + idx];
+                for (int j = 0; j < nd.y; j++) dv.slot_of[c + j] = nd.x + j * stride;
+            }
+        }
+    }
+}
+
+int bbx_ensure_slot_of(BbxDev* d)
+{
+    if (!d->slot_of_stale) return 0;
+    BBX_LAUNCH(d, k_build_slot_of, BBX_NUM_SMS * 4, 256, 0, *d);
+    BBX_CUDA(d, cudaGetLastError());
+    d->slot_of_stale = 0;
+    return 0;
+}
+
 // warm-start table, allocated at first use: at most half full
 int bbx_warm_ensure(BbxDev* d)
 {
@@ -831,6 +874,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, warm > 0.0f ? 1 : 0, levels_path);
     if (warm > 0.0f) BBX_LAUNCH(d, k_warm_apply, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, p->settings.friction);
     d->last_flow = flow; d->last_per_contact = per_contact;
+    d->slot_of_stale = levels_path;          // the level kernels do not write slot_of: bbx_ensure_slot_of builds it on demand
     if (flow) return bbx_flow_solve(d, p, iterations);
     SolveParams sp;
     sp.restitution = p->settings.restitution; sp.friction = p->settings.friction;

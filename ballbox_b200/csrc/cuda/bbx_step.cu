@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <vector>
 #include "bbx_dev.cuh"
+int bbx_ensure_slot_of(BbxDev* d);             // bbx_solver.cu
 #include <nvtx3/nvToolsExt.h>          // header-only; ranges are pushed only with BBX_NVTX=1
 
 void bbx_timing_mark(BbxDev* d, int mark)
@@ -222,6 +223,7 @@ int bbx_stage_warm_save(BbxDev* d, const BbxStepParams* p)
     int rc = bbx_warm_ensure(d);
     if (rc) return rc;
     BBX_CUDA(d, cudaMemsetAsync(d->warm_key, 0xff, sizeof(unsigned long long) * ((size_t)d->warm_mask + 1), d->stream));
+    { int rcs = bbx_ensure_slot_of(d); if (rcs) return rcs; }
     BBX_LAUNCH(d, k_warm_save, BBX_NUM_SMS * 8, 256, 0, *d, p->settings.solver_iterations > 0 ? 1 : 0, p->settings.friction);
     BBX_CUDA(d, cudaGetLastError());
     return 0;
@@ -370,6 +372,7 @@ extern "C" int bbx_dev_download_constraints(BbxDev* d, ContactConstraint* out, i
     if (total_bits > 64) return bbx_fail(d, BBX_ERR_BAD_ARGUMENT, "export key does not fit 64 bits", __FILE__, __LINE__);
     { int rc0 = ensure_export_buffers(d); if (rc0) return rc0; }
     const BbxStepParams* p = &d->last_params;
+    { int rcs = bbx_ensure_slot_of(d); if (rcs) return rcs; }
     BBX_LAUNCH(d, k_export_constraints, BBX_NUM_SMS * 8, 256, 0, *d, d->export_buf, d->sort_keys,
                p->settings.restitution, p->settings.friction, p->settings.solver_iterations > 0 ? 1 : 0, kb);
     BBX_CUDA(d, cudaGetLastError());
@@ -529,6 +532,7 @@ extern "C" int bbx_dev_export_list(BbxDev* d, ContactConstraint* out, int n, flo
     int rc = ensure_export_buffers(d);
     if (rc) return rc;
     KeyBits kb = key_bits_of(d);
+    { int rcs = bbx_ensure_slot_of(d); if (rcs) return rcs; }
     BBX_LAUNCH(d, k_export_constraints, BBX_NUM_SMS * 8, 256, 0, *d, d->export_buf, d->sort_keys, restitution, friction, solved, kb);
     BBX_CUDA(d, cudaGetLastError());
     BBX_CUDA(d, cudaMemcpyAsync(out, d->export_buf, sizeof(ContactConstraint) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));

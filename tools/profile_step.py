@@ -43,7 +43,21 @@ cnt = (C.c_int * (8 * 4096))(); ns = (C.c_ulonglong * 4097)()
 lib.dll.BallboxDebugLevels.argtypes = [bb.WP, C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.c_int]
 lib.dll.BallboxDebugLevels(w.ptr, cnt, ns, 4096)
 fd = np.frombuffer(ns, dtype=np.uint64)[4088:4096].astype(np.float64)
-if os.environ.get("BBX_TRACE_LEVEL"):
+if os.environ.get("BBX_TRACE_IT0"):
+    NW = 2 * 148 * 8
+    tr = (C.c_ulonglong * (8 * NW))()
+    lib.dll.BallboxDebugWarpTrace.argtypes = [bb.WP, C.POINTER(C.c_ulonglong), C.c_int]
+    lib.dll.BallboxDebugWarpTrace(w.ptr, tr, 2 * NW)
+    t = np.frombuffer(tr, dtype=np.uint64).reshape(NW, 8).astype(np.int64)
+    ok = (t[:, 1] > 0) & (t[:, 4] > 0)
+    t0 = t[ok, 0].min()
+    names = ["node+links", "record+bodies", "sweep+stores", "in-degree atomics", "rest of level (other rounds, flushes)", "grid barrier"]
+    print(f"iteration 0, level {int(os.environ['BBX_TRACE_LEVEL']) - 1}: {ok.sum()} warps with a first chunk; rounds {int(t[ok, 6].max())}")
+    for k, nm in enumerate(names):
+        d = (t[ok, k + 1] - t[ok, k]) / 1e3
+        print(f"  {nm}: mean {d.mean():.2f} us  p90 {np.percentile(d, 90):.2f}  max {d.max():.2f}")
+    print(f"  level, first warp start to last barrier exit: {(t[ok, 7].max() - t0) / 1e3:.2f} us")
+elif os.environ.get("BBX_TRACE_LEVEL"):
     NW = 2 * 148 * 8
     tr = (C.c_ulonglong * (4 * NW))()
     lib.dll.BallboxDebugWarpTrace.argtypes = [bb.WP, C.POINTER(C.c_ulonglong), C.c_int]
