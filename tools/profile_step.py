@@ -85,7 +85,7 @@ cnt = np.frombuffer(cnt, dtype=np.int32).reshape(-1, 8)[:L]; ns = np.frombuffer(
 dt_us = np.diff(ns)[1:] / 1e3
 print("levels", L, "nodes/level (first 12):", cnt.sum(1)[:12].tolist())
 print("class totals:", cnt.sum(0).tolist())
-print("level time us (levels 1..):", np.round(dt_us[:40], 1).tolist())
+print("level time us (levels 1..):", np.round(dt_us[:40], 1).tolist(), "| levels 41..:", np.round(dt_us[40:], 1).tolist())
 print("sum level times (iteration 1) ms:", dt_us.sum() / 1e3, "tail levels (<1000 nodes):", int((cnt.sum(1) < 1000).sum()))
 for l in range(0, L, 4):
     print(l, cnt[l].tolist(), "us=%.1f" % (dt_us[l - 1] if l >= 1 and l - 1 < len(dt_us) else -1))
