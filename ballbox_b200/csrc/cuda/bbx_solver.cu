@@ -138,9 +138,13 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
             dv.indeg[c] = (dynA ? 1 : 0) + (dynB ? 1 : 0);
             if (dynA) atomicAdd(&dv.deg[a], 1);
             if (dynB) atomicAdd(&dv.deg[b], 1);
-        } else if (RUN_K(id.z) == 0) {                                                  // node head
+        } else if (RUN_K(id.z) != 0) {
+            // level path: one 16-byte node record per CONTACT (dv.node[c]); a continuation of a run gets a dummy so that the
+            // warp writes whole sectors (16 bytes at a 32-byte stride, heads only, was a DRAM read-modify-write per record)
+            dv.node[c] = make_int4(-1, -1, 0, 0);
+        } else {                                                                        // node head
             int m = RUN_LEN(id.z);
-            dv.node[2 * (size_t)c] = make_int4(dynA ? a : -1, dynB ? b : -1, m, bbx_node_class(m, a >= dv.NS || b >= dv.NS));
+            dv.node[c] = make_int4(dynA ? a : -1, dynB ? b : -1, m, bbx_node_class(m, a >= dv.NS || b >= dv.NS));
             // successor links live in their own dense array: k_adj_link fills them with scattered 4-byte stores, which in the
             // 32-byte node records were DRAM read-modify-writes (669 MB of traffic for 70 MB of links); at 8 bytes per
             // contact the array is small enough for those partial writes to be merged in L2 (presolve+graph 0.81 -> 0.69 ms;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(256) k_adj_fill(BbxDev dv, int order, int per_
             continue;
         }
         if (RUN_K(id.z) != 0) continue;
-        int4 l = dv.node[2 * (size_t)c];
+        int4 l = dv.node[c];
         if (l.x >= 0) {
             int slot = atomicAdd(&dv.adj_cursor[l.x], 1);
             unsigned int key = order == 1 ? coloured_key(id, l.w) : (order == 2 ? (((unsigned int)c << 3) | (unsigned int)l.w) : body_order_key(dv, id, true, l.w));
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
             int4 nd0 = make_int4(-1, -1, 0, 0);
             if (live) {
                 c = __ldcg(&dv.queue_k[k][p]);
-                const int4 rec = ld128i_cg_pol(&dv.node[2 * (size_t)c], pol_stream);             // ids, run length
+                const int4 rec = ld128i_cg_pol(&dv.node[c], pol_stream);                         // ids, run length
                 const int2 lk = ld64_pol(&dv.link[c], pol_stream);                                // successors (L2 resident, last use)
                 nd0 = make_int4(rec.x, rec.y, rec.z, 0);
                 sa = lk.x; sb = lk.y;

@@ -151,8 +151,9 @@ __device__ __forceinline__ void final_impulses(const BbxDev& dv, int c, int4 id,
         // a constraint between two non-dynamic bodies is never scheduled, but the reference still
         // sweeps it: with zero effective masses it ends at fmaxf(-0, fminf(+0, +-0)) = -0 (:1477).
         // (In the block-per-world path scheduled constraints keep their impulses in L: slot < 0 too.)
-        int4 hd = dv.node[2 * (size_t)(c - RUN_K(id.z))];
-        if (dv.last_per_contact) hd.y = dv.node[2 * (size_t)(c - RUN_K(id.z)) + 1].x;   // per-constraint layout: one half per body
+        const int h = c - RUN_K(id.z);
+        int4 hd = dv.last_per_contact ? dv.node[2 * (size_t)h] : dv.node[h];           // level path: one record per contact
+        if (dv.last_per_contact) hd.y = dv.node[2 * (size_t)h + 1].x;                   // per-constraint layout: one half per body
         if (hd.x < 0 && hd.y < 0) { jt0 = -0.0f; jt1 = -0.0f; }
     }
 }
