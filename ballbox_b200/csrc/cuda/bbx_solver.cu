@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(256) k_presolve(BbxDev dv, float baumgarte, fl
         }
         else if (mode == 0) L[3] = make_float4(0.0f, 0.0f, 0.0f, mT1);                  // impulses start at 0 (:1203-1206)
         else                L[3] = make_float4(keep.x, keep.y, keep.z, mT1);
-        dv.slot_of[c] = -1;
         if (per_contact) {
+            dv.slot_of[c] = -1;                     // (level path: bbx_ensure_slot_of clears and builds the table on demand)
             dv.node[2 * (size_t)c] = make_int4(dynA ? a : -1, 0, 0, -1);
             dv.node[2 * (size_t)c + 1] = make_int4(dynB ? b : -1, 0, 0, -1);
             st64_pol(&dv.link[c], make_int2(-1, -1), pol_links);        // group solver: successors in the dense array (see below)
@@ -829,6 +829,7 @@ __global__ void __launch_bounds__(256) k_build_slot_of(BbxDev dv)
 int bbx_ensure_slot_of(BbxDev* d)
 {
     if (!d->slot_of_stale) return 0;
+    BBX_CUDA(d, cudaMemsetAsync(d->slot_of, 0xff, sizeof(int) * (size_t)d->cap_contacts, d->stream));      // -1: not scheduled
     BBX_LAUNCH(d, k_build_slot_of, BBX_NUM_SMS * 4, 256, 0, *d);
     BBX_CUDA(d, cudaGetLastError());
     d->slot_of_stale = 0;
