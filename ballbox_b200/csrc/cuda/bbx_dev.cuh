@@ -76,6 +76,7 @@ struct StepCounters {
     int replay_done;         // k_solve_levels ran iterations 1..I-1 itself (more levels than the staged replay's tables hold)
     int n_surv_bb;           // box-box candidates not separated by a face axis (compacted into cand_sb by k_bb_face)
     int n_deferred;          // level kernel: heavy terminal nodes held back for the last level (list in adj_cursor)
+    int colour_overflow;     // coloured schedule: a node found all 64 colours taken on its bodies (the step replays in level order)
 };
 
 struct BbxDev {
@@ -142,6 +143,14 @@ struct BbxDev {
                                                  // each = node | class << 28, -1 = none (level path)
     // warm starting (extension): open-addressing table (body A, body B, k) -> final impulses of the previous step
     unsigned long long *warm_key; float4 *warm_val; unsigned int warm_mask;
+    // coloured schedule (bbx_colour.cu, allocated at first use): the second set of level-major buffers the colour-major
+    // order is written to (swapped with the first set after every coloured solve), and the colouring scratch
+    float4 *M2; int *queue2_k[BBX_NCLS]; int4 *Nd2_k[BBX_NCLS]; int *level_count2;
+    int *colq_k[BBX_NCLS];                       // colour of the node at the same position of queue_k
+    unsigned long long *col_used;                // per body: colours of the nodes swept so far in iteration 0
+    int *col_tab;                                // class totals, counts / fill / heads per (colour, class), record bases (COL_* offsets)
+    int coop_blocks_col;                         // co-resident blocks of k_solve_levels<true>
+    int colour_limit;                            // colours a step may use (64; BBX_COLOUR_LIMIT lowers it to exercise the fallback)
     int *warm_epoch;                             // per world: bumped by a world reset, stored with every entry (stale entries miss)
     int *level_count;                            // (cap_levels + 4) * BBX_NCLS
     // ---- barrier-free flow solver (single large world, bbx_solver.cu k_solve_flow) ----

@@ -227,3 +227,13 @@ __device__ __forceinline__ void level_map_load(LevelMap& lm, const int* lc_level
 int bbx_flow_solve(BbxDev* d, const BbxStepParams* p, int iterations);
 int bbx_ensure_slot_of(BbxDev* d);
 int bbx_replay_staged(BbxDev* d, const SolveParams& sp);
+// coloured schedule (bbx_colour.cu)
+#define BBX_MAX_COLOURS 64
+#define COL_TOT   0                                   // [BBX_NCLS] nodes per class (all levels)
+#define COL_CNT   8                                   // [64 * BBX_NCLS] nodes per (colour, class)
+#define COL_FILL  (COL_CNT + BBX_MAX_COLOURS * BBX_NCLS)
+#define COL_HEAD  (COL_FILL + BBX_MAX_COLOURS * BBX_NCLS)
+#define COL_MBASE (COL_HEAD + BBX_MAX_COLOURS * BBX_NCLS)
+#define COL_INTS  (COL_MBASE + BBX_MAX_COLOURS + 8)
+int bbx_colour_ensure(BbxDev* d);
+int bbx_colour_rebucket(BbxDev* d);

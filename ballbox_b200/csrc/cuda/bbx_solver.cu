@@ -409,6 +409,11 @@ __global__ void __launch_bounds__(128) k_warm_apply(BbxDev dv, int per_contact, 
 
 __device__ __forceinline__ unsigned long long gtime0_ns() { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); return ns; }
 
+// COLOUR (coloured schedule with the staged replay): every node also takes the smallest colour not yet used on its two
+// bodies (the per-body masks ride along the chains: a node is the only ready node of both its bodies, so the masks need no
+// atomics; greedy colouring in the order of the hash priorities, <= deg(A) + deg(B) - 1 colours, ~max degree + 1 in a pile)
+// and stores it at its queue position; bbx_colour_rebucket then rewrites the level-major order colour-major
+template <bool COLOUR>
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_levels(BbxDev dv, SolveParams sp)
 {
     cg::grid_group grid = cg::this_grid();
@@ -504,6 +509,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
             if (live) {
                 __stcg(&dv.Nd_k[k][p], make_int4(slot0, m, nd0.x, nd0.y));
                 bool hasA = nd0.x >= 0, hasB = nd0.y >= 0;
+                if (COLOUR) {
+                    const unsigned long long ua = hasA ? __ldcg(&dv.col_used[nd0.x]) : 0ull, ub = hasB ? __ldcg(&dv.col_used[nd0.y]) : 0ull;
+                    const unsigned long long fr = ~(ua | ub);
+                    int colr = fr == 0ull ? BBX_MAX_COLOURS : __ffsll((long long)fr) - 1;
+                    if (colr >= dv.colour_limit) { atomicOr(&dv.ctr->colour_overflow, 1); colr = dv.colour_limit - 1; }      // (the step replays its levels)
+                    if (hasA) __stcg(&dv.col_used[nd0.x], ua | (1ull << colr));
+                    if (hasB) __stcg(&dv.col_used[nd0.y], ub | (1ull << colr));
+                    __stcg(&dv.colq_k[k][p], colr);
+                }
                 BodyState A, B;
                 if (hasA) load_body_keep(dv, nd0.x, A, pol_keep);
                 if (hasB) load_body_keep(dv, nd0.y, B, pol_keep);
@@ -578,7 +592,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
     // level the two are equal, at 85k the staged replay wins by 0.55 ms)
     // (first_only == 2, BBX_REPLAY=2: the staged replay also for thin schedules -- test coverage)
     const bool own_replay = !sp.first_only || n_levels > RS_MAXLEV ||
-                            (sp.first_only == 1 && __ldcg(&dv.ctr->n_nodes) < RS_MIN_NODES_PER_LEVEL * n_levels);
+                            (!COLOUR && sp.first_only == 1 && __ldcg(&dv.ctr->n_nodes) < RS_MIN_NODES_PER_LEVEL * n_levels);   // (colour-major replay: a dozen levels)
     if (tid == 0) { dv.ctr->n_levels = n_levels; dv.ctr->replay_done = own_replay ? 1 : 0; }
     if (!own_replay) return;
     if (tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); dv.level_ns[4096 + 1] = ns; }
@@ -908,26 +922,37 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         return 0;
     }
     // (level 0 of the class queues was filled by k_adj_link)
-    if (d->coop_blocks == 0) {
-        int per_sm = 0, coop = 0;
-        BBX_CUDA(d, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d->device));
-        if (!coop) return bbx_fail(d, BBX_ERR_NO_DEVICE, "device lacks cooperative launch", __FILE__, __LINE__);
-        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_levels, SOLVE_THREADS, 0));
-        if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "solver kernel does not fit on an SM", __FILE__, __LINE__);
-        if (per_sm > SOLVE_BLOCKS_PER_SM) per_sm = SOLVE_BLOCKS_PER_SM;
-        d->coop_blocks = per_sm * d->num_sms;
-        if (d->tune_solve_blocks > 0 && d->tune_solve_blocks < d->coop_blocks) d->coop_blocks = d->tune_solve_blocks;
-    }
-    bbx_timing_mark(d, 4);
-    if (d->trace_level > 0) { sp.gather = d->trace_level; BBX_CUDA(d, cudaMemsetAsync(d->level_ns + FLOW_DBG, 0, 8 * sizeof(unsigned long long), d->stream)); }
     // iteration 0 (level discovery fused with the first sweep) in k_solve_levels; iterations 1..I-1 replay the recorded
     // level-major order in k_replay_staged (BBX_REPLAY=0: inside k_solve_levels, the round-1 replay loop)
     sp.first_only = (iterations > 1 && d->replay_mode != 0) ? d->replay_mode : 0;
+    // coloured schedule: colours are taken during iteration 0 and the replay runs colour-major (bbx_colour.cu)
+    const int colour = (p->solver_schedule == BBX_SOLVER_COLOURED && !imported && sp.first_only) ? 1 : 0;
+    if (colour) {
+        int rcc = bbx_colour_ensure(d); if (rcc) return rcc;
+        BBX_CUDA(d, cudaMemsetAsync(d->col_used, 0, sizeof(unsigned long long) * (size_t)d->N, d->stream));
+        BBX_CUDA(d, cudaMemsetAsync(&d->ctr->colour_overflow, 0, sizeof(int), d->stream));
+    }
+    int* coop_blocks = colour ? &d->coop_blocks_col : &d->coop_blocks;
+    void* kernel = colour ? (void*)k_solve_levels<true> : (void*)k_solve_levels<false>;
+    if (*coop_blocks == 0) {
+        int per_sm = 0, coop = 0;
+        BBX_CUDA(d, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d->device));
+        if (!coop) return bbx_fail(d, BBX_ERR_NO_DEVICE, "device lacks cooperative launch", __FILE__, __LINE__);
+        if (colour) BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_levels<true>, SOLVE_THREADS, 0));
+        else        BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_levels<false>, SOLVE_THREADS, 0));
+        if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "solver kernel does not fit on an SM", __FILE__, __LINE__);
+        if (per_sm > SOLVE_BLOCKS_PER_SM) per_sm = SOLVE_BLOCKS_PER_SM;
+        *coop_blocks = per_sm * d->num_sms;
+        if (d->tune_solve_blocks > 0 && d->tune_solve_blocks < *coop_blocks) *coop_blocks = d->tune_solve_blocks;
+    }
+    bbx_timing_mark(d, 4);
+    if (d->trace_level > 0) { sp.gather = d->trace_level; BBX_CUDA(d, cudaMemsetAsync(d->level_ns + FLOW_DBG, 0, 8 * sizeof(unsigned long long), d->stream)); }
     BbxDev dv = *d;
     void* args[] = { (void*)&dv, (void*)&sp };
-    BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_solve_levels, dim3(d->coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
+    BBX_CUDA(d, cudaLaunchCooperativeKernel(kernel, dim3(*coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
     d->launches++;
     BBX_CUDA(d, cudaGetLastError());
+    if (colour) { int rcc = bbx_colour_rebucket(d); if (rcc) return rcc; }
     if (sp.first_only) {
         if (d->timing_on && d->timing_steps < d->timing_cap) { bbx_timing_mark(d, 7); d->timing_has7[d->timing_steps] = 1; }
         return bbx_replay_staged(d, sp);

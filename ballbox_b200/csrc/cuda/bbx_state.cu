@@ -124,6 +124,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     DALLOC(d->flow, 4 * (size_t)N); DALLOC(d->fq, C); DALLOC(d->fnd, 2 * (size_t)C); DALLOC(d->fimp, 2 * (size_t)C);
     BBX_CUDA(d, cudaMemsetAsync(d->fq, 0xff, sizeof(int) * (size_t)C, d->stream));
     // measurement switches (A/B runs of tools/ and profiles/r01_notes.md), read once per device state
+    { const char* e = getenv("BBX_COLOUR_LIMIT"); d->colour_limit = e ? atoi(e) : 64; if (d->colour_limit < 1 || d->colour_limit > 64) d->colour_limit = 64; }
     { const char* e = getenv("BBX_FIND_PAIRS"); d->find_pairs_mode = e ? (e[0] == '0' ? 0 : 1) : -1; }
     { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1); }   // 1 (default): staged replay kernel unless the schedule is thin; 2: always; 0: never
@@ -154,9 +155,10 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->sorted_pos, d->big_list, d->big_start, d->scan_tmp, d->cand_sb, d->cand_bb, d->hit_ids, d->hit_ax, d->c_ids, d->c_pt, d->c_nrm,
         d->L, d->node, d->bar, d->deg, d->adj_start, d->adj_cursor, d->adj, d->indeg,
         d->sdf_grid, d->slot_of, d->link, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->wake_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
-        d->sort_hist, d->sort_hist_scan, d->warm_key, d->warm_val, d->warm_epoch };
+        d->sort_hist, d->sort_hist_scan, d->warm_key, d->warm_val, d->warm_epoch, d->M2, d->level_count2, d->col_used, d->col_tab };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
+    for (int k = 0; k < BBX_NCLS; k++) { if (d->queue2_k[k]) cudaFree(d->queue2_k[k]); if (d->Nd2_k[k]) cudaFree(d->Nd2_k[k]); if (d->colq_k[k]) cudaFree(d->colq_k[k]); }
     if (d->ctr_host) cudaFreeHost(d->ctr_host);
     if (d->timing_ev) { for (int i = 0; i < d->timing_cap * BBX_TIMING_MARKS; i++) cudaEventDestroy(d->timing_ev[i]); free(d->timing_ev); free(d->timing_has7); }
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);

@@ -665,3 +665,39 @@ extern "C" int bbx_dev_debug_levels(BbxDev* d, int* counts, unsigned long long* 
     BBX_CUDA(d, cudaMemcpy(ns, d->level_ns, sizeof(unsigned long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost));   // [0..n]: replay, [2048..]: iteration 0 (when n = 4096)
     return 0;
 }
+
+// Debug / tests: the visiting order of the last level-path solve.  out[i] = (level, constraints of the node, gid A, gid B)
+// for every node, level by level and class by class; returns the number of nodes (or a negative error).
+extern "C" int bbx_dev_debug_schedule(BbxDev* d, int* out4, int cap_nodes)
+{
+    if (!d || !out4) return BBX_ERR_BAD_ARGUMENT;
+    BBX_CUDA(d, cudaSetDevice(d->device));
+    BBX_CUDA(d, cudaStreamSynchronize(d->stream));
+    StepCounters c;
+    BBX_CUDA(d, cudaMemcpy(&c, d->ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    if (d->last_flow || d->last_per_contact || c.n_levels <= 0) return 0;
+    const int L = c.n_levels;
+    int* lc = (int*)malloc(sizeof(int) * (size_t)L * BBX_NCLS);
+    if (!lc) return BBX_ERR_BAD_ARGUMENT;
+    cudaError_t e = cudaMemcpy(lc, d->level_count, sizeof(int) * (size_t)L * BBX_NCLS, cudaMemcpyDeviceToHost);
+    int n = 0;
+    for (int k = 0; k < BBX_NCLS && e == cudaSuccess; k++) {
+        long long tot = 0;
+        for (int l = 0; l < L; l++) tot += lc[l * BBX_NCLS + k];
+        if (tot == 0) continue;
+        int4* nd = (int4*)malloc(sizeof(int4) * (size_t)tot);
+        if (!nd) { free(lc); return BBX_ERR_BAD_ARGUMENT; }
+        e = cudaMemcpy(nd, d->Nd_k[k], sizeof(int4) * (size_t)tot, cudaMemcpyDeviceToHost);
+        long long at = 0;
+        for (int l = 0; l < L && e == cudaSuccess; l++)
+            for (int i = 0; i < lc[l * BBX_NCLS + k]; i++, at++) {
+                if (n < cap_nodes) { out4[4 * n] = l; out4[4 * n + 1] = nd[at].y; out4[4 * n + 2] = nd[at].z; out4[4 * n + 3] = nd[at].w; }
+                n++;
+            }
+        free(nd);
+    }
+    free(lc);
+    BBX_CUDA(d, e);
+    return n;
+}
+

@@ -1192,6 +1192,13 @@ int BallboxDebugLevels(PhysicsWorld* w, int* counts8, unsigned long long* ns, in
     return batch_check_dev(p->batch, bbx_dev_debug_levels(p->batch->dev, counts8, ns, max_levels));
 }
 
+int BallboxDebugSchedule(PhysicsWorld* w, int* out4, int cap_nodes)
+{
+    BbxWorldPriv* p = priv_of(w);
+    if (!p || !p->batch->dev) return BBX_ERR_BAD_ARGUMENT;
+    return bbx_dev_debug_schedule(p->batch->dev, out4, cap_nodes);
+}
+
 int BallboxDebugDeferred(PhysicsWorld* w)
 {
     BbxWorldPriv* p = priv_of(w);

@@ -72,7 +72,7 @@ int  BallboxSdfInUse(PhysicsWorld* world);      /* BBX_SDF_* the next step will 
 /* ---- solver schedule ------------------------------------------------------- */
 #define BBX_SOLVER_EXACT     0 /* level-scheduled Gauss-Seidel: bit-identical to the
                                   reference's sequential sweep (default)                    */
-#define BBX_SOLVER_COLOURED  1 /* graph-coloured Gauss-Seidel: reorders the sweep          */
+#define BBX_SOLVER_COLOURED  1 /* graph-coloured Gauss-Seidel (greedy colours, ~max degree + 1 classes): reorders the sweep */
 #define BBX_SOLVER_EXACT_FLOW 2 /* the same exact schedule, barrier-free: every constraint waits
                                   only for its own two predecessors (versioned body records,
                                   iterations overlap); bit-identical results, experimental:
@@ -117,6 +117,10 @@ int  BallboxGetStageTiming(PhysicsWorld* world, float* out6, int* steps);
 int  BallboxGetReplayTiming(PhysicsWorld* world, float* ms, int* steps);      /* k_replay_staged alone (part of out6[4]); call after BallboxGetStageTiming */
 
 int  BallboxDebugLevels(PhysicsWorld* world, int* counts8, unsigned long long* ns, int max_levels);
+/* visiting order of the last solve (single world, level path): out4[4 i ..] = (level or colour, constraints of the node,
+   dynamic body A or -1, dynamic body B or -1); returns the number of nodes.  Tests use it to check that a level is an
+   independent set. */
+int  BallboxDebugSchedule(PhysicsWorld* world, int* out4, int cap_nodes);
 int  BallboxDebugDeferred(PhysicsWorld* world);   /* after BallboxGetStats: heavy terminal nodes the last step swept in its extra final level */
 int  BallboxDebugWarpTrace(PhysicsWorld* world, unsigned long long* out4, int n_warps);   /* BBX_TRACE_LEVEL=l+1: per warp of the staged replay in level l, iteration 1: start, data ready, end (ns), constraints<<16|chunks */
 

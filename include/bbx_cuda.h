@@ -145,6 +145,7 @@ int  bbx_dev_get_replay_timing(BbxDev* dev, float* ms, int* steps);
  * ns[l+1] = globaltimer at the end of level l of solver iteration 1 (ns[l+1]-ns[l] = level time, l >= 1) */
 int  bbx_dev_debug_levels(BbxDev* dev, int* counts, unsigned long long* ns, int max_levels);
 int  bbx_dev_debug_warp_trace(BbxDev* dev, unsigned long long* out, int n_warps);
+int  bbx_dev_debug_schedule(BbxDev* dev, int* out4, int cap_nodes);   /* nodes of the last level-path solve in visiting order */
 int  bbx_dev_debug_deferred(BbxDev* dev);        /* call after bbx_dev_stats */
 const char* bbx_dev_error(BbxDev* dev);          /* NULL when healthy */
 void bbx_dev_clear_error(BbxDev* dev);

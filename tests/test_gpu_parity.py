@@ -991,3 +991,91 @@ def test_both_cell_walks_find_the_same_pairs(product, truth, monkeypatch, mode):
         mm = parity.compare_worlds(views[i], w)
         assert not mm, f"world {i}: {mm[:3]}"
     d.DestroyPhysicsWorldBatch(batch)
+
+
+def _schedule(product, w, cap=2_000_000):
+    """(level, constraints, body A, body B) of every node of the last solve, in visiting order."""
+    import ctypes as C
+    buf = (C.c_int * (4 * cap))()
+    product.dll.BallboxDebugSchedule.argtypes = [bb.WP, C.POINTER(C.c_int), C.c_int]
+    n = product.dll.BallboxDebugSchedule(w.ptr, buf, cap)
+    assert 0 < n <= cap, n
+    return np.frombuffer(buf, dtype=np.int32)[:4 * n].reshape(n, 4).copy()
+
+
+def _assert_levels_are_independent_sets(sched):
+    """No dynamic body twice in one level / colour: the property that lets a level be swept without atomics."""
+    lv = np.concatenate([sched[:, 0], sched[:, 0]]).astype(np.int64)
+    body = np.concatenate([sched[:, 2], sched[:, 3]]).astype(np.int64)
+    keep = body >= 0
+    key = lv[keep] * (1 << 32) + body[keep]
+    assert len(np.unique(key)) == len(key)
+
+
+@pytest.mark.gpu
+def test_levels_of_the_exact_schedule_are_independent_sets(product):
+    w = product.build_scene(bb.SCENE_MIXED, 30000, 5)
+    w.set_sync_mode(bb.SYNC_RESIDENT)
+    w.step_n(DT, 150); w.synchronize()
+    st = w.stats()
+    s = _schedule(product, w)
+    assert s[:, 1].sum() == st.solver_contacts and s[:, 0].max() + 1 == st.levels
+    _assert_levels_are_independent_sets(s)
+
+
+@pytest.mark.gpu
+def test_coloured_schedule_replays_colour_major(product, truth, monkeypatch):
+    """BBX_SOLVER_COLOURED with the staged replay: iteration 0 sweeps the hash levels and takes greedy colours, iterations
+    1.. replay colour classes.  Far fewer classes than exact levels, every class an independent set, every constraint
+    scheduled exactly once, identical bits from two runs and from a different grid size; detection untouched."""
+    def run(blocks=None, steps=60):
+        if blocks: monkeypatch.setenv("BBX_SOLVE_BLOCKS", str(blocks))
+        else: monkeypatch.delenv("BBX_SOLVE_BLOCKS", raising=False)
+        w = product.build_scene(bb.SCENE_MIXED, 30000, 5)
+        w.set_sync_mode(bb.SYNC_RESIDENT)
+        w.step_n(DT, 150); w.synchronize()                      # settle with the exact schedule
+        exact_levels = w.stats().levels
+        product.dll.BallboxSetSolverSchedule(w.ptr, bb.SOLVER_COLOURED)
+        w.step_n(DT, steps); w.synchronize()
+        w.download(bb.DL_BODIES | bb.DL_CONSTRAINTS)
+        return w, exact_levels
+    a, exact_levels = run()
+    st = a.stats()
+    assert st.overflow == 0
+    assert 4 <= st.levels <= 24 and st.levels < exact_levels, (st.levels, exact_levels)
+    s = _schedule(product, a)
+    assert s[:, 1].sum() == st.solver_contacts and s[:, 0].max() + 1 == st.levels
+    _assert_levels_are_independent_sets(s)
+    b, _ = run()
+    assert a.state_hash() == b.state_hash()
+    c, _ = run(blocks=96)
+    assert a.state_hash() == c.state_hash()
+    # detection does not depend on the schedule: one coloured step from a state the checker shares
+    g = product.build_scene(bb.SCENE_MIXED, 4000, 9)
+    product.dll.BallboxSetSolverSchedule(g.ptr, bb.SOLVER_COLOURED)
+    t = truth.build_scene(bb.SCENE_MIXED, 4000, 9)
+    g.step(DT); t.step(DT, pruned=True)
+    kg, kt = g.constraints(), t.constraints()
+    for f in ("a_type", "a_index", "b_type", "b_index", "point", "normal", "penetration", "normal_mass", "position_bias"):
+        assert parity.first_mismatch(kg[f], kt[f]) is None, f
+
+
+@pytest.mark.gpu
+def test_coloured_schedule_falls_back_when_colours_run_out(product, monkeypatch):
+    """More than 64 colours cannot be represented: the step then replays the hash levels (identity re-bucketing).  Forced
+    here by BBX_COLOUR_LIMIT; the result must equal the coloured schedule with the in-kernel replay (BBX_REPLAY=0),
+    which sweeps the same hash levels in every iteration."""
+    def run(env):
+        for k in ("BBX_COLOUR_LIMIT", "BBX_REPLAY"): monkeypatch.delenv(k, raising=False)
+        for k, v in env.items(): monkeypatch.setenv(k, v)
+        w = product.build_scene(bb.SCENE_MIXED, 6000, 11)
+        product.dll.BallboxSetSolverSchedule(w.ptr, bb.SOLVER_COLOURED)
+        w.set_sync_mode(bb.SYNC_RESIDENT)
+        w.step_n(DT, 80); w.synchronize()
+        w.download(bb.DL_BODIES | bb.DL_CONSTRAINTS)
+        return w
+    a = run({"BBX_COLOUR_LIMIT": "3", "BBX_REPLAY": "2"})
+    b = run({"BBX_REPLAY": "0"})
+    assert a.stats().contacts > 5000
+    assert a.state_hash() == b.state_hash()
+    assert not parity.compare_worlds(a, b, constraints=True)

@@ -1,5 +1,5 @@
 """Drift of the coloured (reordered) solver schedule against the exact schedule, on the GPU.
-Usage: python tools/drift_report.py [bodies] -> markdown on stdout (profiles/r01_drift.md)."""
+Usage: python tools/drift_report.py [bodies] -> markdown on stdout (profiles/r02_drift.md; round 1: r01_drift.md)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -43,6 +43,12 @@ for target in (1, 10, 100, 1000):
     dp = np.linalg.norm(pos[0].astype(np.float64) - pos[1], axis=1); dv = np.linalg.norm(vel[0].astype(np.float64) - vel[1], axis=1)
     print(f"| {target} | {e.stats().levels} | {c.stats().levels} | {dp.mean():.3e} | {np.percentile(dp, 99):.3e} | {dp.max():.3e} | "
           f"{dv.mean():.3e} | {np.percentile(dv, 99):.3e} | {dv.max():.3e} |")
+# aggregate state after the last target: the pile is chaotic (bodies end elsewhere) but statistically the same
+for name, w in (("exact", e), ("coloured", c)):
+    sn = w.snapshot()
+    v = np.concatenate([sn["s_vel"], sn["b_vel"]]).astype(np.float64); y = np.concatenate([sn["s_pos"], sn["b_pos"]])[:, 1].astype(np.float64)
+    print(f"\n{name} after {done} steps: contacts {w.stats().contacts}, mean speed {np.linalg.norm(v, axis=1).mean():.4e} m/s, "
+          f"mean height {y.mean():.4f} m, sleeping {int(sn['s_sleeping'].sum() + sn['b_sleeping'].sum()) if 's_sleeping' in sn else -1}")
 # timing of both schedules on this scene
 for name, w in (("exact", e), ("coloured", c)):
     w.set_stage_timing(True); w.stage_timing(); w.step_n(DT, 20); t, k = w.stage_timing()

@@ -13,6 +13,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--scene", type=int, default=bb.SCENE_MIXED)
 ap.add_argument("--friction", type=float, default=None, help="override friction for the timed steps (timing experiment)")
 ap.add_argument("--iterations", type=int, default=None)
+ap.add_argument("--coloured", action="store_true", help="timed steps with BBX_SOLVER_COLOURED (settled with the exact schedule)")
 a = ap.parse_args()
 lib = bbx.load()
 w = lib.build_scene(a.scene, a.bodies, 20261019)
@@ -27,6 +28,9 @@ print(f"settled {a.settle} steps in {time.time()-t0:.1f}s: contacts={st.contacts
       f"levels={st.levels} pairs={st.candidate_pairs} sb={st.reserved[0]} bb={st.reserved[1]} ovf={st.overflow}", flush=True)
 if a.friction is not None: w.w.settings.friction = a.friction
 if a.iterations is not None: w.w.settings.solver_iterations = a.iterations
+if a.coloured:
+    lib.dll.BallboxSetSolverSchedule(w.ptr, bb.SOLVER_COLOURED)
+    w.step_n(1 / 60, 3); w.synchronize()          # (first coloured step allocates the second buffer set)
 w.set_stage_timing(True); w.stage_timing()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
