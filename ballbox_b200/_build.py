@@ -19,7 +19,7 @@ BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libballbox_b200.so")
 
 CUDA_SOURCES = ["bbx_state.cu", "bbx_integrate.cu", "bbx_broadphase.cu", "bbx_narrowphase.cu",
-                "bbx_solver.cu", "bbx_solver_flow.cu", "bbx_replay.cu", "bbx_colour.cu", "bbx_step.cu", "bbx_sort.cu", "bbx_queries.cu"]
+                "bbx_solver.cu", "bbx_solver_flow.cu", "bbx_replay.cu", "bbx_colour.cu", "bbx_joints.cu", "bbx_step.cu", "bbx_sort.cu", "bbx_queries.cu"]
 HOST_SOURCES = ["ballbox_host.c", "bbx_scenes.c"]
 
 # -fmad=false: no FMA contraction, results must match the reference bit for bit

@@ -154,6 +154,13 @@ class BallboxLib:
         d.CreatePhysicsWorld.argtypes = [C.c_int, C.c_int, C.c_int]
         if hasattr(d, "OracleSetWarmStarting"):          # the C restatement's definition of the warm-start extension
             d.OracleSetWarmStarting.argtypes = [WP, C.c_float]; d.OracleSetWarmStarting.restype = None
+        if hasattr(d, "BallboxAddBallJoint"):            # joints extension (include/ballbox_ext.h; sequential definition in oracle/)
+            d.BallboxAddSpring.argtypes = [WP, C.c_int, C.c_int, C.c_int, C.c_int, Vec3, Vec3, C.c_float, C.c_float, C.c_float]
+            d.BallboxAddBallJoint.argtypes = [WP, C.c_int, C.c_int, C.c_int, C.c_int, Vec3]
+            d.BallboxAddHingeJoint.argtypes = [WP, C.c_int, C.c_int, C.c_int, C.c_int, Vec3, Vec3, C.c_float]
+            d.BallboxAddDistanceJoint.argtypes = [WP, C.c_int, C.c_int, C.c_int, C.c_int, Vec3, Vec3]
+            d.BallboxJointCount.argtypes = [WP]; d.BallboxSpringCount.argtypes = [WP]
+            d.BallboxClearJoints.argtypes = [WP]; d.BallboxClearJoints.restype = None
         d.DestroyPhysicsWorld.argtypes = [WP]
         d.DestroyPhysicsWorld.restype = None
         d.PhysicsStep.argtypes = [WP, C.c_float]
@@ -333,6 +340,30 @@ class World:
 
     def use_sdf(self, sdf_id):
         self.lib.dll.BbxSceneUseSdf(self.ptr, sdf_id)
+
+    # joints extension: a body is (type, index) with type 0 sphere, 1 box, -1 the world -----------------------------
+    def add_spring(self, a, b, anchor_a, anchor_b, rest, stiffness, damping=0.0):
+        r = self.lib.dll.BallboxAddSpring(self.ptr, a[0], a[1], b[0], b[1], Vec3(*anchor_a), Vec3(*anchor_b), rest, stiffness, damping)
+        if r < 0: raise BallboxError("BallboxAddSpring failed")
+        return r
+
+    def add_ball_joint(self, a, b, anchor):
+        r = self.lib.dll.BallboxAddBallJoint(self.ptr, a[0], a[1], b[0], b[1], Vec3(*anchor))
+        if r < 0: raise BallboxError("BallboxAddBallJoint failed")
+        return r
+
+    def add_distance_joint(self, a, b, anchor_a, anchor_b):
+        r = self.lib.dll.BallboxAddDistanceJoint(self.ptr, a[0], a[1], b[0], b[1], Vec3(*anchor_a), Vec3(*anchor_b))
+        if r < 0: raise BallboxError("BallboxAddDistanceJoint failed")
+        return r
+
+    def clear_joints(self):
+        self.lib.dll.BallboxClearJoints(self.ptr)
+
+    def add_hinge_joint(self, a, b, anchor, axis, half_span=0.25):
+        r = self.lib.dll.BallboxAddHingeJoint(self.ptr, a[0], a[1], b[0], b[1], Vec3(*anchor), Vec3(*axis), half_span)
+        if r < 0: raise BallboxError("BallboxAddHingeJoint failed")
+        return r
 
     # stepping -----------------------------------------------------------------
     def check(self):

@@ -198,6 +198,21 @@ struct BbxDev {
     // baked SDF (host function sampled on a grid, bbx_dev_set_baked_sdf)
     float *sdf_grid; int sdf_ch; int sdf_nx, sdf_ny, sdf_nz; float sdf_ox, sdf_oy, sdf_oz, sdf_inv_cell;
 
+    // joints and springs (extension, bbx_joints.cu).  Joints are stored in SCHEDULE order: the joints of one connected
+    // component of the joint graph belong to one block, sorted by dependency level inside it
+    int n_joints, n_jblocks, n_jlevels_max;
+    int *j_blk_off;              // [n_jblocks + 1] range of this block's entries in j_lev_off
+    int *j_lev_off;              // ranges of schedule positions, one per (block, level), + 1
+    int4 *j_ids;                 // (gid A, gid B or -1, kind, -)
+    float4 *j_local;             // 2 per joint: (anchor in A's frame, rest) (anchor in B's frame, -)
+    float4 *j_rec;               // 5 per joint, written by k_joint_presolve: (rA, m0) (rB, m1) (bias xyz, m2) (imp xyz, -) (rod direction, -)
+    int n_springs, n_spring_bodies;
+    int *sp_body;                // [n_spring_bodies] body slots with at least one spring end
+    int *sp_off;                 // [n_spring_bodies + 1] range in sp_list
+    int *sp_list;                // spring index << 1 | end (0 = A, 1 = B), creation order per body
+    int2 *sp_ids;                // (gid A, gid B or -1)
+    float4 *sp_def;              // 3 per spring: (anchor A, rest) (anchor B, k) (c, -, -, -)
+
     StepCounters *ctr;           // device
     StepCounters *ctr_host;      // pinned host copy
     unsigned long long *sort_keys;   // export: 64-bit reference-order keys
@@ -265,6 +280,10 @@ int bbx_stage_integrate_positions(BbxDev* d, const BbxStepParams* p);
 int bbx_stage_collect_events(BbxDev* d, const BbxStepParams* p);
 int bbx_warm_ensure(BbxDev* d);
 int bbx_stage_warm_save(BbxDev* d, const BbxStepParams* p);
+int bbx_springs_apply(BbxDev* d);                                       // bbx_joints.cu
+int bbx_joints_presolve(BbxDev* d, const BbxStepParams* p, int wake);
+int bbx_joints_sweep(BbxDev* d);
+void bbx_joints_free(BbxDev* d);
 int bbx_scan_exclusive(BbxDev* d, const int* in, int* out, int* out2, int n_max, const int* n_dev, int* total_out);
 
 #ifdef __CUDACC__

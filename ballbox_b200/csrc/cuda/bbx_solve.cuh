@@ -13,6 +13,13 @@ __device__ __forceinline__ void tangents_of(float3 n, float3& t1, float3& t2)   
     t2 = v3cross(n, t1);
 }
 
+// sum of the inverse masses seen along `dir` at the two lever arms (:1321-1326); the effective mass is its inverse
+__device__ __forceinline__ float inv_mass_sum(float imA, float imB, float3 rA, float3 rB, float3 iA, float3 iB, float3 dir)
+{
+    float3 ra = v3cross(rA, dir), rb = v3cross(rB, dir);
+    return imA + imB + v3dot(ra, v3mul(ra, iA)) + v3dot(rb, v3mul(rb, iB));             // :1323-1325
+}
+
 struct SolveParams { float restitution, friction, vel_threshold; int iterations; int gather; int first_only; };
 
 struct BodyState {

@@ -38,11 +38,7 @@ namespace cg = cooperative_groups;
 // K9 presolve: contact -> 64-byte solver record (contact order); node heads also
 // get their graph fields
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float inv_mass_sum(float imA, float imB, float3 rA, float3 rB, float3 iA, float3 iB, float3 dir)
-{
-    float3 ra = v3cross(rA, dir), rb = v3cross(rB, dir);
-    return imA + imB + v3dot(ra, v3mul(ra, iA)) + v3dot(rb, v3mul(rb, iB));             // :1323-1325
-}
+// (inv_mass_sum: bbx_solve.cuh)
 
 // mode 0: PhysicsStep (everything computed, impulses zeroed)            -- :1176-1211 + :1295-1356
 // mode 1: PreSolveConstraints on an imported list (impulses kept)         -- :1295-1356
@@ -866,6 +862,10 @@ int bbx_warm_ensure(BbxDev* d)
     return 0;
 }
 
+// steps with joints replay one iteration per launch of k_replay_staged, whose tables hold RS_MAXLEV levels: a deeper
+// contact graph cannot be replayed that way and is reported (overflow bit 16) instead of being skipped silently
+__global__ void k_joint_guard(BbxDev dv) { if (dv.ctr->replay_done) atomicOr(&dv.ctr->overflow, 16); }
+
 // touched-body statistics and sanity for the host
 int bbx_stage_solve(BbxDev* d, const BbxStepParams* p) { return bbx_stage_solve_ex(d, p, 0, p->settings.solver_iterations, 0); }
 
@@ -874,9 +874,13 @@ int bbx_stage_solve(BbxDev* d, const BbxStepParams* p) { return bbx_stage_solve_
 int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int iterations, int imported)
 {
     const int G = BBX_NUM_SMS * 8;
+    // joints (extension, bbx_joints.cu): their rows are swept after the contacts in EVERY iteration, so a step with joints
+    // runs the exact level schedule one iteration per launch with a joint sweep after each (PhysicsStep paths only)
+    const int nj = (!imported && presolve_mode == 0) ? d->n_joints : 0;
+    const int schedule = nj ? BBX_SOLVER_EXACT : p->solver_schedule;
     // opt-in (BBX_SOLVER_EXACT_FLOW or BBX_SOLVER_FLOW=1): barrier-free flow solver, every constraint its own node
-    const int flow = (p->solver_schedule == BBX_SOLVER_EXACT_FLOW || (d->force_flow && p->solver_schedule == BBX_SOLVER_EXACT)) ? 1 : 0;
-    const int groups = (!flow && use_world_groups(d, imported, p->solver_schedule)) ? 1 : 0;
+    const int flow = (!nj && (schedule == BBX_SOLVER_EXACT_FLOW || (d->force_flow && schedule == BBX_SOLVER_EXACT))) ? 1 : 0;
+    const int groups = (!nj && !flow && use_world_groups(d, imported, schedule)) ? 1 : 0;
     const int per_contact = flow | groups;                 // every constraint is its own node
     BBX_CUDA(d, cudaMemsetAsync(d->deg, 0, sizeof(int) * ((size_t)d->N + 1), d->stream));
     const float warm = (presolve_mode == 0 && !imported && p->warm_start > 0.0f) ? p->warm_start : 0.0f;
@@ -885,10 +889,11 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     const int levels_path = (!flow && !groups) ? 1 : 0;
     BBX_LAUNCH(d, k_body_records, bbx_blocks(d->N, 256), 256, 0, *d);
     BBX_LAUNCH(d, k_presolve, G, 256, 0, *d, p->settings.baumgarte_bias, p->settings.allowed_penetration, p->dt, presolve_mode, per_contact, warm, (levels_path && iterations > 0) ? 1 : 0);
+    if (nj) { int rcj = bbx_joints_presolve(d, p, iterations > 0 ? 1 : 0); if (rcj) return rcj; }
     if (iterations <= 0) { bbx_timing_mark(d, 4); BBX_CUDA(d, cudaGetLastError()); return 0; }    // :1223 loop does not run
     int rc = bbx_scan_exclusive(d, d->deg, d->adj_start, d->adj_cursor, d->N + 1, NULL, NULL);
     if (rc) return rc;
-    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (p->solver_schedule == BBX_SOLVER_COLOURED ? 1 : 0), per_contact);
+    BBX_LAUNCH(d, k_adj_fill, G, 256, 0, *d, imported ? 2 : (schedule == BBX_SOLVER_COLOURED ? 1 : 0), per_contact);
     if (levels_path) BBX_CUDA(d, cudaMemsetAsync(d->level_count, 0, 2 * BBX_NCLS * sizeof(int), d->stream));
     BBX_LAUNCH(d, k_adj_link, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, warm > 0.0f ? 1 : 0, levels_path);
     if (warm > 0.0f) BBX_LAUNCH(d, k_warm_apply, bbx_blocks(d->N, 128), 128, 0, *d, per_contact, flow, p->settings.friction);
@@ -925,8 +930,9 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     // iteration 0 (level discovery fused with the first sweep) in k_solve_levels; iterations 1..I-1 replay the recorded
     // level-major order in k_replay_staged (BBX_REPLAY=0: inside k_solve_levels, the round-1 replay loop)
     sp.first_only = (iterations > 1 && d->replay_mode != 0) ? d->replay_mode : 0;
+    if (nj) { sp.iterations = 1; sp.first_only = 2; }       // iteration 0 only; the later ones are single-iteration replays below
     // coloured schedule: colours are taken during iteration 0 and the replay runs colour-major (bbx_colour.cu)
-    const int colour = (p->solver_schedule == BBX_SOLVER_COLOURED && !imported && sp.first_only) ? 1 : 0;
+    const int colour = (schedule == BBX_SOLVER_COLOURED && !imported && sp.first_only) ? 1 : 0;
     if (colour) {
         int rcc = bbx_colour_ensure(d); if (rcc) return rcc;
         BBX_CUDA(d, cudaMemsetAsync(d->col_used, 0, sizeof(unsigned long long) * (size_t)d->N, d->stream));
@@ -952,6 +958,18 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
     BBX_CUDA(d, cudaLaunchCooperativeKernel(kernel, dim3(*coop_blocks), dim3(SOLVE_THREADS), args, 0, d->stream));
     d->launches++;
     BBX_CUDA(d, cudaGetLastError());
+    if (nj) {
+        // contacts of iteration it, then the joint rows of iteration it (oracle/bbx_oracle.c stage_solve)
+        if (iterations > 1) BBX_LAUNCH(d, k_joint_guard, 1, 1, 0, *d);
+        int rcj = bbx_joints_sweep(d);
+        SolveParams one = sp;
+        one.iterations = 2; one.gather = 0;                  // k_replay_staged runs iterations 1 .. I-1: exactly one sweep
+        for (int it = 1; it < iterations && !rcj; it++) {
+            rcj = bbx_replay_staged(d, one);
+            if (!rcj) rcj = bbx_joints_sweep(d);
+        }
+        return rcj;
+    }
     if (colour) { int rcc = bbx_colour_rebucket(d); if (rcc) return rcc; }
     if (sp.first_only) {
         if (d->timing_on && d->timing_steps < d->timing_cap) { bbx_timing_mark(d, 7); d->timing_has7[d->timing_steps] = 1; }

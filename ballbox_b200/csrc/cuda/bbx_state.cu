@@ -157,6 +157,7 @@ extern "C" void bbx_dev_destroy(BbxDev* d)
         d->sdf_grid, d->slot_of, d->link, d->level_count, d->flow, d->fq, d->fnd, d->fimp, d->level_ns, d->M, d->ctr, d->snap_pos, d->snap_vel, d->snap_boxq, d->snap_timer, d->snap_flags, d->reset_ids, d->wake_ids, d->ev_key, d->ev_step, d->ev_contact, d->sort_keys, d->export_buf, d->export_sorted, d->sort_keys_b, d->sort_vals_a, d->sort_vals_b,
         d->sort_hist, d->sort_hist_scan, d->warm_key, d->warm_val, d->warm_epoch, d->M2, d->level_count2, d->col_used, d->col_tab };
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
+    bbx_joints_free(d);
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue_k[k]) cudaFree(d->queue_k[k]); if (d->Nd_k[k]) cudaFree(d->Nd_k[k]); }
     for (int k = 0; k < BBX_NCLS; k++) { if (d->queue2_k[k]) cudaFree(d->queue2_k[k]); if (d->Nd2_k[k]) cudaFree(d->Nd2_k[k]); if (d->colq_k[k]) cudaFree(d->colq_k[k]); }
     if (d->ctr_host) cudaFreeHost(d->ctr_host);

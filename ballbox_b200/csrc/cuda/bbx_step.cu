@@ -94,6 +94,10 @@ extern "C" int bbx_dev_step(BbxDev* d, const BbxStepParams* p, int steps)
         int rc;
         if (nvtx_on) nvtxRangePushA("bbx:integrate_velocities");
         bbx_timing_mark(d, 0);
+        if (d->n_springs > 0) {                                        // extension: spring forces join the accumulators before gravity
+            if ((rc = bbx_springs_apply(d))) return rc;
+            q.has_forces = 1;
+        }
         if ((rc = bbx_stage_integrate_velocities(d, &q))) return rc;   // stages 1-2
         bbx_timing_mark(d, 1);
         BBX_RANGE("bbx:broadphase");

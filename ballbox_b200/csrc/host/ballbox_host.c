@@ -50,6 +50,10 @@ struct PhysicsWorldBatch {
     int dev_ahead;                      /* device steps ran since the host arrays were last in sync (upload or body download) */
     int *wake_ids; int n_wake, cap_wake;    /* bodies woken by Add*Force/Torque while the state is resident (:420-423) */
     CollisionContact* ev_contacts; int *ev_steps, *ev_worlds; int ev_cap;
+    /* joints and springs (extension, ballbox_ext.h): creation order, body slots of bbx_cuda.h */
+    BbxJointDef* joints; int n_joints, cap_joints;
+    BbxSpringDef* springs; int n_springs, cap_springs;
+    int joints_dirty;                   /* the device lists are out of date */
     int has_err; char err[256];
 };
 
@@ -185,6 +189,7 @@ static void settings_defaults(PhysicsSettings* s)          /* values: reference 
 
 static void batch_free(struct PhysicsWorldBatch* b)
 {
+    free(b->joints); free(b->springs);
     if (!b) return;
     if (b->dev) bbx_dev_destroy(b->dev);
     void* arrs[] = { b->hb.s_pos, b->hb.s_radius, b->hb.s_vel, b->hb.s_force, b->hb.s_mass, b->hb.s_angvel,
@@ -876,6 +881,7 @@ static int replay_events(struct PhysicsWorldBatch* b)
     return rc;
 }
 
+static int sync_joints(struct PhysicsWorldBatch* b);
 static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
 {
     if (b->has_err) return BBX_ERR_STICKY;
@@ -883,6 +889,10 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
     if (steps <= 0) return 0;
     int rc;
     for (int w = 0; w < b->n_worlds; w++) b->worlds[w].pub.dt = dt;
+    if (b->joints_dirty) {
+        if ((rc = batch_ensure_dev(b))) return rc;
+        if ((rc = sync_joints(b))) return rc;
+    }
     if (b->sync_mode == BBX_SYNC_COMPAT || b->sync_mode == BBX_SYNC_COMPAT_BODIES) {
         /* drop-in semantics: whatever the user wrote into the host arrays is what the step sees.
          * COMPAT_BODIES leaves the constraint list on the device (it is 6x the size of the body state at
@@ -954,6 +964,128 @@ static int batch_step(struct PhysicsWorldBatch* b, float dt, int steps)
         if (!rc) rc = rc2;
         zero_host_forces(b);
     }
+    return rc;
+}
+
+/* ------------------------------------------------------------------------- */
+/* joints and springs (extension; sequential definition: oracle/bbx_oracle.c) */
+/* ------------------------------------------------------------------------- */
+static int joint_body_slot(BbxWorldPriv* p, int type, int index, int world_allowed, int* slot)
+{
+    struct PhysicsWorldBatch* b = p->batch;
+    if (type == -1) { *slot = -1; return world_allowed; }
+    if (type == 0 && index >= 0 && index < p->spheres.count) { *slot = p->index * b->cap_s + index; return 1; }
+    if (type == 1 && index >= 0 && index < p->boxes.count) { *slot = b->n_worlds * b->cap_s + p->index * b->cap_b + index; return 1; }
+    return 0;
+}
+/* world point -> body frame: boxes rotate, a sphere is attached at its centre (SphereSystem has no rotations), the world is fixed */
+static Vec3 joint_to_local(BbxWorldPriv* p, int type, int index, Vec3 pt)
+{
+    if (type == 0) return V0;
+    if (type == 1) return QuatRotateVec3(QuatConjugate(p->boxes.rotations[index]), Vec3Sub(pt, p->boxes.positions[index]));
+    return pt;
+}
+static Vec3 joint_to_world(BbxWorldPriv* p, int type, int index, Vec3 l)
+{
+    if (type == 0) return Vec3Add(p->spheres.positions[index], l);
+    if (type == 1) return Vec3Add(p->boxes.positions[index], QuatRotateVec3(p->boxes.rotations[index], l));
+    return l;
+}
+static int slot_world(struct PhysicsWorldBatch* b, int slot)
+{
+    const int NS = b->n_worlds * b->cap_s;
+    return slot < NS ? slot / (b->cap_s > 0 ? b->cap_s : 1) : (slot - NS) / (b->cap_b > 0 ? b->cap_b : 1);
+}
+static int joint_add(PhysicsWorld* world, int kind, int ta, int ia, int tb, int ib, Vec3 anchorA, Vec3 anchorB)
+{
+    BbxWorldPriv* p = priv_of(world);
+    int ga, gb;
+    if (!p || !joint_body_slot(p, ta, ia, 0, &ga) || !joint_body_slot(p, tb, ib, 1, &gb)) return -1;
+    struct PhysicsWorldBatch* b = p->batch;
+    host_edit_begin(world);             /* anchors are taken from the CURRENT positions: a resident world is downloaded first */
+    if (b->n_joints == b->cap_joints) {
+        int cap = b->cap_joints ? 2 * b->cap_joints : 16;
+        BbxJointDef* q = (BbxJointDef*)realloc(b->joints, sizeof(BbxJointDef) * (size_t)cap);
+        if (!q) return -1;
+        b->joints = q; b->cap_joints = cap;
+    }
+    BbxJointDef* j = &b->joints[b->n_joints];
+    Vec3 la = joint_to_local(p, ta, ia, anchorA), lb = joint_to_local(p, tb, ib, anchorB);
+    j->kind = kind; j->ga = ga; j->gb = gb;
+    j->la[0] = la.x; j->la[1] = la.y; j->la[2] = la.z; j->lb[0] = lb.x; j->lb[1] = lb.y; j->lb[2] = lb.z;
+    j->rest = Vec3Length(Vec3Sub(joint_to_world(p, tb, ib, lb), joint_to_world(p, ta, ia, la)));
+    b->joints_dirty = 1;
+    int id = 0;                                         /* index among this world's joints, like a single world's creation order */
+    for (int k = 0; k < b->n_joints; k++) if (slot_world(b, b->joints[k].ga) == p->index) id++;
+    b->n_joints++;
+    return id;
+}
+int BallboxAddBallJoint(PhysicsWorld* world, int ta, int ia, int tb, int ib, Vec3 anchor) { return joint_add(world, BBX_JOINT_BALL, ta, ia, tb, ib, anchor, anchor); }
+int BallboxAddDistanceJoint(PhysicsWorld* world, int ta, int ia, int tb, int ib, Vec3 anchorA, Vec3 anchorB) { return joint_add(world, BBX_JOINT_ROD, ta, ia, tb, ib, anchorA, anchorB); }
+int BallboxAddHingeJoint(PhysicsWorld* world, int ta, int ia, int tb, int ib, Vec3 anchor, Vec3 axis, float half_span)
+{
+    Vec3 d = Vec3Scale(Vec3Normalize(axis), half_span);
+    int first = BallboxAddBallJoint(world, ta, ia, tb, ib, Vec3Sub(anchor, d));
+    if (first < 0) return -1;
+    return BallboxAddBallJoint(world, ta, ia, tb, ib, Vec3Add(anchor, d)) < 0 ? -1 : first;
+}
+int BallboxAddSpring(PhysicsWorld* world, int ta, int ia, int tb, int ib, Vec3 anchorA, Vec3 anchorB, float rest, float k, float c)
+{
+    BbxWorldPriv* p = priv_of(world);
+    int ga, gb;
+    if (!p || !joint_body_slot(p, ta, ia, 0, &ga) || !joint_body_slot(p, tb, ib, 1, &gb)) return -1;
+    struct PhysicsWorldBatch* b = p->batch;
+    host_edit_begin(world);
+    if (b->n_springs == b->cap_springs) {
+        int cap = b->cap_springs ? 2 * b->cap_springs : 16;
+        BbxSpringDef* q = (BbxSpringDef*)realloc(b->springs, sizeof(BbxSpringDef) * (size_t)cap);
+        if (!q) return -1;
+        b->springs = q; b->cap_springs = cap;
+    }
+    BbxSpringDef* sp = &b->springs[b->n_springs];
+    Vec3 la = joint_to_local(p, ta, ia, anchorA), lb = joint_to_local(p, tb, ib, anchorB);
+    sp->ga = ga; sp->gb = gb; sp->rest = rest; sp->k = k; sp->c = c;
+    sp->la[0] = la.x; sp->la[1] = la.y; sp->la[2] = la.z; sp->lb[0] = lb.x; sp->lb[1] = lb.y; sp->lb[2] = lb.z;
+    b->joints_dirty = 1;
+    int id = 0;
+    for (int k2 = 0; k2 < b->n_springs; k2++) if (slot_world(b, b->springs[k2].ga) == p->index) id++;
+    b->n_springs++;
+    return id;
+}
+int BallboxJointCount(PhysicsWorld* world)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return 0;
+    int n = 0;
+    for (int k = 0; k < p->batch->n_joints; k++) if (slot_world(p->batch, p->batch->joints[k].ga) == p->index) n++;
+    return n;
+}
+int BallboxSpringCount(PhysicsWorld* world)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return 0;
+    int n = 0;
+    for (int k = 0; k < p->batch->n_springs; k++) if (slot_world(p->batch, p->batch->springs[k].ga) == p->index) n++;
+    return n;
+}
+void BallboxClearJoints(PhysicsWorld* world)
+{
+    BbxWorldPriv* p = priv_of(world);
+    if (!p) return;
+    struct PhysicsWorldBatch* b = p->batch;
+    int n = 0;
+    for (int k = 0; k < b->n_joints; k++) if (slot_world(b, b->joints[k].ga) != p->index) b->joints[n++] = b->joints[k];
+    b->n_joints = n;
+    n = 0;
+    for (int k = 0; k < b->n_springs; k++) if (slot_world(b, b->springs[k].ga) != p->index) b->springs[n++] = b->springs[k];
+    b->n_springs = n;
+    b->joints_dirty = 1;
+}
+static int sync_joints(struct PhysicsWorldBatch* b)
+{
+    int rc = batch_check_dev(b, bbx_dev_set_joints(b->dev, b->joints, b->n_joints));
+    if (!rc) rc = batch_check_dev(b, bbx_dev_set_springs(b->dev, b->springs, b->n_springs));
+    if (!rc) b->joints_dirty = 0;
     return rc;
 }
 

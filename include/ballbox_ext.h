@@ -92,6 +92,34 @@ void BallboxSetSolverSchedule(PhysicsWorld* world, int schedule);
  * stage functions ignore it.  A world reset (BatchResetWorlds) forgets that world's impulses. */
 void BallboxSetWarmStarting(PhysicsWorld* world, float factor);
 
+/* ---- joints and springs (NOT in the reference: its README lists "constraints, like hinges, springs" as planned,
+ * README.md:25).  A body is (type, index): type 0 = sphere, 1 = box, -1 = the world (a fixed point; end B only).
+ * Anchors are given in world coordinates at the time of the call and stored in the body's frame.  A sphere has no
+ * orientation in this engine (SphereSystem has no rotations), so a sphere is always attached at its CENTRE: the
+ * anchor given for a sphere end is replaced by the centre.  All calls return the index of the new element among the
+ * world's joints / springs, or -1.
+ *   spring          force k (len - rest) + c (relative anchor velocity along the line), added to the force / torque
+ *                   accumulators of both bodies in creation order BEFORE gravity (ApplyForces); wakes dynamic ends
+ *   ball joint      three bilateral velocity rows (world x, y, z) that hold the two anchor points together
+ *   distance joint  one bilateral row along the line between the anchors that keeps the distance they had when the
+ *                   joint was created (a rigid rod; with a sphere end this is the pendulum)
+ *   hinge           two ball joints at anchor -+ half_span * axis (returns the index of the first)
+ * Joint rows are presolved after the contacts (bias = -baumgarte_bias / dt * position error) and swept after the contacts
+ * in every solver iteration, joints in creation order; they use ApplyConstraintImpulse, so jointed dynamic bodies stay
+ * awake.  The sequential definition is restated in oracle/bbx_oracle.c and the GPU path is bit-identical to it.  A
+ * world with joints always runs the exact level schedule (no coloured / flow / group solver), and its contact graph may
+ * be at most 256 levels deep (a deeper one is reported as an overflow error).  PhysicsStep / PhysicsStepN /
+ * PhysicsStepBatch only; the public stage functions ignore joints and springs.  In a RESIDENT world the call first
+ * downloads the bodies so that anchors refer to the current positions. */
+int  BallboxAddSpring(PhysicsWorld* world, int typeA, int indexA, int typeB, int indexB, Vec3 anchorA, Vec3 anchorB,
+                      float rest_length, float stiffness, float damping);
+int  BallboxAddBallJoint(PhysicsWorld* world, int typeA, int indexA, int typeB, int indexB, Vec3 anchor);
+int  BallboxAddDistanceJoint(PhysicsWorld* world, int typeA, int indexA, int typeB, int indexB, Vec3 anchorA, Vec3 anchorB);
+int  BallboxAddHingeJoint(PhysicsWorld* world, int typeA, int indexA, int typeB, int indexB, Vec3 anchor, Vec3 axis, float half_span);
+int  BallboxJointCount(PhysicsWorld* world);
+int  BallboxSpringCount(PhysicsWorld* world);
+void BallboxClearJoints(PhysicsWorld* world);          /* removes the world's joints AND springs */
+
 /* ---- statistics of the most recent step (and totals since creation) -------- */
 typedef struct {
     long long steps;               /* device steps executed                                 */

@@ -173,6 +173,18 @@ int  bbx_dev_add_wrench(BbxDev* dev, const float* d_sphere_force, const float* d
 int  bbx_dev_snapshot(BbxDev* dev);
 int  bbx_dev_restore_worlds(BbxDev* dev, const int* world_ids, int n);
 
+/* ---- joints and springs (extension, ballbox_ext.h BallboxAddSpring / BallboxAdd*Joint; sequential definition:
+ * oracle/bbx_oracle.c).  Bodies are global slots: sphere (w,i) = w*cap_s + i, box (w,i) = n_worlds*cap_s + w*cap_b + i,
+ * -1 = the world (end B only).  Anchors are in the body frame (spheres: the centre, 0; the world: the point itself).
+ * A call replaces the whole list; lists are in creation order, which is the order the sequential definition sweeps
+ * joints and accumulates spring forces in. */
+#define BBX_JOINT_BALL 0   /* three rows (world x, y, z) holding the two anchor points together */
+#define BBX_JOINT_ROD  1   /* one row along the line between the anchor points keeping their distance at `rest` */
+typedef struct { int kind, ga, gb; float la[3], lb[3]; float rest; } BbxJointDef;
+typedef struct { int ga, gb; float la[3], lb[3]; float rest, k, c; } BbxSpringDef;
+int  bbx_dev_set_joints(BbxDev* dev, const BbxJointDef* joints, int n);
+int  bbx_dev_set_springs(BbxDev* dev, const BbxSpringDef* springs, int n);
+
 /* pinned host memory for the public arrays (falls back to calloc without a device) */
 void* bbx_host_alloc(size_t bytes, int* pinned);
 void  bbx_host_free(void* p, int pinned);

@@ -110,10 +110,12 @@ PhysicsWorld* CreatePhysicsWorld(int ms, int mb, int mc)
     return w;
 }
 static void warm_forget(PhysicsWorld* w);
+static void joints_forget(PhysicsWorld* w);
 void DestroyPhysicsWorld(PhysicsWorld* w)
 {
     if (!w) return;
     warm_forget(w);
+    joints_forget(w);
     SphereSystem* s = w->spheres; BoxSystem* b = w->boxes;
     free(s->positions); free(s->radii); free(s->velocities); free(s->forces); free(s->masses); free(s->angular_velocities);
     free(s->torques); free(s->inertias); free(s->is_static); free(s->is_sleeping); free(s->sleep_timers); free(s->collision_callbacks); free(s);
@@ -177,6 +179,124 @@ void AddBoxForce(PhysicsWorld* w, int i, Vec3 f) { if (!w || i < 0 || i >= w->bo
 void AddBoxTorque(PhysicsWorld* w, int i, Vec3 t) { if (!w || i < 0 || i >= w->boxes->count) return; WAKE(w->boxes, i); w->boxes->torques[i] = Vec3Add(w->boxes->torques[i], t); }
 void SetSphereCollisionCallback(PhysicsWorld* w, int i, OnCollision cb) { if (w && i >= 0 && i < w->spheres->count) w->spheres->collision_callbacks[i] = cb; }
 void SetBoxCollisionCallback(PhysicsWorld* w, int i, OnCollision cb) { if (w && i >= 0 && i < w->boxes->count) w->boxes->collision_callbacks[i] = cb; }
+
+/* ---- joints: an EXTENSION of this repo (include/ballbox_ext.h: BallboxAddSpring / BallboxAddBallJoint /
+ * BallboxAddDistanceJoint / BallboxAddHingeJoint); the reference only lists "constraints, like hinges, springs" as
+ * planned (README.md:25).  This is the SEQUENTIAL definition the CUDA path is checked against bit for bit; nothing pins it
+ * but itself.
+ *   spring         : a force element, applied in creation order before gravity in ApplyForces
+ *   ball joint     : three bilateral velocity rows (world x, y, z) that hold two anchor points together
+ *   distance joint : one bilateral row along the line between the two anchor points that keeps their distance (a rod)
+ *   hinge          : two ball joints on the hinge axis
+ * Joint rows are presolved after the contacts and swept after the contacts in every solver iteration, joints in creation
+ * order.  Anchors are stored in the body frame.  A sphere has no orientation in this engine (SphereSystem has no rotations),
+ * so a sphere is always attached at its CENTRE (the anchor given for a sphere end is replaced by the centre).  Body type
+ * -1 = the world (a fixed point). */
+#define ORACLE_JOINT_WORLDS 512
+#define ORACLE_JOINT_BALL 0
+#define ORACLE_JOINT_ROD  1
+typedef struct { int ta, ia, tb, ib; Vec3 la, lb; float rest, k, c; } OracleSpring;
+typedef struct { int kind, ta, ia, tb, ib; Vec3 la, lb; float rest; Vec3 rA, rB, dir; float mass[3], bias[3], imp[3]; } OracleJoint;
+static struct { PhysicsWorld* w; OracleSpring* sp; int nsp, csp; OracleJoint* jt; int njt, cjt; } g_joints[ORACLE_JOINT_WORLDS];
+static int joint_slot(PhysicsWorld* w, int create)
+{
+    for (int i = 0; i < ORACLE_JOINT_WORLDS; i++) if (g_joints[i].w == w) return i;
+    if (create) for (int i = 0; i < ORACLE_JOINT_WORLDS; i++) if (!g_joints[i].w) { g_joints[i].w = w; return i; }
+    return -1;
+}
+static void joints_forget(PhysicsWorld* w)
+{
+    int i = joint_slot(w, 0);
+    if (i >= 0) { free(g_joints[i].sp); free(g_joints[i].jt); memset(&g_joints[i], 0, sizeof(g_joints[i])); }
+}
+void BallboxClearJoints(PhysicsWorld* w) { joints_forget(w); }
+static bool joint_body_ok(PhysicsWorld* w, int t, int i)
+{
+    if (t == -1) return true;
+    if (t == 0) return i >= 0 && i < w->spheres->count;
+    if (t == 1) return i >= 0 && i < w->boxes->count;
+    return false;
+}
+/* world point -> body frame (boxes rotate; a sphere is attached at its centre; the world is a fixed point) */
+static Vec3 joint_to_local(PhysicsWorld* w, int t, int i, Vec3 p)
+{
+    if (t == 0) return (Vec3){0, 0, 0};
+    if (t == 1) return QuatRotateVec3(QuatConjugate(w->boxes->rotations[i]), Vec3Sub(p, w->boxes->positions[i]));
+    return p;
+}
+static Vec3 joint_to_world(PhysicsWorld* w, int t, int i, Vec3 l)
+{
+    if (t == 0) return Vec3Add(w->spheres->positions[i], l);
+    if (t == 1) return Vec3Add(w->boxes->positions[i], QuatRotateVec3(w->boxes->rotations[i], l));
+    return l;
+}
+int BallboxAddSpring(PhysicsWorld* w, int ta, int ia, int tb, int ib, Vec3 anchorA, Vec3 anchorB, float rest, float k, float c)
+{
+    if (!w || ta == -1 || !joint_body_ok(w, ta, ia) || !joint_body_ok(w, tb, ib)) return -1;
+    int g = joint_slot(w, 1); if (g < 0) return -1;
+    if (g_joints[g].nsp == g_joints[g].csp) { g_joints[g].csp = g_joints[g].csp ? 2 * g_joints[g].csp : 16; g_joints[g].sp = (OracleSpring*)realloc(g_joints[g].sp, sizeof(OracleSpring) * (size_t)g_joints[g].csp); }
+    OracleSpring* s = &g_joints[g].sp[g_joints[g].nsp];
+    s->ta = ta; s->ia = ia; s->tb = tb; s->ib = tb == -1 ? -1 : ib; s->rest = rest; s->k = k; s->c = c;
+    s->la = joint_to_local(w, ta, ia, anchorA); s->lb = joint_to_local(w, tb, ib, anchorB);
+    return g_joints[g].nsp++;
+}
+static int joint_add(PhysicsWorld* w, int kind, int ta, int ia, int tb, int ib, Vec3 anchorA, Vec3 anchorB)
+{
+    if (!w || ta == -1 || !joint_body_ok(w, ta, ia) || !joint_body_ok(w, tb, ib)) return -1;
+    int g = joint_slot(w, 1); if (g < 0) return -1;
+    if (g_joints[g].njt == g_joints[g].cjt) { g_joints[g].cjt = g_joints[g].cjt ? 2 * g_joints[g].cjt : 16; g_joints[g].jt = (OracleJoint*)realloc(g_joints[g].jt, sizeof(OracleJoint) * (size_t)g_joints[g].cjt); }
+    OracleJoint* j = &g_joints[g].jt[g_joints[g].njt];
+    memset(j, 0, sizeof(*j));
+    j->kind = kind; j->ta = ta; j->ia = ia; j->tb = tb; j->ib = tb == -1 ? -1 : ib;
+    j->la = joint_to_local(w, ta, ia, anchorA); j->lb = joint_to_local(w, tb, ib, anchorB);
+    j->rest = Vec3Length(Vec3Sub(joint_to_world(w, j->tb, j->ib, j->lb), joint_to_world(w, j->ta, j->ia, j->la)));   /* rods keep the distance they were created with */
+    return g_joints[g].njt++;
+}
+int BallboxAddBallJoint(PhysicsWorld* w, int ta, int ia, int tb, int ib, Vec3 anchor) { return joint_add(w, ORACLE_JOINT_BALL, ta, ia, tb, ib, anchor, anchor); }
+int BallboxAddDistanceJoint(PhysicsWorld* w, int ta, int ia, int tb, int ib, Vec3 anchorA, Vec3 anchorB) { return joint_add(w, ORACLE_JOINT_ROD, ta, ia, tb, ib, anchorA, anchorB); }
+int BallboxAddHingeJoint(PhysicsWorld* w, int ta, int ia, int tb, int ib, Vec3 anchor, Vec3 axis, float half_span)
+{
+    Vec3 d = Vec3Scale(Vec3Normalize(axis), half_span);
+    int first = BallboxAddBallJoint(w, ta, ia, tb, ib, Vec3Sub(anchor, d));
+    if (first < 0) return -1;
+    return BallboxAddBallJoint(w, ta, ia, tb, ib, Vec3Add(anchor, d)) < 0 ? -1 : first;
+}
+int BallboxSpringCount(PhysicsWorld* w) { int g = joint_slot(w, 0); return g < 0 ? 0 : g_joints[g].nsp; }
+int BallboxJointCount(PhysicsWorld* w) { int g = joint_slot(w, 0); return g < 0 ? 0 : g_joints[g].njt; }
+
+static void joint_body_state(PhysicsWorld* w, int t, int i, Vec3* pos, Vec3* v, Vec3* om, bool* dyn)
+{
+    *v = *om = (Vec3){0, 0, 0}; *dyn = false;
+    if (t == 0) { *pos = w->spheres->positions[i]; if (!w->spheres->is_static[i]) { *dyn = true; *v = w->spheres->velocities[i]; *om = w->spheres->angular_velocities[i]; } }
+    else if (t == 1) { *pos = w->boxes->positions[i]; if (!w->boxes->is_static[i]) { *dyn = true; *v = w->boxes->velocities[i]; *om = w->boxes->angular_velocities[i]; } }
+}
+static void spring_push(PhysicsWorld* w, int t, int i, Vec3 F, Vec3 T)
+{
+    if (t == 0) { SphereSystem* s = w->spheres; WAKE(s, i); s->forces[i] = Vec3Add(s->forces[i], F); s->torques[i] = Vec3Add(s->torques[i], T); }
+    else { BoxSystem* b = w->boxes; WAKE(b, i); b->forces[i] = Vec3Add(b->forces[i], F); b->torques[i] = Vec3Add(b->torques[i], T); }
+}
+/* spring-dampers: forces and torques on both ends, in creation order, before gravity is added */
+static void stage_springs(PhysicsWorld* w)
+{
+    int g = joint_slot(w, 0); if (g < 0) return;
+    for (int n = 0; n < g_joints[g].nsp; n++) {
+        const OracleSpring* s = &g_joints[g].sp[n];
+        Vec3 posA, vA, oA, posB = s->lb, vB, oB; bool dynA, dynB;
+        joint_body_state(w, s->ta, s->ia, &posA, &vA, &oA, &dynA);
+        joint_body_state(w, s->tb, s->ib, &posB, &vB, &oB, &dynB);
+        Vec3 pA = joint_to_world(w, s->ta, s->ia, s->la), pB = joint_to_world(w, s->tb, s->ib, s->lb);
+        Vec3 d = Vec3Sub(pB, pA);
+        float len = Vec3Length(d);
+        if (len < 1e-6f) continue;
+        Vec3 dir = Vec3Scale(d, 1.0f / len);
+        Vec3 rA = Vec3Sub(pA, posA), rB = Vec3Sub(pB, posB);
+        Vec3 velA = Vec3Add(vA, Vec3Cross(oA, rA)), velB = Vec3Add(vB, Vec3Cross(oB, rB));
+        float f = s->k * (len - s->rest) + s->c * Vec3Dot(Vec3Sub(velB, velA), dir);
+        Vec3 F = Vec3Scale(dir, f), Fm = Vec3Scale(F, -1.0f);
+        if (dynA) spring_push(w, s->ta, s->ia, F, Vec3Cross(rA, F));
+        if (dynB) spring_push(w, s->tb, s->ib, Fm, Vec3Cross(rB, Fm));
+    }
+}
 
 /* ===== stage 1-2: ApplyForces :1820-1838, IntegrateVelocities :1841-1925 ==== */
 static void stage_forces_velocities(PhysicsWorld* w)
@@ -567,6 +687,8 @@ static Vec3 point_velocity(PhysicsWorld* w, const BodyRef* b, Vec3 p)           
     Vec3 om = b->type == 0 ? w->spheres->angular_velocities[b->idx] : w->boxes->angular_velocities[b->idx];
     return Vec3Add(v, Vec3Cross(om, Vec3Sub(p, b->pos)));
 }
+static Vec3 body_v(PhysicsWorld* w, const BodyRef* b) { return b->type == 0 ? w->spheres->velocities[b->idx] : w->boxes->velocities[b->idx]; }
+static Vec3 body_om(PhysicsWorld* w, const BodyRef* b) { return b->type == 0 ? w->spheres->angular_velocities[b->idx] : w->boxes->angular_velocities[b->idx]; }
 static void push(PhysicsWorld* w, const BodyRef* b, Vec3 J, Vec3 L)                          /* ApplyConstraintImpulse :1359-1408 */
 {
     if (!b->dyn) return;
@@ -663,6 +785,28 @@ static void stage_solve(PhysicsWorld* w)
         for (int j = 0; j < 2; j++) c->tangent_mass[j] = eff_mass(&a, &b, rA, rB, c->tangent[j]);
         c->position_bias = (w->settings.baumgarte_bias / w->dt) * fmaxf(0.0f, c->penetration - w->settings.allowed_penetration);
     }
+    const int jg = joint_slot(w, 0);
+    const int njt = jg >= 0 ? g_joints[jg].njt : 0;
+    for (int n = 0; n < njt; n++) {                                                          /* joint rows: presolve */
+        OracleJoint* j = &g_joints[jg].jt[n];
+        Vec3 pA = joint_to_world(w, j->ta, j->ia, j->la), pB = joint_to_world(w, j->tb, j->ib, j->lb);
+        BodyRef a = body_ref(w, j->ta, j->ia, pA), b = body_ref(w, j->tb == -1 ? 2 : j->tb, j->ib, pB);
+        j->rA = Vec3Sub(pA, a.pos); j->rB = Vec3Sub(pB, b.pos);
+        Vec3 C = Vec3Sub(pB, pA);
+        if (j->kind == ORACLE_JOINT_ROD) {
+            j->dir = Vec3Normalize(C);
+            j->mass[0] = eff_mass(&a, &b, j->rA, j->rB, j->dir);
+            j->bias[0] = -((w->settings.baumgarte_bias / w->dt) * (Vec3Length(C) - j->rest));
+            j->imp[0] = 0.0f;
+            continue;
+        }
+        for (int r = 0; r < 3; r++) {
+            Vec3 e = { r == 0 ? 1.0f : 0.0f, r == 1 ? 1.0f : 0.0f, r == 2 ? 1.0f : 0.0f };
+            j->mass[r] = eff_mass(&a, &b, j->rA, j->rB, e);
+            j->bias[r] = -((w->settings.baumgarte_bias / w->dt) * comp(C, r));
+            j->imp[r] = 0.0f;
+        }
+    }
     if (warm > 0.0f && w->settings.solver_iterations > 0) {
         for (int i = 0; i < K->count; i++) {
             if (!matched[i]) continue;
@@ -708,6 +852,25 @@ static void stage_solve(PhysicsWorld* w)
                 }
             }
         }
+        for (int n = 0; n < njt; n++) {                                                      /* joint rows: after the contacts */
+            OracleJoint* j = &g_joints[jg].jt[n];
+            Vec3 pA = joint_to_world(w, j->ta, j->ia, j->la), pB = joint_to_world(w, j->tb, j->ib, j->lb);
+            BodyRef a = body_ref(w, j->ta, j->ia, pA), b = body_ref(w, j->tb == -1 ? 2 : j->tb, j->ib, pB);
+            const int rows = j->kind == ORACLE_JOINT_ROD ? 1 : 3;
+            for (int r = 0; r < rows; r++) {
+                Vec3 e = { r == 0 ? 1.0f : 0.0f, r == 1 ? 1.0f : 0.0f, r == 2 ? 1.0f : 0.0f };
+                if (j->kind == ORACLE_JOINT_ROD) e = j->dir;
+                Vec3 velA = a.dyn ? Vec3Add(body_v(w, &a), Vec3Cross(body_om(w, &a), j->rA)) : (Vec3){0, 0, 0};
+                Vec3 velB = b.dyn ? Vec3Add(body_v(w, &b), Vec3Cross(body_om(w, &b), j->rB)) : (Vec3){0, 0, 0};
+                float vn = Vec3Dot(Vec3Sub(velB, velA), e);
+                float jn = j->mass[r] * (-(vn + 0.0f) + j->bias[r]), old = j->imp[r];
+                j->imp[r] = j->imp[r] + jn;                                                  /* bilateral: no clamp, no restitution, no friction */
+                jn = j->imp[r] - old;
+                Vec3 P = Vec3Scale(e, jn), Pm = Vec3Scale(P, -1.0f);
+                push(w, &a, Pm, Vec3Cross(j->rA, Pm));
+                push(w, &b, P, Vec3Cross(j->rB, P));
+            }
+        }
     }
 }
 
@@ -744,6 +907,7 @@ static void oracle_step(PhysicsWorld* w, float dt, int pruned)
     if (!w) return;
     if (dt <= 0.0f || dt < 1e-6f) return;                                                    /* :1791 */
     w->dt = dt;
+    stage_springs(w);
     stage_forces_velocities(w);
     stage_detect(w, pruned);
     stage_solve(w);
