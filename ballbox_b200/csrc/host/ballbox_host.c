@@ -66,6 +66,7 @@ typedef struct BbxWorldPriv {
     BoxSystem boxes;
     CollisionCollection collisions;
     ConstraintCollection constraints;
+    int n_joints, n_springs;            /* this world's share of the batch's joint / spring lists (extension) */
 } BbxWorldPriv;
 
 /* ------------------------------------------------------------------------- */
@@ -1015,10 +1016,8 @@ static int joint_add(PhysicsWorld* world, int kind, int ta, int ia, int tb, int 
     j->la[0] = la.x; j->la[1] = la.y; j->la[2] = la.z; j->lb[0] = lb.x; j->lb[1] = lb.y; j->lb[2] = lb.z;
     j->rest = Vec3Length(Vec3Sub(joint_to_world(p, tb, ib, lb), joint_to_world(p, ta, ia, la)));
     b->joints_dirty = 1;
-    int id = 0;                                         /* index among this world's joints, like a single world's creation order */
-    for (int k = 0; k < b->n_joints; k++) if (slot_world(b, b->joints[k].ga) == p->index) id++;
     b->n_joints++;
-    return id;
+    return p->n_joints++;                               /* index among this world's joints, like a single world's creation order */
 }
 int BallboxAddBallJoint(PhysicsWorld* world, int ta, int ia, int tb, int ib, Vec3 anchor) { return joint_add(world, BBX_JOINT_BALL, ta, ia, tb, ib, anchor, anchor); }
 int BallboxAddDistanceJoint(PhysicsWorld* world, int ta, int ia, int tb, int ib, Vec3 anchorA, Vec3 anchorB) { return joint_add(world, BBX_JOINT_ROD, ta, ia, tb, ib, anchorA, anchorB); }
@@ -1047,27 +1046,11 @@ int BallboxAddSpring(PhysicsWorld* world, int ta, int ia, int tb, int ib, Vec3 a
     sp->ga = ga; sp->gb = gb; sp->rest = rest; sp->k = k; sp->c = c;
     sp->la[0] = la.x; sp->la[1] = la.y; sp->la[2] = la.z; sp->lb[0] = lb.x; sp->lb[1] = lb.y; sp->lb[2] = lb.z;
     b->joints_dirty = 1;
-    int id = 0;
-    for (int k2 = 0; k2 < b->n_springs; k2++) if (slot_world(b, b->springs[k2].ga) == p->index) id++;
     b->n_springs++;
-    return id;
+    return p->n_springs++;
 }
-int BallboxJointCount(PhysicsWorld* world)
-{
-    BbxWorldPriv* p = priv_of(world);
-    if (!p) return 0;
-    int n = 0;
-    for (int k = 0; k < p->batch->n_joints; k++) if (slot_world(p->batch, p->batch->joints[k].ga) == p->index) n++;
-    return n;
-}
-int BallboxSpringCount(PhysicsWorld* world)
-{
-    BbxWorldPriv* p = priv_of(world);
-    if (!p) return 0;
-    int n = 0;
-    for (int k = 0; k < p->batch->n_springs; k++) if (slot_world(p->batch, p->batch->springs[k].ga) == p->index) n++;
-    return n;
-}
+int BallboxJointCount(PhysicsWorld* world) { BbxWorldPriv* p = priv_of(world); return p ? p->n_joints : 0; }
+int BallboxSpringCount(PhysicsWorld* world) { BbxWorldPriv* p = priv_of(world); return p ? p->n_springs : 0; }
 void BallboxClearJoints(PhysicsWorld* world)
 {
     BbxWorldPriv* p = priv_of(world);
@@ -1079,6 +1062,7 @@ void BallboxClearJoints(PhysicsWorld* world)
     n = 0;
     for (int k = 0; k < b->n_springs; k++) if (slot_world(b, b->springs[k].ga) != p->index) b->springs[n++] = b->springs[k];
     b->n_springs = n;
+    p->n_joints = p->n_springs = 0;
     b->joints_dirty = 1;
 }
 static int sync_joints(struct PhysicsWorldBatch* b)

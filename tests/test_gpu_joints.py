@@ -154,3 +154,66 @@ def test_contact_graph_deeper_than_the_replay_tables_is_an_error_with_joints(pro
     with pytest.raises(bb.BallboxError, match="deeper"):
         for _ in range(3):
             w.step(DT)
+
+
+def _log(w, log):
+    for i in range(0, w.n_spheres, 2):
+        w.set_sphere_callback(i, lambda s, t, o, c: log.append(("s", s, t, o, c.contents.bodyA_index, c.contents.bodyB_index, c.contents.penetration)))
+    for i in range(0, w.n_boxes, 3):
+        w.set_box_callback(i, lambda s, t, o, c: log.append(("b", s, t, o, c.contents.bodyA_index, c.contents.bodyB_index, c.contents.penetration)))
+
+
+@pytest.mark.parametrize("mode", [bb.SYNC_COMPAT, bb.SYNC_COMPAT_BODIES, bb.SYNC_RESIDENT])
+def test_callbacks_with_joints_in_every_sync_mode(product, oracle, mode):
+    """the one-iteration-per-launch solve of a jointed world leaves callbacks, events and the constraint export alone"""
+    g, c = pair(product, oracle, js.chain_on_pile, seed=12, n_loose=30)
+    gl, cl = [], []
+    _log(g, gl); _log(c, cl)
+    g.set_sync_mode(mode)
+    if mode == bb.SYNC_RESIDENT:
+        g.step_n(DT, 70); g.download()
+    else:
+        for _ in range(70):
+            g.step(DT)
+        if mode == bb.SYNC_COMPAT_BODIES:
+            g.download(bb.DL_CONSTRAINTS)
+    for _ in range(70):
+        c.step(DT)
+    assert len(cl) > 100 and gl == cl
+    assert not parity.compare_worlds(g, c)
+
+
+def test_batch_reset_with_joints(product, oracle):
+    """BatchSnapshot / BatchResetWorlds on jointed worlds: joints are kept (their anchors are body-frame), the reset world
+    equals a fresh one"""
+    d = product.dll
+    d.BatchSnapshot.argtypes = [bb.C.c_void_p]
+    d.BatchResetWorlds.argtypes = [bb.C.c_void_p, bb.C.POINTER(bb.C.c_int), bb.C.c_int]
+    n_worlds = 16
+    s, b, k = js.capacity("pile")
+    batch = d.CreatePhysicsWorldBatch(n_worlds, s, b, k)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(n_worlds)]
+    kws = [dict(seed=300 + i, n_loose=12, links=3 + i % 3) for i in range(n_worlds)]
+    refs = []
+    for v, kw in zip(views, kws):
+        js.chain_on_pile(v, **kw)
+        refs.append(js.chain_on_pile(oracle.create_world(s, b, k), **kw))
+    assert d.BatchUpload(batch) == 0
+    assert d.BatchSnapshot(batch) == 0
+    assert d.PhysicsStepBatch(batch, DT, 45) == 0, d.BatchGetLastError(batch)
+    for r in refs:
+        for _ in range(45):
+            r.step(DT)
+    ids = (bb.C.c_int * 3)(2, 7, 15)
+    assert d.BatchResetWorlds(batch, ids, 3) == 0
+    for i in (2, 7, 15):
+        refs[i] = js.chain_on_pile(oracle.create_world(s, b, k), **kws[i])
+    assert d.PhysicsStepBatch(batch, DT, 30) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    for r in refs:
+        for _ in range(30):
+            r.step(DT)
+    for i, (v, r) in enumerate(zip(views, refs)):
+        mm = parity.compare_worlds(v, r)
+        assert not mm, f"world {i}: {mm[:3]}"
+    d.DestroyPhysicsWorldBatch(batch)
