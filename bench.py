@@ -235,10 +235,12 @@ def time_resident(world, steps, warmup, torch, barrier):
     barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()                  # cudaProfilerStart: `ncu --profile-from-start off python bench.py ...` lists exactly the timed launches
     e0.record(stream)
     world.step_n(DT, steps)
     e1.record(stream)
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     barrier()
     ms = e0.elapsed_time(e1)
     stages, covered = world.stage_timing()
