@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(
                     if (trace && r == 0) tr[1] = gtime_ns();
                     // ---- this chunk: staging slots -> registers
                     const bool hasA = live && nd.z >= 0, hasB = live && nd.w >= 0;
-                    BodyState A, B;
+                    BodyState A = body_state_zero(), B = body_state_zero();       // (absent bodies must hold defined values for the branch-free sweep)
                     float4 c0, c1, c2, c3;
                     if (hasA) read_body(dv, cx, 0, nd.z, A);
                     if (hasB) read_body(dv, cx, 1, nd.w, B);
@@ -284,7 +284,10 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(
                                 n0 = ld128_cg_pol(Mn, cx.pol_stream); n1 = ld128_cg_pol(Mn + cx.PL, cx.pol_stream);
                                 n2 = ld128_cg_pol(Mn + 2 * cx.PL, cx.pol_stream); n3 = ld128_cg_pol(Mn + 3 * cx.PL, cx.pol_stream);
                             }
-                            solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                            // class 0 = single constraints between spheres (and statics): the plain form skips the box
+                            // arithmetic for the whole warp; every other class uses the branch-free form (bbx_solve.cuh)
+                            if (ww.cls == 0) solve_constraint<false>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                            else             solve_constraint<true>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                             st128_cg_pol(M + 3 * cx.PL, c3, cx.pol_stream);
                             c0 = n0; c1 = n1; c2 = n2; c3 = n3;
                         }

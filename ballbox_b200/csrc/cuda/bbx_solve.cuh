@@ -77,6 +77,25 @@ __device__ __forceinline__ void load_body_keep(const BbxDev& dv, int g, BodyStat
         s.k1 = s.q.w * s.q.w - v3dot(u, u); s.k2 = 2.0f * s.q.w;
     }
 }
+// Both bodies of a node at once: ALL loads are issued before the first value is used.  With two calls of load_body_keep
+// the box scalars of body A (k1, k2) are computed inside A's branch, i.e. the warp waits for A's rotation before it even
+// requests body B: two (for a box-box node: two DRAM / L2 round trips) instead of one.
+__device__ __forceinline__ void load_bodies_keep(const BbxDev& dv, int gA, int gB, bool hasA, bool hasB, BodyState& A, BodyState& B,
+                                                 unsigned long long pol)
+{
+    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    F8 va, vb, qa, qb;
+    va.a = va.b = vb.a = vb.b = qa.a = qa.b = qb.a = qb.b = z4;
+    const bool boxA = hasA && gA >= dv.NS, boxB = hasB && gB >= dv.NS;
+    if (hasA) va = ld256_cg_pol(&dv.vel[2 * (size_t)gA], pol);
+    if (boxA) qa = ld256_nc_pol(&dv.boxq[2 * (size_t)(gA - dv.NS)], pol);
+    if (hasB) vb = ld256_cg_pol(&dv.vel[2 * (size_t)gB], pol);
+    if (boxB) qb = ld256_nc_pol(&dv.boxq[2 * (size_t)(gB - dv.NS)], pol);
+    A.v = xyz(va.a); A.w = xyz(va.b); A.im = va.a.w; A.ii = va.b.w; A.box = boxA; A.q = qa.a; A.iI = xyz(qa.b);
+    B.v = xyz(vb.a); B.w = xyz(vb.b); B.im = vb.a.w; B.ii = vb.b.w; B.box = boxB; B.q = qb.a; B.iI = xyz(qb.b);
+    { const float3 u = f3(A.q.x, A.q.y, A.q.z); A.k1 = A.q.w * A.q.w - v3dot(u, u); A.k2 = 2.0f * A.q.w; }
+    { const float3 u = f3(B.q.x, B.q.y, B.q.z); B.k1 = B.q.w * B.q.w - v3dot(u, u); B.k2 = 2.0f * B.q.w; }
+}
 __device__ __forceinline__ void store_body_keep(const BbxDev& dv, int g, const BodyState& s, unsigned long long pol)
 {
     st256_cg_pol(&dv.vel[2 * g], make_float4(s.v.x, s.v.y, s.v.z, s.im), make_float4(s.w.x, s.w.y, s.w.z, s.ii), pol);
@@ -152,15 +171,53 @@ __device__ __forceinline__ void apply_impulse(BodyState& s, float3 J, float3 L)
     }
 }
 
+// The same operations without control flow: both angular updates are computed and one is selected.  A body that is absent
+// (static) must hold defined values (zeros); its state is updated with garbage that nobody reads (velocities of an absent
+// body enter the sweep as zero, and it is never stored).  With the `if (hasA) ... if (hasB) ...` of the plain form the two
+// applications of an impulse sit in different basic blocks and a lone warp executes their dependent chains one after the
+// other; here ptxas interleaves them.  Used where a sweep is latency bound (k_solve_groups: one warp per level of a world).
+__device__ __forceinline__ void apply_impulse_flat(BodyState& s, float3 J, float3 L)
+{
+    s.v = v3add(s.v, v3scale(J, s.im));
+    const float3 ws = v3add(s.w, v3scale(L, s.ii));
+    const float3 u = f3(s.q.x, s.q.y, s.q.z), um = f3(-s.q.x, -s.q.y, -s.q.z);
+    const float3 loc = qrot_pre(um, s.k1, s.k2, L);
+    const float3 dl = v3mul(loc, s.iI);
+    const float3 wb = v3add(s.w, qrot_pre(u, s.k1, s.k2, dl));
+    s.w = s.box ? wb : ws;
+}
+__device__ __forceinline__ BodyState body_state_zero()
+{
+    BodyState s;
+    s.v = s.w = s.iI = f3(0.0f, 0.0f, 0.0f); s.im = s.ii = s.k1 = s.k2 = 0.0f; s.q = make_float4(0.0f, 0.0f, 0.0f, 0.0f); s.box = false;
+    return s;
+}
+// velocity of a body at the contact point (:1233-1261), zero for an absent body.  FLAT: computed unconditionally and
+// masked (bit-and with all ones or zero: exactly v or +0), so that the A and B sides stay in one basic block
+template <bool FLAT>
+__device__ __forceinline__ float3 point_velocity(const BodyState& s, bool has, float3 r)
+{
+    if (!FLAT) return has ? v3add(s.v, v3cross(s.w, r)) : f3(0.0f, 0.0f, 0.0f);
+    const float3 t = v3add(s.v, v3cross(s.w, r));
+    const int m = has ? -1 : 0;
+    return f3(__int_as_float(__float_as_int(t.x) & m), __int_as_float(__float_as_int(t.y) & m), __int_as_float(__float_as_int(t.z) & m));
+}
+template <bool FLAT>
+__device__ __forceinline__ void apply_side(BodyState& s, bool has, float3 J, float3 L)
+{
+    if (FLAT) apply_impulse_flat(s, J, L);
+    else if (has) apply_impulse(s, J, L);
+}
+
 // one constraint, one Gauss-Seidel visit (:1414-1488) on bodies held in registers
+template <bool FLAT = false>
 __device__ __forceinline__ void solve_constraint(float4 c0, float4 c1, float4 c2, float4& c3, bool hasA, bool hasB,
                                                  BodyState& A, BodyState& B, const SolveParams& sp)
 {
     float3 n = xyz(c0), rA = xyz(c1), rB = xyz(c2);
     float bias = c0.w, mN = c1.w, mT0 = c2.w, mT1 = c3.w;
-    const float3 zero = f3(0.0f, 0.0f, 0.0f);
-    float3 vA = hasA ? v3add(A.v, v3cross(A.w, rA)) : zero;                  // :1233-1261
-    float3 vB = hasB ? v3add(B.v, v3cross(B.w, rB)) : zero;
+    float3 vA = point_velocity<FLAT>(A, hasA, rA);                           // :1233-1261
+    float3 vB = point_velocity<FLAT>(B, hasB, rB);
     float3 rel = v3sub(vB, vA);
     float vn = v3dot(rel, n);
     float vbias = 0.0f;
@@ -171,11 +228,11 @@ __device__ __forceinline__ void solve_constraint(float4 c0, float4 c1, float4 c2
     jn = c3.x - old;
     float3 P = v3scale(n, jn);
     float3 Pm = v3scale(P, -1.0f);
-    if (hasA) apply_impulse(A, Pm, v3cross(rA, Pm));                         // :1456-1459
-    if (hasB) apply_impulse(B, P, v3cross(rB, P));
+    apply_side<FLAT>(A, hasA, Pm, v3cross(rA, Pm));                         // :1456-1459
+    apply_side<FLAT>(B, hasB, P, v3cross(rB, P));
     if (sp.friction > 0.0f) {                                                // :1462-1487
-        vA = hasA ? v3add(A.v, v3cross(A.w, rA)) : zero;
-        vB = hasB ? v3add(B.v, v3cross(B.w, rB)) : zero;
+        vA = point_velocity<FLAT>(A, hasA, rA);
+        vB = point_velocity<FLAT>(B, hasB, rB);
         rel = v3sub(vB, vA);
         float3 t1, t2;
         tangents_of(n, t1, t2);
@@ -187,8 +244,8 @@ __device__ __forceinline__ void solve_constraint(float4 c0, float4 c1, float4 c2
             c3.y = bb_fmaxf(-maxF, bb_fminf(maxF, c3.y + jt));
             jt = c3.y - o;
             float3 T = v3scale(t1, jt), Tm = v3scale(T, -1.0f);
-            if (hasA) apply_impulse(A, Tm, v3cross(rA, Tm));
-            if (hasB) apply_impulse(B, T, v3cross(rB, T));
+            apply_side<FLAT>(A, hasA, Tm, v3cross(rA, Tm));
+            apply_side<FLAT>(B, hasB, T, v3cross(rB, T));
         }
         {
             float vt = v3dot(rel, t2);                                       // same pre-loop rel (:1466 is outside the j loop)
@@ -197,8 +254,8 @@ __device__ __forceinline__ void solve_constraint(float4 c0, float4 c1, float4 c2
             c3.z = bb_fmaxf(-maxF, bb_fminf(maxF, c3.z + jt));
             jt = c3.z - o;
             float3 T = v3scale(t2, jt), Tm = v3scale(T, -1.0f);
-            if (hasA) apply_impulse(A, Tm, v3cross(rA, Tm));
-            if (hasB) apply_impulse(B, T, v3cross(rB, T));
+            apply_side<FLAT>(A, hasA, Tm, v3cross(rA, Tm));
+            apply_side<FLAT>(B, hasB, T, v3cross(rB, T));
         }
     }
 }

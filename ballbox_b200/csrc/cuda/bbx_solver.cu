@@ -515,8 +515,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                     __stcg(&dv.colq_k[k][p], colr);
                 }
                 BodyState A, B;
-                if (hasA) load_body_keep(dv, nd0.x, A, pol_keep);
-                if (hasB) load_body_keep(dv, nd0.y, B, pol_keep);
+                if (k == 0) {                                          // class 0: spheres only, plain sweep below
+                    if (hasA) load_body_keep(dv, nd0.x, A, pol_keep);
+                    if (hasB) load_body_keep(dv, nd0.y, B, pol_keep);
+                } else load_bodies_keep(dv, nd0.x, nd0.y, hasA, hasB, A, B, pol_keep);
                 // contact-order records are gathered once (two 256-bit loads, the next record in flight while
                 // the current constraint is swept), then written plane-major
                 const float4* L = dv.L + 4 * (size_t)c;
@@ -525,7 +527,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 for (int j = 0; j < m; j++, L += 4) {
                     float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
                     if (j + 1 < m) { lo = ld256_nc_pol(L + 4, pol_stream); hi = ld256_nc_pol(L + 6, pol_stream); }
-                    solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    if (k == 0) solve_constraint<false>(c0, c1, c2, c3, hasA, hasB, A, B, sp);     // class 0: no box in the warp
+                    else        solve_constraint<true>(c0, c1, c2, c3, hasA, hasB, A, B, sp);      // branch-free form (bbx_solve.cuh)
                     float4* M = dv.M + (size_t)(slot0 + j * mstride);
                     st128_cg_pol(M, c0, pol_stream); st128_cg_pol(M + PL, c1, pol_stream); st128_cg_pol(M + 2 * PL, c2, pol_stream); st128_cg_pol(M + 3 * PL, c3, pol_stream);
                 }
@@ -639,8 +642,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 int4 nd = ld128i_cg_pol(&dv.Nd_k[k][head[k] + idx], pol_stream);
                 bool hasA = nd.z >= 0, hasB = nd.w >= 0;
                 BodyState A, B;
-                if (hasA) load_body_keep(dv, nd.z, A, pol_keep);
-                if (hasB) load_body_keep(dv, nd.w, B, pol_keep);
+                if (k == 0) {
+                    if (hasA) load_body_keep(dv, nd.z, A, pol_keep);
+                    if (hasB) load_body_keep(dv, nd.w, B, pol_keep);
+                } else load_bodies_keep(dv, nd.z, nd.w, hasA, hasB, A, B, pol_keep);
                 float4* M = dv.M + (size_t)nd.x;
                 const int ms = k <= 4 ? cnt[k] : 1;                   // distance between a node's consecutive records (RECORD SLOTS above)
                 // software pipeline: the record of constraint j+1 is in flight while constraint j is swept
@@ -648,7 +653,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
                 for (int j = 0; j < nd.y; j++, M += ms) {
                     float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
                     if (j + 1 < nd.y) { n0 = ld128_cg_pol(M + ms, pol_stream); n1 = ld128_cg_pol(M + ms + PL, pol_stream); n2 = ld128_cg_pol(M + ms + 2 * PL, pol_stream); n3 = ld128_cg_pol(M + ms + 3 * PL, pol_stream); }
-                    solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    if (k == 0) solve_constraint<false>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    else        solve_constraint<true>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                     st128_cg_pol(M + 3 * PL, c3, pol_stream);
                 }
                 if (hasA) store_body_keep(dv, nd.z, A, pol_keep);
@@ -677,8 +683,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
 // iterations 1..I-1 stream them.  Same per-body constraint order as everywhere else: bit-identical results.
 // ---------------------------------------------------------------------------
 #define GRP_THREADS 128
+#ifndef GRP_FLAT
+#define GRP_FLAT true                  // branch-free sweep (bbx_solve.cuh): a level of a small world is ONE warp, latency bound
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-#define GRP_BLOCKS_PER_SM 6
+#define GRP_BLOCKS_PER_SM 4
 #define GRP_LMAX 2047                  // dependency levels of a group
 
 __global__ void __launch_bounds__(256) k_frontier0_groups(BbxDev dv, int* gq, int* gq_count, int wpb, int gcap)
@@ -712,6 +721,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     __shared__ int level_start[GRP_LMAX + 2];
     __shared__ int s_next;
     const int g = blockIdx.x, tid = threadIdx.x;
+    const int vt = tid;                                               // (rotating the block's warps by a per-block offset measured SLOWER: profiles/r02_notes.md)
     // slots this group owns in queue / M / Nd: gcap, except for a ragged last group (fewer than wpb worlds), whose slice
     // ends with the allocations; every append and the overflow test are bounded by it
     const int glim = (int)min((long long)gcap, (long long)dv.cap_contacts - (long long)g * gcap);
@@ -730,7 +740,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     int head = 0, tail = n0, lvl = 0;
     bool bad = false;
     while (head < tail) {
-        for (int p = head + tid; p < tail; p += GRP_THREADS) {
+        for (int p = head + vt; p < tail; p += GRP_THREADS) {
             const int c = __ldcg(&queue[p]);
             F8 nd = ld256_nc_pol((const float4*)&dv.node[2 * (size_t)c], pol_stream);    // (gid A, ...) (gid B, ...)
             const int2 lk = ld64_pol(&dv.link[c], pol_stream);                           // successors on A's and B's chain
@@ -741,9 +751,8 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
             float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
             const bool hasA = gA >= 0, hasB = gB >= 0;
             BodyState A, B;
-            if (hasA) load_body_keep(dv, gA, A, pol_keep);
-            if (hasB) load_body_keep(dv, gB, B, pol_keep);
-            solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+            load_bodies_keep(dv, gA, gB, hasA, hasB, A, B, pol_keep);
+            solve_constraint<GRP_FLAT>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
             if (hasA) store_body_keep(dv, gA, A, pol_keep);
             if (hasB) store_body_keep(dv, gB, B, pol_keep);
             float4* M = dv.M + base + p;
@@ -770,14 +779,14 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     // swept (descriptors are static), so that after the barrier the body loads can be issued at once; the next
     // level's records are pulled into L2 at the same time (prefetch, no registers).
     int2 dn = make_int2(-1, -1);
-    { const int pn = level_start[0] + tid; if (pn < level_start[1]) { int4 t4 = ld128i_cg_pol(&gd[pn], pol_stream); dn = make_int2(t4.x, t4.y); } }
+    { const int pn = level_start[0] + vt; if (pn < level_start[1]) { int4 t4 = ld128i_cg_pol(&gd[pn], pol_stream); dn = make_int2(t4.x, t4.y); } }
     for (int it = 1; it < sp.iterations; it++) {
         for (int l = 0; l < n_levels; l++) {
             const int s0 = level_start[l], s1 = level_start[l + 1];
             const int2 dc = dn;
             {
                 const int ln = (l + 1 < n_levels) ? l + 1 : 0;
-                const int pn = level_start[ln] + tid;
+                const int pn = level_start[ln] + vt;
                 dn = make_int2(-1, -1);
                 if (pn < level_start[ln + 1]) {
                     int4 t4 = ld128i_cg_pol(&gd[pn], pol_stream); dn = make_int2(t4.x, t4.y);
@@ -786,16 +795,15 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
                     if (n_levels > 1) prefetch_l2(Mn + 3 * PL);
                 }
             }
-            for (int p = s0 + tid; p < s1; p += GRP_THREADS) {
+            for (int p = s0 + vt; p < s1; p += GRP_THREADS) {
                 int2 d = dc;
-                if (p != s0 + tid) { int4 t4 = ld128i_cg_pol(&gd[p], pol_stream); d = make_int2(t4.x, t4.y); }      // (levels wider than the block)
+                if (p != s0 + vt) { int4 t4 = ld128i_cg_pol(&gd[p], pol_stream); d = make_int2(t4.x, t4.y); }      // (levels wider than the block)
                 float4* M = dv.M + base + p;
                 float4 c0 = ld128_cg_pol(M, pol_stream), c1 = ld128_cg_pol(M + PL, pol_stream), c2 = ld128_cg_pol(M + 2 * PL, pol_stream), c3 = ld128_cg_pol(M + 3 * PL, pol_stream);
                 const bool hasA = d.x >= 0, hasB = d.y >= 0;
                 BodyState A, B;
-                if (hasA) load_body_keep(dv, d.x, A, pol_keep);
-                if (hasB) load_body_keep(dv, d.y, B, pol_keep);
-                solve_constraint(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                load_bodies_keep(dv, d.x, d.y, hasA, hasB, A, B, pol_keep);
+                solve_constraint<GRP_FLAT>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
                 if (hasA) store_body_keep(dv, d.x, A, pol_keep);
                 if (hasB) store_body_keep(dv, d.y, B, pol_keep);
                 st128_cg_pol(M + 3 * PL, c3, pol_stream);
