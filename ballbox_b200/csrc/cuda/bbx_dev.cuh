@@ -174,6 +174,9 @@ struct BbxDev {
     int tune_solve_blocks;                       // BBX_SOLVE_BLOCKS: smaller grid for k_solve_levels
     int tune_flow_blocks, tune_flow_gather, trace_level;   // BBX_FLOW_BLOCKS, BBX_FLOW_GATHER, BBX_TRACE_LEVEL
     int grp_blocks;                              // co-resident blocks of k_solve_groups (sizes the groups of worlds)
+    int grp_force_wpb;                           // BBX_GRP_WPB: at least this many worlds per group (tests of multi-world groups on small batches)
+    int grp_pair_cap;                            // BBX_GRP_PAIR_CAP: lowers the constraints a group may keep in shared memory (tests of the hand-over)
+    int grp_smem_wpb;                            // BBX_GRP_SMEM: groups of up to this many worlds keep their body state in shared memory during the solve
     int find_pairs_mode;                         // BBX_FIND_PAIRS: 0 lane-per-body walk, 1 flattened warp walk, unset (-1): by batch size
     int force_flow;                              // BBX_SOLVER_FLOW=1: the exact schedule runs on the flow solver (A/B measurements)
     unsigned long long *level_ns;                // optional trace: globaltimer at the end of each level of iteration 1 (first 4096)

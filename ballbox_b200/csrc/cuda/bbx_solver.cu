@@ -690,6 +690,35 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #define GRP_BLOCKS_PER_SM 4
 #define GRP_LMAX 2047                  // dependency levels of a group
 
+// ---- shared-memory body state of a group (k_solve_groups, small groups) ----
+__device__ __forceinline__ void grp_cp16(void* sdst, const void* g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned int)__cvta_generic_to_shared(sdst)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void grp_cp_commit_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory"); }
+// both bodies of a constraint from the group's slots (ia / ib = 0xffff: absent); same values as load_bodies_keep
+__device__ __forceinline__ void load_bodies_smem(const float4* s_vel, const float4* s_boxq, unsigned int nsl, unsigned int ia, unsigned int ib,
+                                                 BodyState& A, BodyState& B)
+{
+    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const bool hasA = ia != 0xffffu, hasB = ib != 0xffffu;
+    const bool boxA = hasA && ia >= nsl, boxB = hasB && ib >= nsl;
+    F8 va, vb, qa, qb;
+    va.a = va.b = vb.a = vb.b = qa.a = qa.b = qb.a = qb.b = z4;
+    if (hasA) { va.a = s_vel[2 * ia]; va.b = s_vel[2 * ia + 1]; }
+    if (boxA) { qa.a = s_boxq[2 * (ia - nsl)]; qa.b = s_boxq[2 * (ia - nsl) + 1]; }
+    if (hasB) { vb.a = s_vel[2 * ib]; vb.b = s_vel[2 * ib + 1]; }
+    if (boxB) { qb.a = s_boxq[2 * (ib - nsl)]; qb.b = s_boxq[2 * (ib - nsl) + 1]; }
+    A.v = xyz(va.a); A.w = xyz(va.b); A.im = va.a.w; A.ii = va.b.w; A.box = boxA; A.q = qa.a; A.iI = xyz(qa.b);
+    B.v = xyz(vb.a); B.w = xyz(vb.b); B.im = vb.a.w; B.ii = vb.b.w; B.box = boxB; B.q = qb.a; B.iI = xyz(qb.b);
+    { const float3 u = f3(A.q.x, A.q.y, A.q.z); A.k1 = A.q.w * A.q.w - v3dot(u, u); A.k2 = 2.0f * A.q.w; }
+    { const float3 u = f3(B.q.x, B.q.y, B.q.z); B.k1 = B.q.w * B.q.w - v3dot(u, u); B.k2 = 2.0f * B.q.w; }
+}
+__device__ __forceinline__ void store_body_smem(float4* s_vel, unsigned int i, const BodyState& s)
+{
+    s_vel[2 * i] = make_float4(s.v.x, s.v.y, s.v.z, s.im); s_vel[2 * i + 1] = make_float4(s.w.x, s.w.y, s.w.z, s.ii);
+}
+
 __global__ void __launch_bounds__(256) k_frontier0_groups(BbxDev dv, int* gq, int* gq_count, int wpb, int gcap)
 {
     __shared__ int s_solver;
@@ -716,10 +745,24 @@ __global__ void __launch_bounds__(256) k_frontier0_groups(BbxDev dv, int* gq, in
     if (threadIdx.x == 0 && s_solver) { atomicAdd(&dv.ctr->n_solver, s_solver); atomicAdd(&dv.ctr->n_nodes, s_solver); }
 }
 
-__global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups(BbxDev dv, SolveParams sp, int* gq, const int* gq_count, int gcap)
+// SHARED-MEMORY FORM (smem_bodies, small groups).  A level of a small group is ONE warp walking one constraint per lane
+// (~700 instructions, two dependent chains), and the step time of a small batch is the number of block-synchronised
+// levels of its deepest world times that latency, whatever the number of worlds: the per-GPU share of a batch that is
+// partitioned over many GPUs is bound by it.  ncu on the global-memory form at 512 worlds: per issued instruction 1.09
+// cycles of long-scoreboard stall (queue entry -> node -> bodies in iteration 0, the body gather after every barrier in
+// the replay) on top of 0.72 of fixed-latency waits.  The block is the only reader and writer of its worlds' velocities
+// during the solve, so here they live in shared memory (32 bytes per body slot + 32 per box: rotation and inverse
+// inertia; loaded once, written back once), together with the visiting order (iteration 0 reads its queue from shared
+// memory) and the two body slots of every constraint (16 bits each); the next level's record is staged by cp.async
+// into thread-private slots while the current level is swept, so that a replayed level starts from shared memory only.
+// Same per-body order, same arithmetic: bit-identical.  Measured (512 worlds of config 5): profiles/r02_notes.md.
+__global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups(BbxDev dv, SolveParams sp, int* gq, const int* gq_count, int gcap,
+                                                                                 int wpb, int pair_cap, int smem_bodies)
 {
     __shared__ int level_start[GRP_LMAX + 2];
     __shared__ int s_next;
+    extern __shared__ __align__(16) int g_pair[];                     // shared-memory form: [pair_cap] body slots, [pair_cap] visiting order, bodies, record staging
+    #define GRP_STAMP(i) do { if (sp.gather < 0 && tid == 0 && g < 256) { unsigned long long ns_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_)); dv.level_ns[g * 8 + (i)] = ns_; } } while (0)
     const int g = blockIdx.x, tid = threadIdx.x;
     const int vt = tid;                                               // (rotating the block's warps by a per-block offset measured SLOWER: profiles/r02_notes.md)
     // slots this group owns in queue / M / Nd: gcap, except for a ragged last group (fewer than wpb worlds), whose slice
@@ -733,15 +776,36 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     int4* gd = dv.Nd_k[0] + base;                                     // descriptors in visiting order: (gid A, gid B, contact, -)
     const size_t PL = (size_t)dv.cap_contacts;
     if (tid == 0) { s_next = 0; level_start[0] = 0; }
-    __syncthreads();
+    GRP_STAMP(0);
     const bool big = dv.ctr->n_contacts > BBX_L2_STREAM_CONTACTS;     // bodies stay in L2, records stream
     const unsigned long long pol_keep = big ? l2_policy_keep() : l2_policy_normal(), pol_stream = big ? l2_policy_stream() : l2_policy_normal();
+    // shared-memory form: body slot of a gid = gid - s_off (spheres) / gid - b_off (boxes, after the nsl sphere slots)
+    const int nsl = wpb * dv.cap_s, nbl = wpb * (dv.cap_s + dv.cap_b);
+    const int s_off = g * wpb * dv.cap_s, b_off = dv.NS + g * wpb * dv.cap_b - nsl;
+    int* s_queue = g_pair + pair_cap;
+    float4* s_vel = reinterpret_cast<float4*>(s_queue + pair_cap);
+    float4* s_boxq = s_vel + 2 * nbl;
+    float4* s_rec = s_boxq + 2 * (nbl - nsl);                           // [plane][thread]
+    const int nwg = min(wpb, dv.n_worlds - g * wpb);                     // worlds of this group (the last group may be ragged)
+    const int ns_valid = nwg * dv.cap_s, nb_valid = nwg * dv.cap_b;
+    bool in_smem = smem_bodies != 0;                                    // (uniform over the block) the velocities live in s_vel
+    if (in_smem) {
+        for (int i = tid; i < nbl; i += GRP_THREADS) {
+            if (!(i < nsl ? i < ns_valid : (i - nsl) < nb_valid)) continue;
+            const int gid = i < nsl ? s_off + i : b_off + i;
+            grp_cp16(&s_vel[2 * i], &dv.vel[2 * (size_t)gid]); grp_cp16(&s_vel[2 * i + 1], &dv.vel[2 * (size_t)gid + 1]);
+            if (i >= nsl) { const size_t bx = (size_t)(gid - dv.NS); grp_cp16(&s_boxq[2 * (i - nsl)], &dv.boxq[2 * bx]); grp_cp16(&s_boxq[2 * (i - nsl) + 1], &dv.boxq[2 * bx + 1]); }
+        }
+        for (int p = tid; p < min(n0, pair_cap); p += GRP_THREADS) s_queue[p] = __ldcg(&queue[p]);
+        grp_cp_commit_wait();
+    }
+    __syncthreads();
     // ---- iteration 0: Kahn levels ----
     int head = 0, tail = n0, lvl = 0;
     bool bad = false;
     while (head < tail) {
         for (int p = head + vt; p < tail; p += GRP_THREADS) {
-            const int c = __ldcg(&queue[p]);
+            const int c = (in_smem && p < pair_cap) ? s_queue[p] : __ldcg(&queue[p]);
             F8 nd = ld256_nc_pol((const float4*)&dv.node[2 * (size_t)c], pol_stream);    // (gid A, ...) (gid B, ...)
             const int2 lk = ld64_pol(&dv.link[c], pol_stream);                           // successors on A's and B's chain
             const int gA = __float_as_int(nd.a.x), gB = __float_as_int(nd.b.x);
@@ -751,16 +815,26 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
             float4 c0 = lo.a, c1 = lo.b, c2 = hi.a, c3 = hi.b;
             const bool hasA = gA >= 0, hasB = gB >= 0;
             BodyState A, B;
-            load_bodies_keep(dv, gA, gB, hasA, hasB, A, B, pol_keep);
-            solve_constraint<GRP_FLAT>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
-            if (hasA) store_body_keep(dv, gA, A, pol_keep);
-            if (hasB) store_body_keep(dv, gB, B, pol_keep);
+            if (in_smem) {
+                const unsigned int ia = gA < 0 ? 0xffffu : (unsigned int)(gA < dv.NS ? gA - s_off : gA - b_off);
+                const unsigned int ib = gB < 0 ? 0xffffu : (unsigned int)(gB < dv.NS ? gB - s_off : gB - b_off);
+                if (p < pair_cap) g_pair[p] = (int)(ia | (ib << 16));
+                load_bodies_smem(s_vel, s_boxq, (unsigned int)nsl, ia, ib, A, B);
+                solve_constraint<GRP_FLAT>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                if (hasA) store_body_smem(s_vel, ia, A);
+                if (hasB) store_body_smem(s_vel, ib, B);
+            } else {
+                load_bodies_keep(dv, gA, gB, hasA, hasB, A, B, pol_keep);
+                solve_constraint<GRP_FLAT>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                if (hasA) store_body_keep(dv, gA, A, pol_keep);
+                if (hasB) store_body_keep(dv, gB, B, pol_keep);
+            }
             float4* M = dv.M + base + p;
             st128_cg_pol(M, c0, pol_stream); st128_cg_pol(M + PL, c1, pol_stream); st128_cg_pol(M + 2 * PL, c2, pol_stream); st128_cg_pol(M + 3 * PL, c3, pol_stream);
             __stcg(&gd[p], make_int4(gA, gB, c, 0));
             dv.slot_of[c] = (int)(base + p);
-            if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) __stcg(&queue[q], sa); }
-            if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) __stcg(&queue[q], sb); }
+            if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) { __stcg(&queue[q], sa); if (in_smem && q < pair_cap) s_queue[q] = sa; } }
+            if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) { __stcg(&queue[q], sb); if (in_smem && q < pair_cap) s_queue[q] = sb; } }
         }
         __syncthreads();
         const int pushed = s_next;
@@ -774,6 +848,52 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     const int n_levels = lvl;
     if (tid == 0) { atomicMax(&dv.ctr->n_levels, n_levels); level_start[n_levels] = tail; }
     __syncthreads();
+    GRP_STAMP(1);
+    if (sp.gather < 0 && tid == 0 && g < 256) { dv.level_ns[g * 8 + 5] = n_levels; dv.level_ns[g * 8 + 7] = tail; }
+    if (in_smem && sp.iterations > 1 && tail <= pair_cap) {
+        // ---- iterations 1..I-1 from shared memory ----
+        const bool stage = n_levels > 1;                                // (one level: the next record IS the current one, whose impulses are being updated)
+        if (stage) { const int pn = level_start[0] + vt; if (pn < level_start[1]) { const float4* Mn = dv.M + base + pn; for (int r = 0; r < 4; r++) grp_cp16(&s_rec[r * GRP_THREADS + tid], Mn + r * PL); } }
+        grp_cp_commit_wait();
+        for (int it = 1; it < sp.iterations; it++) {
+            for (int l = 0; l < n_levels; l++) {
+                const int s0 = level_start[l], s1 = level_start[l + 1];
+                float4 c0, c1, c2, c3;
+                if (stage && s0 + vt < s1) { c0 = s_rec[tid]; c1 = s_rec[GRP_THREADS + tid]; c2 = s_rec[2 * GRP_THREADS + tid]; c3 = s_rec[3 * GRP_THREADS + tid]; }
+                if (stage) {
+                    const int ln = (l + 1 < n_levels) ? l + 1 : 0;
+                    const int pn = level_start[ln] + vt;
+                    if (pn < level_start[ln + 1]) { const float4* Mn = dv.M + base + pn; for (int r = 0; r < 4; r++) grp_cp16(&s_rec[r * GRP_THREADS + tid], Mn + r * PL); }
+                }
+                for (int p = s0 + vt; p < s1; p += GRP_THREADS) {
+                    float4* M = dv.M + base + p;
+                    if (!stage || p != s0 + vt) { c0 = ld128_cg_pol(M, pol_stream); c1 = ld128_cg_pol(M + PL, pol_stream); c2 = ld128_cg_pol(M + 2 * PL, pol_stream); c3 = ld128_cg_pol(M + 3 * PL, pol_stream); }   // (levels wider than the block)
+                    const unsigned int pr = (unsigned int)g_pair[p];
+                    const unsigned int ia = pr & 0xffffu, ib = pr >> 16;
+                    const bool hasA = ia != 0xffffu, hasB = ib != 0xffffu;
+                    BodyState A, B;
+                    load_bodies_smem(s_vel, s_boxq, (unsigned int)nsl, ia, ib, A, B);
+                    solve_constraint<GRP_FLAT>(c0, c1, c2, c3, hasA, hasB, A, B, sp);
+                    if (hasA) store_body_smem(s_vel, ia, A);
+                    if (hasB) store_body_smem(s_vel, ib, B);
+                    st128_cg_pol(M + 3 * PL, c3, pol_stream);
+                }
+                grp_cp_commit_wait();
+                __syncthreads();
+            }
+        }
+    }
+    if (in_smem) {
+        // the velocities go back to the packed array (also when the group turned out too large for the shared-memory
+        // replay: the level replay below then continues on global memory)
+        for (int i = tid; i < nbl; i += GRP_THREADS) {
+            if (!(i < nsl ? i < ns_valid : (i - nsl) < nb_valid)) continue;
+            const int gid = i < nsl ? s_off + i : b_off + i;
+            st256_cg_pol(&dv.vel[2 * (size_t)gid], s_vel[2 * i], s_vel[2 * i + 1], pol_keep);
+        }
+        if (tail <= pair_cap || sp.iterations <= 1) { GRP_STAMP(4); return; }
+        __syncthreads();
+    }
     // ---- iterations 1..I-1: stream the visiting order ----
     // The descriptor of this thread's first constraint of the NEXT level is fetched while the current level is
     // swept (descriptors are static), so that after the barrier the body loads can be issued at once; the next
@@ -811,6 +931,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
             __syncthreads();
         }
     }
+    GRP_STAMP(4);
 }
 
 // Batches go to the group solver when there are enough worlds to fill the SMs with groups and a world is small enough
@@ -918,9 +1039,11 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
             BBX_CUDA(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_groups, GRP_THREADS, 0));
             if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "group solver kernel does not fit on an SM", __FILE__, __LINE__);
             d->grp_blocks = per_sm * d->num_sms;
+            BBX_CUDA(d, cudaFuncSetAttribute(k_solve_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         }
         int wpb = (d->n_worlds + d->grp_blocks - 1) / d->grp_blocks;
         if (wpb < 1) wpb = 1;
+        if (d->grp_force_wpb > wpb) wpb = d->grp_force_wpb;           // BBX_GRP_WPB (tests): larger groups than the batch needs
         const int n_groups = (d->n_worlds + wpb - 1) / wpb;
         long long gcap_ll = (long long)wpb * d->cap_contacts_world;
         if (gcap_ll > d->cap_contacts) gcap_ll = d->cap_contacts;
@@ -930,7 +1053,21 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         BBX_CUDA(d, cudaMemsetAsync(gq_count, 0, sizeof(int) * (size_t)n_groups, d->stream));
         BBX_LAUNCH(d, k_frontier0_groups, G, 256, 0, *d, gq, gq_count, wpb, gcap);
         bbx_timing_mark(d, 4);
-        BBX_LAUNCH(d, k_solve_groups, n_groups, GRP_THREADS, 0, *d, sp, gq, gq_count, gcap);
+        // small groups keep their body state, visiting order and body slots in shared memory (see k_solve_groups)
+        int pair_cap = 0, smem_bodies = 0;
+        size_t dyn_bytes = 0;
+        {
+            const size_t nbl = (size_t)wpb * (size_t)(d->cap_s + d->cap_b), nboxl = (size_t)wpb * (size_t)d->cap_b;
+            if (iterations > 1 && wpb <= d->grp_smem_wpb && nbl < 65535) {
+                pair_cap = gcap < 1536 * wpb ? gcap : 1536 * wpb;        // (a group with more constraints continues on the global-memory replay)
+                if (d->grp_pair_cap > 0 && d->grp_pair_cap < pair_cap) pair_cap = d->grp_pair_cap;   // BBX_GRP_PAIR_CAP (tests): forces that hand-over
+                pair_cap &= ~3;                                          // keeps what follows 16-byte aligned
+                dyn_bytes = 2 * (size_t)pair_cap * sizeof(int) + (2 * nbl + 2 * nboxl + 4 * GRP_THREADS) * sizeof(float4);
+                if (dyn_bytes <= 65536 && pair_cap > 0) smem_bodies = 1; else { pair_cap = 0; dyn_bytes = 0; }
+            }
+        }
+        if (d->trace_level < 0) sp.gather = d->trace_level;         // BBX_TRACE_LEVEL=-1: per-block phase stamps in level_ns (tools/profile_batch.py)
+        BBX_LAUNCH(d, k_solve_groups, n_groups, GRP_THREADS, dyn_bytes, *d, sp, gq, gq_count, gcap, wpb, pair_cap, smem_bodies);
         BBX_CUDA(d, cudaGetLastError());
         return 0;
     }

@@ -560,6 +560,44 @@ def test_world_block_solver_path(product, truth):
     d.DestroyPhysicsWorldBatch(batch)
 
 
+@pytest.mark.parametrize("env", [{"BBX_GRP_SMEM": "0"}, {"BBX_GRP_SMEM": "1"}, {"BBX_GRP_SMEM": "1", "BBX_GRP_PAIR_CAP": "256"},
+                                 {"BBX_GRP_SMEM": "2", "BBX_GRP_WPB": "2"}, {"BBX_GRP_SMEM": "0", "BBX_GRP_WPB": "3"}])
+def test_group_solver_forms_agree_with_the_reference(product, truth, env, monkeypatch):
+    """k_solve_groups has two forms: body state in the packed global array (any group), and -- for small groups -- body
+    state, visiting order and body slots in shared memory (BBX_GRP_SMEM = largest group in worlds, read when the batch's
+    device state is created).  BBX_GRP_PAIR_CAP forces the hand-over from the second to the first after iteration 0 (a group
+    with more constraints than its shared-memory tables hold), BBX_GRP_WPB groups of several worlds on a batch that would
+    not need them.  Ragged batch of 37 worlds (the last group of the 2- and 3-worlds-per-group runs is short), 70 steps, sampled worlds compared bit for bit with the same world stepped alone by
+    the reference, all worlds by hash across the forms."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    d = product.dll
+    n_worlds = 37
+    s, b, c = product.scene_capacity(bb.SCENE_RLWORLD, 0)
+    batch = d.CreatePhysicsWorldBatch(n_worlds, s, b, c)
+    views = [bb.World(product, d.BatchWorld(batch, i), owned=False) for i in range(n_worlds)]
+    for i, v in enumerate(views):
+        d.BbxSceneBuild(v.ptr, bb.SCENE_RLWORLD, 0, 5100 + i)
+    assert d.PhysicsStepBatch(batch, DT, 45) == 0, d.BatchGetLastError(batch)
+    assert d.PhysicsStepBatch(batch, DT, 25) == 0, d.BatchGetLastError(batch)
+    assert d.BatchDownload(batch, bb.DL_BODIES | bb.DL_CONSTRAINTS) == 0, d.BatchGetLastError(batch)
+    st = bb.BallboxStats(); d.BatchGetStats(batch, bb.C.byref(st))
+    assert st.overflow == 0 and st.levels > 3
+    for i in (0, 18, 36):
+        w = truth.build_scene(bb.SCENE_RLWORLD, 0, 5100 + i)
+        for _ in range(70):
+            w.step(DT)
+        mm = parity.compare_worlds(views[i], w)
+        assert not mm, f"{env}: world {i}: {mm[:3]}"
+    hashes = tuple(v.state_hash() for v in views)
+    seen = _GROUP_FORM_HASHES.setdefault("h", hashes)
+    assert hashes == seen, f"{env}: world hashes differ from the first form run"
+    d.DestroyPhysicsWorldBatch(batch)
+
+
+_GROUP_FORM_HASHES = {}
+
+
 @pytest.mark.parametrize("kind,n,steps", [(bb.SCENE_MIXED, 3000, 40), (bb.SCENE_SDF, 1500, 40), (bb.SCENE_BALLS, 5000, 30)])
 def test_flow_schedule_is_bit_exact(product, truth, kind, n, steps):
     """BBX_SOLVER_EXACT_FLOW: the barrier-free solver (every constraint waits for its own two predecessors
