@@ -30,6 +30,7 @@
 // chunks pulled through a shared-memory ticket counter (the look-ahead of the staging hands out all tickets at once).
 // Per-body constraint order, operations and rounding are those of k_solve_levels: bit-identical results.
 #include <stdlib.h>
+#include <stdio.h>
 #include <cooperative_groups.h>
 #include "bbx_solve.cuh"
 namespace cg = cooperative_groups;
@@ -44,7 +45,10 @@ namespace cg = cooperative_groups;
 #define RS_WARP_BYTES 7168
 #define RS_TABLE_BYTES (RS_MAXLEV * (4 * BBX_NCLS + 1) * 4)
 // measured cost of one 32-node chunk of class k in 0.1 us (C3, 16 warps per SM): m = 1 (no box), 1 (box), 2, 3, 4, 5-6, 7-8, 9+
-__constant__ int rs_cost[BBX_NCLS] = { 22, 25, 50, 75, 98, 130, 180, 320 };
+// (per-warp trace of fat levels with the branch-free sweep, tools/profile_step.py with BBX_TRACE_LEVEL: (busy - first data
+// wait) / chunks; BBX_RS_COST="c0,...,c7" overrides the table for measurements)
+struct ReplayCost { int c[BBX_NCLS]; };
+static const int rs_cost_default[BBX_NCLS] = { 21, 22, 37, 50, 59, 78, 105, 180 };
 
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp16(unsigned int saddr, const void* g, unsigned long long pol)
@@ -157,8 +161,9 @@ __device__ __forceinline__ void read_body(const BbxDev& dv, const ReplayCtx& cx,
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(BbxDev dv, SolveParams sp)
+__global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_replay_staged(BbxDev dv, SolveParams sp, ReplayCost rc)
 {
+    const int* rs_cost = rc.c;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const int n_levels = dv.ctr->n_levels;
@@ -331,7 +336,15 @@ int bbx_replay_staged(BbxDev* d, const SolveParams& sp_in)
     }
     SolveParams sp = sp_in;
     BbxDev dv = *d;
-    void* args[] = { (void*)&dv, (void*)&sp };
+    static ReplayCost rc;                                            // read once per process
+    static int rc_set = 0;
+    if (!rc_set) {
+        for (int k = 0; k < BBX_NCLS; k++) rc.c[k] = rs_cost_default[k];
+        const char* e = getenv("BBX_RS_COST");
+        if (e) { int v[BBX_NCLS]; if (sscanf(e, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]) == BBX_NCLS) for (int k = 0; k < BBX_NCLS; k++) if (v[k] > 0) rc.c[k] = v[k]; }
+        rc_set = 1;
+    }
+    void* args[] = { (void*)&dv, (void*)&sp, (void*)&rc };
     BBX_CUDA(d, cudaLaunchCooperativeKernel((void*)k_replay_staged, dim3(d->replay_blocks), dim3(RS_THREADS), args, smem, d->stream));
     d->launches++;
     BBX_CUDA(d, cudaGetLastError());

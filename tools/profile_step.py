@@ -78,6 +78,10 @@ elif os.environ.get("BBX_TRACE_LEVEL"):
     widx = np.nonzero(work)[0]
     print("  slowest warps (warp index, class, chunks, constraints, first data wait us, busy us):",
           [(int(widx[o]), int(cls[o]), int(nc[o]), int(m[o]), round(float(wait[o]), 2), round(float(busy[o]), 2)) for o in order])
+    for kk in sorted(set(cls.tolist())):                      # per node class: what a 32-node chunk costs (calibration of rs_cost in bbx_replay.cu)
+        sel = cls == kk
+        per = (busy[sel] - wait[sel]) / np.maximum(nc[sel], 1)
+        print(f"  class {kk}: warps {sel.sum()} chunks/warp {nc[sel].mean():.2f} (busy - first wait) per chunk us: mean {per.mean():.2f} p90 {np.percentile(per, 90):.2f} | busy mean {busy[sel].mean():.2f} max {busy[sel].max():.2f}")
     for mm in sorted(set(m.tolist())):
         sel = m == mm
         print(f"  head node m={mm}: warps {sel.sum()} chunks/warp {nc[sel].mean():.2f} busy mean {busy[sel].mean():.2f} max {busy[sel].max():.2f} end mean {((t[work, 2][sel] - t0) / 1e3).mean():.2f}")
