@@ -782,10 +782,10 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     // shared-memory form: body slot of a gid = gid - s_off (spheres) / gid - b_off (boxes, after the nsl sphere slots)
     const int nsl = wpb * dv.cap_s, nbl = wpb * (dv.cap_s + dv.cap_b);
     const int s_off = g * wpb * dv.cap_s, b_off = dv.NS + g * wpb * dv.cap_b - nsl;
-    int* s_queue = g_pair + pair_cap;
-    float4* s_vel = reinterpret_cast<float4*>(s_queue + pair_cap);
+    int* s_queue = g_pair + pair_cap;                                   // visiting order: read by iteration 0 only, so that
+    float4* s_rec = reinterpret_cast<float4*>(s_queue);                 // the replay's record staging [plane][thread] shares its place
+    float4* s_vel = reinterpret_cast<float4*>(s_queue + max(pair_cap, 16 * GRP_THREADS));
     float4* s_boxq = s_vel + 2 * nbl;
-    float4* s_rec = s_boxq + 2 * (nbl - nsl);                           // [plane][thread]
     const int nwg = min(wpb, dv.n_worlds - g * wpb);                     // worlds of this group (the last group may be ragged)
     const int ns_valid = nwg * dv.cap_s, nb_valid = nwg * dv.cap_b;
     bool in_smem = smem_bodies != 0;                                    // (uniform over the block) the velocities live in s_vel
@@ -1040,6 +1040,7 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
             if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "group solver kernel does not fit on an SM", __FILE__, __LINE__);
             d->grp_blocks = per_sm * d->num_sms;
             BBX_CUDA(d, cudaFuncSetAttribute(k_solve_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            BBX_CUDA(d, cudaFuncSetAttribute(k_solve_groups, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         int wpb = (d->n_worlds + d->grp_blocks - 1) / d->grp_blocks;
         if (wpb < 1) wpb = 1;
@@ -1059,10 +1060,11 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
         {
             const size_t nbl = (size_t)wpb * (size_t)(d->cap_s + d->cap_b), nboxl = (size_t)wpb * (size_t)d->cap_b;
             if (iterations > 1 && wpb <= d->grp_smem_wpb && nbl < 65535) {
-                pair_cap = gcap < 1536 * wpb ? gcap : 1536 * wpb;        // (a group with more constraints continues on the global-memory replay)
+                pair_cap = gcap < 1408 * wpb ? gcap : 1408 * wpb;        // (a group with more constraints continues on the global-memory replay)
                 if (d->grp_pair_cap > 0 && d->grp_pair_cap < pair_cap) pair_cap = d->grp_pair_cap;   // BBX_GRP_PAIR_CAP (tests): forces that hand-over
                 pair_cap &= ~3;                                          // keeps what follows 16-byte aligned
-                dyn_bytes = 2 * (size_t)pair_cap * sizeof(int) + (2 * nbl + 2 * nboxl + 4 * GRP_THREADS) * sizeof(float4);
+                const size_t q_ints = pair_cap > 16 * GRP_THREADS ? (size_t)pair_cap : (size_t)(16 * GRP_THREADS);   // visiting order / record staging
+                dyn_bytes = ((size_t)pair_cap + q_ints) * sizeof(int) + (2 * nbl + 2 * nboxl) * sizeof(float4);
                 if (dyn_bytes <= 65536 && pair_cap > 0) smem_bodies = 1; else { pair_cap = 0; dyn_bytes = 0; }
             }
         }
