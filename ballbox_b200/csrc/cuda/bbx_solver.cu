@@ -1040,7 +1040,6 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
             if (per_sm < 1) return bbx_fail(d, BBX_ERR_NO_DEVICE, "group solver kernel does not fit on an SM", __FILE__, __LINE__);
             d->grp_blocks = per_sm * d->num_sms;
             BBX_CUDA(d, cudaFuncSetAttribute(k_solve_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-            BBX_CUDA(d, cudaFuncSetAttribute(k_solve_groups, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         int wpb = (d->n_worlds + d->grp_blocks - 1) / d->grp_blocks;
         if (wpb < 1) wpb = 1;
@@ -1066,6 +1065,16 @@ int bbx_stage_solve_ex(BbxDev* d, const BbxStepParams* p, int presolve_mode, int
                 const size_t q_ints = pair_cap > 16 * GRP_THREADS ? (size_t)pair_cap : (size_t)(16 * GRP_THREADS);   // visiting order / record staging
                 dyn_bytes = ((size_t)pair_cap + q_ints) * sizeof(int) + (2 * nbl + 2 * nboxl) * sizeof(float4);
                 if (dyn_bytes <= 65536 && pair_cap > 0) smem_bodies = 1; else { pair_cap = 0; dyn_bytes = 0; }
+            }
+        }
+        {   // the shared-memory form wants the SM's whole carve-out (4 blocks x ~55 KB); the global-memory form wants L1 (measured:
+            // 1024 worlds in the global form 0.79 ms with the default carve-out, 0.85 ms with the maximum)
+            static int carveout_set[64];                             // per device: 0 unknown, 1 default, 2 maximum
+            const int want = smem_bodies ? 2 : 1, dev = d->device & 63;
+            if (carveout_set[dev] != want) {
+                BBX_CUDA(d, cudaFuncSetAttribute(k_solve_groups, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 smem_bodies ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault));
+                carveout_set[dev] = want;
             }
         }
         if (d->trace_level < 0) sp.gather = d->trace_level;         // BBX_TRACE_LEVEL=-1: per-block phase stamps in level_ns (tools/profile_batch.py)

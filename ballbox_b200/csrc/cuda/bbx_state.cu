@@ -128,7 +128,7 @@ extern "C" int bbx_dev_create(BbxDev** out, int device, int n_worlds, int cap_s,
     { const char* e = getenv("BBX_FIND_PAIRS"); d->find_pairs_mode = e ? (e[0] == '0' ? 0 : 1) : -1; }
     { const char* e = getenv("BBX_GRP_WPB"); d->grp_force_wpb = e ? atoi(e) : 0; }
     { const char* e = getenv("BBX_GRP_PAIR_CAP"); d->grp_pair_cap = e ? atoi(e) : 0; }
-    { const char* e = getenv("BBX_GRP_SMEM"); d->grp_smem_wpb = e ? atoi(e) : 1; }
+    { const char* e = getenv("BBX_GRP_SMEM"); d->grp_smem_wpb = e ? atoi(e) : 2; }
     { const char* e = getenv("BBX_SOLVER_FLOW"); d->force_flow = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("BBX_REPLAY"); d->replay_mode = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1); }   // 1 (default): staged replay kernel unless the schedule is thin; 2: always; 0: never
     { const char* e = getenv("BBX_SOLVE_BLOCKS"); d->tune_solve_blocks = e ? atoi(e) : 0; }
