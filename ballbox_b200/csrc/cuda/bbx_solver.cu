@@ -675,12 +675,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_BLOCKS_PER_SM) k_solve_le
 //
 // A 256-body world offers ~20 independent constraints per dependency level: a warp per world keeps a
 // third of its lanes busy (and sweeps a manifold of m contacts in m dependent rounds).  Here a block of
-// 256 threads owns a group of worlds (as many as it takes to run the whole batch in one wave) and sweeps
+// 128 threads owns a group of worlds (as many as it takes to run the whole batch in one wave) and sweeps
 // level l of all of them together: every constraint is its own node (chains per constraint, as in the flow
-// solver), so the lanes of a warp do equal work, levels are separated by __syncthreads() and body
-// velocities stay in the packed global array (L2), which a block-wide barrier keeps coherent.
+// solver), so the lanes of a warp do equal work and levels are separated by __syncthreads().
 // Iteration 0 discovers the group's levels (Kahn) and writes descriptors and records in visiting order;
 // iterations 1..I-1 stream them.  Same per-body constraint order as everywhere else: bit-identical results.
+// Two forms (chosen per launch by the host): body velocities in the packed global array (L2), which a
+// block-wide barrier keeps coherent (any group), or -- groups of one or two worlds -- in shared memory
+// (see the comment at the kernel).
 // ---------------------------------------------------------------------------
 #define GRP_THREADS 128
 #ifndef GRP_FLAT
