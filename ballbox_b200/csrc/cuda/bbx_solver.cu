@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
                                                                                  int wpb, int pair_cap, int smem_bodies)
 {
     __shared__ int level_start[GRP_LMAX + 2];
-    __shared__ int s_next;
+    __shared__ int s_next[3];                                         // pushes of level l are counted in s_next[l % 3] (see the Kahn loop)
     extern __shared__ __align__(16) int g_pair[];                     // shared-memory form: [pair_cap] body slots, [pair_cap] visiting order, bodies, record staging
     #define GRP_STAMP(i) do { if (sp.gather < 0 && tid == 0 && g < 256) { unsigned long long ns_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_)); dv.level_ns[g * 8 + (i)] = ns_; } } while (0)
     const int g = blockIdx.x, tid = threadIdx.x;
@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     const size_t base = (size_t)g * gcap;                             // the group's slice of M / Nd / slot numbers
     int4* gd = dv.Nd_k[0] + base;                                     // descriptors in visiting order: (gid A, gid B, contact, -)
     const size_t PL = (size_t)dv.cap_contacts;
-    if (tid == 0) { s_next = 0; level_start[0] = 0; }
+    if (tid == 0) { s_next[0] = s_next[1] = s_next[2] = 0; level_start[0] = 0; }
     GRP_STAMP(0);
     const bool big = dv.ctr->n_contacts > BBX_L2_STREAM_CONTACTS;     // bodies stay in L2, records stream
     const unsigned long long pol_keep = big ? l2_policy_keep() : l2_policy_normal(), pol_stream = big ? l2_policy_stream() : l2_policy_normal();
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
     }
     __syncthreads();
     // ---- iteration 0: Kahn levels ----
-    int head = 0, tail = n0, lvl = 0;
+    int head = 0, tail = n0, lvl = 0, par = 0;
     bool bad = false;
     while (head < tail) {
         for (int p = head + vt; p < tail; p += GRP_THREADS) {
@@ -835,16 +835,20 @@ __global__ void __launch_bounds__(GRP_THREADS, GRP_BLOCKS_PER_SM) k_solve_groups
             st128_cg_pol(M, c0, pol_stream); st128_cg_pol(M + PL, c1, pol_stream); st128_cg_pol(M + 2 * PL, c2, pol_stream); st128_cg_pol(M + 3 * PL, c3, pol_stream);
             __stcg(&gd[p], make_int4(gA, gB, c, 0));
             dv.slot_of[c] = (int)(base + p);
-            if (sa >= 0 && atomicSub(&dv.indeg[sa], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) { __stcg(&queue[q], sa); if (in_smem && q < pair_cap) s_queue[q] = sa; } }
-            if (sb >= 0 && atomicSub(&dv.indeg[sb], 1) == 1) { int q = tail + atomicAdd(&s_next, 1); if (q < glim) { __stcg(&queue[q], sb); if (in_smem && q < pair_cap) s_queue[q] = sb; } }
+            // both in-degree atomics are in flight before either result is used (one L2 round trip instead of two)
+            const int ra = sa >= 0 ? atomicSub(&dv.indeg[sa], 1) : 0;
+            const int rb = sb >= 0 ? atomicSub(&dv.indeg[sb], 1) : 0;
+            if (ra == 1) { int q = tail + atomicAdd(&s_next[par], 1); if (q < glim) { __stcg(&queue[q], sa); if (in_smem && q < pair_cap) s_queue[q] = sa; } }
+            if (rb == 1) { int q = tail + atomicAdd(&s_next[par], 1); if (q < glim) { __stcg(&queue[q], sb); if (in_smem && q < pair_cap) s_queue[q] = sb; } }
         }
+        // ONE barrier per level: the counter of level l + 2 (= that of level l - 1, which every thread has read before it
+        // arrived here) is cleared after this barrier and first used after the next one
         __syncthreads();
-        const int pushed = s_next;
-        __syncthreads();
+        const int pushed = s_next[par];
         head = tail; tail += pushed; lvl++;
         if (tail > glim || lvl > GRP_LMAX) { bad = true; break; }
-        if (tid == 0) { s_next = 0; level_start[lvl] = head; }
-        __syncthreads();
+        if (tid == 0) { s_next[par == 0 ? 2 : par - 1] = 0; level_start[lvl] = head; }
+        par = par == 2 ? 0 : par + 1;
     }
     if (bad) { if (tid == 0) atomicOr(&dv.ctr->overflow, 32); return; }
     const int n_levels = lvl;
